@@ -1,0 +1,185 @@
+// See bvh_build.h.  Compiled with -ffp-contract=off: every expression below must round exactly like the
+// reference's x86-64 build (no FMA), because these values feed bit-exact device comparisons.
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+namespace dgb {
+namespace {
+
+struct P3 { double x, y, z; };
+inline P3 operator-(P3 a, P3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline P3 operator+(P3 a, P3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline double dot3(P3 a, P3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }          // Vec3r::dot, left to right
+inline double len(P3 a) { return std::sqrt(dot3(a, a)); }
+inline P3 unit(P3 a) { const double l = len(a); return {a.x / l, a.y / l, a.z / l}; }  // Vec3r::normalized
+inline P3 crs(P3 a, P3 b) { return {a.y * b.z - a.z * b.y, -a.x * b.z + a.z * b.x, a.x * b.y - a.y * b.x}; }
+inline double at(const P3& p, int d) { return d == 0 ? p.x : (d == 1 ? p.y : p.z); }
+
+struct Builder {
+    const P3* V;
+    const uint32_t* F;
+    HostBvh& out;
+    std::vector<int32_t>& order;           // current arrangement of triangle ids (the reference sorts structs in place)
+    struct Key { double k; int32_t id; };
+    std::vector<Key> keys;                 // scratch for the sort (same comparisons => same permutation as the reference)
+
+    inline P3 vert(int32_t tri, int k) const { return V[F[3 * (size_t)tri + k]]; }
+
+    // bounding sphere of the node covering [b, e) in the CURRENT arrangement (TriangleMeshDistance.h:451-491)
+    void build(int b, int e, double sc[3], double& sr, int depth)
+    {
+        out.max_depth = std::max(out.max_depth, depth);
+        const int n = e - b;
+        if (n == 1) {
+            const P3 a = vert(order[b], 0), bb = vert(order[b], 1), c = vert(order[b], 2);
+            const P3 s = (a + bb) + c;
+            const P3 ctr = {s.x / 3.0, s.y / 3.0, s.z / 3.0};
+            sr = std::max(std::max(len(a - ctr), len(bb - ctr)), len(c - ctr));
+            sc[0] = ctr.x; sc[1] = ctr.y; sc[2] = ctr.z;
+            return;
+        }
+        double top[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, bot[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
+        P3 ctr = {0, 0, 0};
+        for (int i = b; i < e; i++)
+            for (int k = 0; k < 3; k++) {
+                const P3 p = vert(order[i], k);
+                ctr = ctr + p;                               // sequential, arrangement order matters for rounding
+                top[0] = std::max(top[0], p.x); top[1] = std::max(top[1], p.y); top[2] = std::max(top[2], p.z);
+                bot[0] = std::min(bot[0], p.x); bot[1] = std::min(bot[1], p.y); bot[2] = std::min(bot[2], p.z);
+            }
+        const double cnt = (double)(3 * n);
+        ctr = {ctr.x / cnt, ctr.y / cnt, ctr.z / cnt};
+        const double diag[3] = {top[0] - bot[0], top[1] - bot[1], top[2] - bot[2]};
+        int split = 0;                                       // std::max_element: first maximum
+        if (diag[1] > diag[split]) split = 1;
+        if (diag[2] > diag[split]) split = 2;
+        double r2 = 0.0;
+        for (int i = b; i < e; i++)
+            for (int k = 0; k < 3; k++) { const P3 d = ctr - vert(order[i], k); r2 = std::max(r2, dot3(d, d)); }
+        sc[0] = ctr.x; sc[1] = ctr.y; sc[2] = ctr.z; sr = std::sqrt(r2);
+
+        // unstable std::sort on the first vertex's coordinate (TriangleMeshDistance.h:494-499)
+        for (int i = b; i < e; i++) keys[i] = {at(vert(order[i], 0), split), order[i]};
+        std::sort(keys.begin() + b, keys.begin() + e, [](const Key& x, const Key& y) { return x.k < y.k; });
+        for (int i = b; i < e; i++) order[i] = keys[i].id;
+
+        const int m = (b + e) >> 1;
+        SpherePair& sp = out.spheres[m];
+        build(b, m, sp.lc, sp.lr, depth + 1);
+        build(m, e, sp.rc, sp.rr, depth + 1);
+    }
+};
+
+}  // namespace
+
+bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err)
+{
+    if (!Vd || !F || nT == 0 || nV == 0) { *err = "empty triangle list or vertex list"; return false; }
+    if (nT > (uint64_t)0x3fffffff || nV > (uint64_t)0x7fffffff) { *err = "mesh too large (int32 indices as in the reference)"; return false; }
+    for (uint64_t i = 0; i < 3 * nT; i++) if (F[i] >= nV) { *err = "triangle index out of range"; return false; }
+    const P3* V = reinterpret_cast<const P3*>(Vd);
+    const int T = (int)nT;
+    out = HostBvh();
+    out.n_vertices = nV; out.n_triangles = nT;
+    out.V.assign(Vd, Vd + 3 * nV);
+    out.F.assign(F, F + 3 * nT);
+    out.spheres.assign(nT, SpherePair());
+    out.order.resize(nT);
+    for (int i = 0; i < T; i++) out.order[i] = i;
+
+    Builder bld{V, F, out, out.order, {}};
+    bld.keys.resize(nT);
+    double root_c[3], root_r;
+    bld.build(0, T, root_c, root_r, 1);      // root sphere is computed and unused, as in the reference (:125,357)
+
+    // ---- pseudonormals (TriangleMeshDistance.h:359-420), in the reference's arrays first
+    out.pn_tri.assign(3 * nT, 0.0); out.pn_edge.assign(9 * nT, 0.0); out.pn_vert.assign(3 * nV, 0.0);
+    P3* pt = reinterpret_cast<P3*>(out.pn_tri.data());
+    P3* pe = reinterpret_cast<P3*>(out.pn_edge.data());
+    P3* pv = reinterpret_cast<P3*>(out.pn_vert.data());
+    struct EdgeAcc { P3 n; int count; };
+    std::unordered_map<uint64_t, EdgeAcc> edges;
+    edges.reserve(2 * nT);
+    auto key_of = [nV](uint32_t i, uint32_t j) { return (uint64_t)std::min(i, j) * nV + (uint64_t)std::max(i, j); };
+    auto add_edge = [&](uint32_t i, uint32_t j, P3 n) {
+        auto it = edges.find(key_of(i, j));
+        if (it == edges.end()) edges.emplace(key_of(i, j), EdgeAcc{n, 1});
+        else { it->second.n = it->second.n + n; it->second.count++; }
+    };
+    for (int i = 0; i < T; i++) {
+        const uint32_t* t = F + 3 * (size_t)i;
+        const P3 a = V[t[0]], b = V[t[1]], c = V[t[2]];
+        const P3 n = unit(crs(b - a, c - a));
+        pt[i] = n;
+        const double al0 = std::acos(std::abs(dot3(unit(b - a), unit(c - a))));
+        const double al1 = std::acos(std::abs(dot3(unit(a - b), unit(c - b))));
+        const double al2 = std::acos(std::abs(dot3(unit(b - c), unit(a - c))));
+        pv[t[0]] = pv[t[0]] + P3{al0 * n.x, al0 * n.y, al0 * n.z};
+        pv[t[1]] = pv[t[1]] + P3{al1 * n.x, al1 * n.y, al1 * n.z};
+        pv[t[2]] = pv[t[2]] + P3{al2 * n.x, al2 * n.y, al2 * n.z};
+        add_edge(t[0], t[1], n); add_edge(t[1], t[2], n); add_edge(t[0], t[2], n);
+    }
+    for (uint64_t i = 0; i < nV; i++) pv[i] = unit(pv[i]);           // Vec3r::normalize: same divisions
+    for (int i = 0; i < T; i++) {
+        const uint32_t* t = F + 3 * (size_t)i;
+        pe[3 * i + 0] = unit(edges.find(key_of(t[0], t[1]))->second.n);
+        pe[3 * i + 1] = unit(edges.find(key_of(t[1], t[2]))->second.n);
+        pe[3 * i + 2] = unit(edges.find(key_of(t[0], t[2]))->second.n);
+    }
+    out.flags = 0;
+    for (const auto& kv : edges) { if (kv.second.count == 1) out.flags |= 1; else if (kv.second.count > 2) out.flags |= 2; }
+
+    // ---- device records in leaf order
+    out.leaves.assign(nT, LeafRecord());
+    out.normals.assign(nT, PseudoNormals());
+    for (int pos = 0; pos < T; pos++) {
+        const int id = out.order[pos];
+        const uint32_t* t = F + 3 * (size_t)id;
+        const P3 v0 = V[t[0]], v1 = V[t[1]], v2 = V[t[2]];
+        const P3 e0 = v1 - v0, e1 = v2 - v0;                            // TriangleMeshDistance.h:567-568
+        LeafRecord& L = out.leaves[pos];
+        L.v0[0] = v0.x; L.v0[1] = v0.y; L.v0[2] = v0.z;
+        L.e0[0] = e0.x; L.e0[1] = e0.y; L.e0[2] = e0.z;
+        L.e1[0] = e1.x; L.e1[1] = e1.y; L.e1[2] = e1.z;
+        L.a00 = dot3(e0, e0); L.a01 = dot3(e0, e1); L.a11 = dot3(e1, e1);  // :569-571
+        L.det = std::abs(L.a00 * L.a11 - L.a01 * L.a01);                   // :575
+        L.inv_det = 1 / L.det;                                            // :675
+        L.denom = L.a00 - 2 * L.a01 + L.a11;                              // :693,740,792
+        L.tri_id = id; L._pad = 0;
+        PseudoNormals& N = out.normals[pos];
+        const P3 src[7] = {pv[t[0]], pv[t[1]], pv[t[2]], pe[3 * id + 0], pe[3 * id + 1], pe[3 * id + 2], pt[id]};
+        for (int k = 0; k < 7; k++) { N.n[k][0] = src[k].x; N.n[k][1] = src[k].y; N.n[k][2] = src[k].z; }
+    }
+    return true;
+}
+
+namespace {
+int export_rec(const HostBvh& bvh, int b, int e, int& next, double* spheres, int32_t* kids)
+{
+    const int id = next++;
+    if (e - b == 1) {
+        if (kids) { kids[2 * id] = -1; kids[2 * id + 1] = bvh.order[b]; }
+        if (spheres) std::memset(spheres + 8 * (size_t)id, 0, 8 * sizeof(double));   // reference leaves hold default spheres
+        return id;
+    }
+    const int m = (b + e) >> 1;
+    if (spheres) std::memcpy(spheres + 8 * (size_t)id, &bvh.spheres[m], 8 * sizeof(double));
+    const int l = export_rec(bvh, b, m, next, spheres, kids);
+    const int r = export_rec(bvh, m, e, next, spheres, kids);
+    if (kids) { kids[2 * id] = l; kids[2 * id + 1] = r; }
+    return id;
+}
+}  // namespace
+
+void export_reference_tree(const HostBvh& bvh, double* spheres, int32_t* kids)
+{
+    int next = 0;
+    export_rec(bvh, 0, (int)bvh.n_triangles, next, spheres, kids);
+}
+
+}  // namespace dgb

@@ -1,0 +1,64 @@
+// Host-side construction of the mesh-distance acceleration data, laid out for the sm_100a traversal kernel.
+//
+// What is built is *numerically* the reference's structure (TriangleMeshDistance.h:336-512: median-split
+// bounding-sphere tree ordered by std::sort on the first vertex, angle-weighted pseudonormals) because the
+// query result -- including which of several equidistant triangles wins and therefore the sign -- depends
+// on the traversal order (TriangleMeshDistance.h:528, 542-560).  The *layout* is new:
+//
+//   * no node array and no child pointers.  After construction the triangles sit in "leaf order"
+//     (position 0..T-1).  A tree node is the half-open range [b, e) of leaf positions it covers; its
+//     children are [b, m) and [m, e) with m = (b + e) >> 1 (== (int)(0.5*(b+e)), TriangleMeshDistance.h:502).
+//     Every internal node has a distinct m in [1, T-1], so the pair of child spheres is stored at
+//     spheres[m] -- one 64-byte, 64-byte-aligned record = two 32-byte sectors.
+//   * one 128-byte record per triangle (leaf order) with every point-independent quantity of
+//     point_triangle_sq_unsigned precomputed with the reference's exact operation order:
+//     v0, e0 = v1-v0, e1 = v2-v0, a00, a01, a11, det = |a00*a11 - a01*a01|, 1/det, a00 - 2*a01 + a11, id.
+//   * one 7x3 block of pseudonormals per triangle (leaf order), indexed directly by NearestEntity
+//     (V0,V1,V2,E01,E12,E02,F), so the sign needs a single 24-byte gather.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace dgb {
+
+struct alignas(64) SpherePair {   // children of the internal node whose split position is the array index
+    double lc[3], lr;             // left child sphere  (TriangleMeshDistance.h:105)
+    double rc[3], rr;             // right child sphere (TriangleMeshDistance.h:106)
+};
+static_assert(sizeof(SpherePair) == 64, "SpherePair must be 64 bytes");
+
+struct alignas(128) LeafRecord {
+    double v0[3];
+    double e0[3];
+    double e1[3];
+    double a00, a01, a11;
+    double det, inv_det, denom;   // |a00*a11-a01*a01|, 1/det, (a00 - 2*a01) + a11
+    int32_t tri_id;               // original triangle index (Result::triangle_id)
+    int32_t _pad;
+};
+static_assert(sizeof(LeafRecord) == 128, "LeafRecord must be 128 bytes");
+
+struct PseudoNormals { double n[7][3]; };   // V0 V1 V2 E01 E12 E02 F
+static_assert(sizeof(PseudoNormals) == 168, "PseudoNormals must be 168 bytes");
+
+struct HostBvh {
+    uint64_t n_vertices = 0, n_triangles = 0;
+    std::vector<SpherePair> spheres;        // [T]  (index 0 unused)
+    std::vector<LeafRecord> leaves;         // [T]
+    std::vector<PseudoNormals> normals;     // [T]
+    std::vector<int32_t> order;             // leaf position -> triangle id
+    int max_depth = 0;                      // number of levels (root = 1)
+    int flags = 0;                          // bit0: edge with a single triangle; bit1: edge with > 2 triangles
+    // reference-numbered copies for dg_mesh_tree / dg_mesh_pseudonormals (diagnostics, built on demand)
+    std::vector<double> V;                  // nV x 3
+    std::vector<uint32_t> F;                // nT x 3
+    std::vector<double> pn_tri, pn_edge, pn_vert;
+};
+
+// Returns false (and leaves *err) on invalid input.
+bool build_host_bvh(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err);
+
+// Re-expresses the implicit tree in the reference's explicit pre-order numbering (diagnostics only).
+void export_reference_tree(const HostBvh& bvh, double* spheres /*(2T-1) x 8*/, int32_t* kids /*(2T-1) x 2*/);
+
+}  // namespace dgb

@@ -1,0 +1,614 @@
+// C-ABI of libdiscregrid_b200.so (include/discregrid_b200.h): handles, error reporting, host<->device plumbing.
+// All numerics live in the kernels (k1_sdf.cu, k2_interp.cu, k3_density.cu) and in bvh_build.cpp.
+#include "../../include/discregrid_b200.h"
+
+#include <atomic>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "bvh_build.h"
+#include "dg_device.cuh"
+#include "k1_sdf.h"
+#include "k2_interp.h"
+#include "k3_density.h"
+
+using namespace dgb;
+
+// ------------------------------------------------------------------------------------------------ state
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define DG_CUDA(call)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            const int code_ = (e_ == cudaErrorMemoryAllocation) ? DG_ERR_NOMEM                           \
+                              : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? DG_ERR_NO_DEVICE \
+                                                                                                : DG_ERR_CUDA; \
+            return fail(code_, "%s failed: %s", #call, cudaGetErrorString(e_));                         \
+        }                                                                                                \
+    } while (0)
+
+#define DG_LAUNCH(call)          \
+    do {                         \
+        DG_CUDA(call);           \
+        g_launches.fetch_add(1); \
+    } while (0)
+
+int require_device()
+{
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(DG_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return DG_OK;
+}
+
+// simple owning device buffer
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        return cudaMalloc(reinterpret_cast<void**>(&p), (count ? count : 1) * sizeof(T));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+bool grid_to_dev(const dg_grid_desc* d, GridDev& g, const char** why)
+{
+    if (!d) { *why = "grid descriptor is NULL"; return false; }
+    for (int k = 0; k < 3; k++) {
+        if (d->resolution[k] == 0) { *why = "resolution must be >= 1 in every dimension"; return false; }
+        g.mn[k] = d->domain_min[k]; g.mx[k] = d->domain_max[k];
+        g.cell[k] = d->cell_size[k]; g.inv[k] = d->inv_cell_size[k];
+        g.n[k] = d->resolution[k];
+    }
+    uint64_t nn = 0;
+    if (dg_grid_num_nodes(d->resolution, &nn) != DG_OK) { *why = "grid too large: node ids must fit uint32 (reference file format)"; return false; }
+    const unsigned nx = g.n[0], ny = g.n[1], nz = g.n[2];
+    g.nv = (nx + 1) * (ny + 1) * (nz + 1);
+    g.ne_x = nx * (ny + 1) * (nz + 1);
+    g.ne_y = (nx + 1) * ny * (nz + 1);
+    g.ne_z = (nx + 1) * (ny + 1) * nz;
+    return true;
+}
+
+std::atomic<int> g_selftest_state{0};   // 0 = not run, 1 = ok, -1 = failed
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ handles
+struct dg_mesh {
+    HostBvh host;
+    DevBuf<SpherePair> d_spheres;
+    DevBuf<LeafRecord> d_leaves;
+    DevBuf<PseudoNormals> d_normals;
+    DeviceBvh dev;
+    int device = 0;
+    uint64_t build_us = 0, upload_us = 0;
+};
+
+struct dg_field {
+    dg_grid_desc desc;
+    FieldDev dev;
+    DevBuf<double> d_packed;
+    DevBuf<unsigned> d_cell_map;
+    DevBuf<double2> d_tab;
+    uint64_t n_nodes = 0, n_cells_kept = 0;
+    int device = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ library
+extern "C" {
+
+int dg_abi_version(void) { return DG_ABI_VERSION; }
+const char* dg_last_error(void) { return g_err.c_str(); }
+uint64_t dg_kernel_launch_count(void) { return g_launches.load(); }
+void dg_kernel_launch_count_reset(void) { g_launches.store(0); }
+
+int dg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int dg_selftest(void)
+{
+    if (int rc = require_device()) return rc;
+    // a*b + c where the unfused result (two roundings) differs from the fused one:
+    // a = b = 1 + 2^-27  ->  a*b = 1 + 2^-26 + 2^-54 (rounds to 1 + 2^-26); c = -(1 + 2^-26).
+    const double a = 1.0 + std::ldexp(1.0, -27), c = -(1.0 + std::ldexp(1.0, -26));
+    DevBuf<double> out;
+    DG_CUDA(out.alloc(1));
+    DG_LAUNCH(k1_launch_fma_probe(a, a, c, out.p, nullptr));
+    double r = -1.0;
+    DG_CUDA(cudaMemcpy(&r, out.p, sizeof r, cudaMemcpyDeviceToHost));
+    if (r != 0.0) {
+        g_selftest_state = -1;
+        return fail(DG_ERR_SELFTEST, "device code was compiled with FMA contraction (a*b+c probe returned %.17g, expected 0): "
+                    "build with -fmad=false", r);
+    }
+    g_selftest_state = 1;
+    return DG_OK;
+}
+
+static int ensure_selftest()
+{
+    const int s = g_selftest_state.load();
+    if (s == 1) return DG_OK;
+    if (s == -1) return fail(DG_ERR_SELFTEST, "device self-test failed earlier (FMA contraction on)");
+    return dg_selftest();
+}
+
+// ------------------------------------------------------------------------------------------------ grid helpers
+int dg_grid_init(const double mn[3], const double mx[3], const uint32_t res[3], dg_grid_desc* out)
+{
+    if (!mn || !mx || !res || !out) return fail(DG_ERR_INVALID, "dg_grid_init: NULL argument");
+    uint64_t nn;
+    if (int rc = dg_grid_num_nodes(res, &nn)) return rc;
+    std::memset(out, 0, sizeof *out);
+    for (int d = 0; d < 3; d++) {
+        out->domain_min[d] = mn[d]; out->domain_max[d] = mx[d]; out->resolution[d] = res[d];
+        out->cell_size[d] = (mx[d] - mn[d]) / (double)res[d];      // diagonal().cwiseQuotient(n.cast<double>())
+        out->inv_cell_size[d] = 1.0 / out->cell_size[d];           // cwiseInverse()
+    }
+    return DG_OK;
+}
+
+int dg_grid_num_nodes(const uint32_t res[3], uint64_t* n_nodes)
+{
+    if (!res || !n_nodes) return fail(DG_ERR_INVALID, "dg_grid_num_nodes: NULL argument");
+    if (res[0] == 0 || res[1] == 0 || res[2] == 0) return fail(DG_ERR_INVALID, "resolution must be >= 1 in every dimension");
+    const uint64_t nx = res[0], ny = res[1], nz = res[2];
+    const uint64_t nv = (nx + 1) * (ny + 1) * (nz + 1);
+    const uint64_t ne = nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz;
+    const uint64_t total = nv + 2 * ne;
+    // the reference indexes nodes with `int l` (cubic_lagrange_discrete_grid.cpp:809) and stores uint32 ids
+    if (nx > 65535 || ny > 65535 || nz > 65535 || total > 0x7fffffffull || nx * ny * nz > 0x7fffffffull)
+        return fail(DG_ERR_INVALID, "grid too large: %llu nodes exceed the reference's int/uint32 node ids", (unsigned long long)total);
+    *n_nodes = total;
+    return DG_OK;
+}
+
+int dg_generate_sdf_domain(const double* V, uint64_t nV, double mn[3], double mx[3])
+{
+    if (!V || !mn || !mx || nV == 0) return fail(DG_ERR_INVALID, "dg_generate_sdf_domain: NULL / empty argument");
+    for (int d = 0; d < 3; d++) { mn[d] = DBL_MAX; mx[d] = -DBL_MAX; }     // AlignedBox::setEmpty + extend
+    for (uint64_t i = 0; i < nV; i++)
+        for (int d = 0; d < 3; d++) { mn[d] = std::fmin(mn[d], V[3 * i + d]); mx[d] = std::fmax(mx[d], V[3 * i + d]); }
+    // cmd/generate_sdf/main.cpp:89-90: max is padded first, then min with the grown diagonal.  Eigen >= 3.3 reduces a
+    // Vector3d as (a0 + a1) + a2.
+    for (int pass = 0; pass < 2; pass++) {
+        const double dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+        const double nrm = std::sqrt((dx * dx + dy * dy) + dz * dz);
+        const double pad = 1.0e-3 * nrm * 1.0;
+        for (int d = 0; d < 3; d++) { if (pass == 0) mx[d] += pad; else mn[d] -= pad; }
+    }
+    return DG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ mesh
+int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT, dg_mesh** out)
+{
+    if (!out) return fail(DG_ERR_INVALID, "dg_mesh_create: out is NULL");
+    *out = nullptr;
+    if (!V || !F || nT == 0 || nV == 0) return fail(DG_ERR_INVALID, "dg_mesh_create: empty triangle list");   // ref: exit(-1)
+    if (int rc = require_device()) return rc;
+    if (int rc = ensure_selftest()) return rc;
+    dg_mesh* m = new (std::nothrow) dg_mesh();
+    if (!m) return fail(DG_ERR_NOMEM, "dg_mesh_create: out of host memory");
+    const auto t0 = std::chrono::steady_clock::now();
+    const char* why = "";
+    try {
+        if (!build_host_bvh(V, nV, F, nT, m->host, &why)) { delete m; return fail(DG_ERR_INVALID, "dg_mesh_create: %s", why); }
+    } catch (const std::bad_alloc&) { delete m; return fail(DG_ERR_NOMEM, "dg_mesh_create: out of host memory"); }
+    const auto t1 = std::chrono::steady_clock::now();
+    m->build_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+
+    auto cleanup = [&](int rc) { delete m; return rc; };
+#define DG_CUDA_M(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cleanup(fail(e_ == cudaErrorMemoryAllocation ? DG_ERR_NOMEM : DG_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
+    DG_CUDA_M(cudaGetDevice(&m->device));
+    DG_CUDA_M(m->d_spheres.alloc(nT));
+    DG_CUDA_M(m->d_leaves.alloc(nT));
+    DG_CUDA_M(m->d_normals.alloc(nT));
+    DG_CUDA_M(cudaMemcpy(m->d_spheres.p, m->host.spheres.data(), nT * sizeof(SpherePair), cudaMemcpyHostToDevice));
+    DG_CUDA_M(cudaMemcpy(m->d_leaves.p, m->host.leaves.data(), nT * sizeof(LeafRecord), cudaMemcpyHostToDevice));
+    DG_CUDA_M(cudaMemcpy(m->d_normals.p, m->host.normals.data(), nT * sizeof(PseudoNormals), cudaMemcpyHostToDevice));
+    m->dev.spheres = m->d_spheres.p; m->dev.leaves = m->d_leaves.p; m->dev.normals = m->d_normals.p;
+    m->dev.n_tri = (int)nT;
+    m->dev.stack_depth = m->host.max_depth > 1 ? m->host.max_depth - 1 : 1;
+    DG_CUDA_M(k1_configure(m->dev.stack_depth));
+#undef DG_CUDA_M
+    const auto t2 = std::chrono::steady_clock::now();
+    m->upload_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
+    // the device records are the product; the host copies of the big arrays are no longer needed
+    std::vector<SpherePair>().swap(m->host.spheres);   // keep `order`, V, F, pseudonormals for diagnostics
+    std::vector<LeafRecord>().swap(m->host.leaves);
+    std::vector<PseudoNormals>().swap(m->host.normals);
+    *out = m;
+    return DG_OK;
+}
+
+int dg_mesh_destroy(dg_mesh* m)
+{
+    if (!m) return DG_OK;
+    delete m;
+    return DG_OK;
+}
+
+int dg_mesh_info(const dg_mesh* m, uint64_t info[8])
+{
+    if (!m || !info) return fail(DG_ERR_INVALID, "dg_mesh_info: NULL argument");
+    info[0] = m->host.n_vertices; info[1] = m->host.n_triangles; info[2] = (uint64_t)m->dev.stack_depth;
+    info[3] = (uint64_t)m->host.flags;
+    info[4] = m->d_spheres.bytes() + m->d_leaves.bytes() + m->d_normals.bytes();
+    info[5] = m->build_us; info[6] = m->upload_us; info[7] = 0;
+    return DG_OK;
+}
+
+int dg_mesh_tree(const dg_mesh* m, double* spheres, int32_t* kids)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_mesh_tree: mesh is NULL");
+    // the sphere pairs were released after upload: read them back from the device
+    HostBvh tmp;
+    tmp.n_triangles = m->host.n_triangles;
+    tmp.order = m->host.order;
+    tmp.spheres.resize(m->host.n_triangles);
+    DG_CUDA(cudaMemcpy(tmp.spheres.data(), m->d_spheres.p, m->host.n_triangles * sizeof(SpherePair), cudaMemcpyDeviceToHost));
+    export_reference_tree(tmp, spheres, kids);
+    return DG_OK;
+}
+
+int dg_mesh_pseudonormals(const dg_mesh* m, double* tri, double* edge, double* vert)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_mesh_pseudonormals: mesh is NULL");
+    if (tri) std::memcpy(tri, m->host.pn_tri.data(), m->host.pn_tri.size() * sizeof(double));
+    if (edge) std::memcpy(edge, m->host.pn_edge.data(), m->host.pn_edge.size() * sizeof(double));
+    if (vert) std::memcpy(vert, m->host.pn_vert.data(), m->host.pn_vert.size() * sizeof(double));
+    return DG_OK;
+}
+
+int dg_mesh_distance_device(const dg_mesh* m, const double* d_pts, uint64_t n, int is_signed, double* d_dist, double* d_near,
+                            int32_t* d_ent, int32_t* d_tri, void* stream)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_mesh_distance: mesh is NULL (not constructed)");
+    if (n && !d_pts) return fail(DG_ERR_INVALID, "dg_mesh_distance: points is NULL");
+    DG_LAUNCH(k1_launch_distance(m->dev, d_pts, n, is_signed, d_dist, d_near, d_ent, d_tri, (cudaStream_t)stream));
+    return DG_OK;
+}
+
+int dg_mesh_distance(const dg_mesh* m, const double* pts, uint64_t n, int is_signed, double* dist, double* nearp, int32_t* ent,
+                     int32_t* tri)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_mesh_distance: mesh is NULL (not constructed)");
+    if (n == 0) return DG_OK;
+    if (!pts) return fail(DG_ERR_INVALID, "dg_mesh_distance: points is NULL");
+    DevBuf<double> d_pts, d_dist, d_near;
+    DevBuf<int> d_ent, d_tri;
+    DG_CUDA(d_pts.alloc(3 * n));
+    DG_CUDA(cudaMemcpy(d_pts.p, pts, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    if (dist) DG_CUDA(d_dist.alloc(n));
+    if (nearp) DG_CUDA(d_near.alloc(3 * n));
+    if (ent) DG_CUDA(d_ent.alloc(n));
+    if (tri) DG_CUDA(d_tri.alloc(n));
+    if (int rc = dg_mesh_distance_device(m, d_pts.p, n, is_signed, d_dist.p, d_near.p, d_ent.p, d_tri.p, nullptr)) return rc;
+    if (dist) DG_CUDA(cudaMemcpy(dist, d_dist.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (nearp) DG_CUDA(cudaMemcpy(nearp, d_near.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (ent) DG_CUDA(cudaMemcpy(ent, d_ent.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (tri) DG_CUDA(cudaMemcpy(tri, d_tri.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    DG_CUDA(cudaDeviceSynchronize());
+    return DG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+static int check_range(const dg_grid_desc* grid, uint64_t b, uint64_t e, GridDev& g, const char* who)
+{
+    const char* why = "";
+    if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "%s: %s", who, why);
+    uint64_t nn = 0;
+    if (int rc = dg_grid_num_nodes(grid->resolution, &nn)) return rc;
+    if (b > e || e > nn) return fail(DG_ERR_INVALID, "%s: node range [%llu, %llu) outside [0, %llu]", who, (unsigned long long)b,
+                                      (unsigned long long)e, (unsigned long long)nn);
+    return DG_OK;
+}
+
+int dg_sample_sdf_device(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* d_out,
+                         void* stream)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf: mesh is NULL (not constructed)");
+    GridDev g;
+    if (int rc = check_range(grid, l_begin, l_end, g, "dg_sample_sdf")) return rc;
+    if (l_end > l_begin && !d_out) return fail(DG_ERR_INVALID, "dg_sample_sdf: output is NULL");
+    DG_LAUNCH(k1_launch_sample_nodes(m->dev, g, sign, l_begin, l_end - l_begin, d_out, (cudaStream_t)stream));
+    return DG_OK;
+}
+
+int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* out_host)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf: mesh is NULL (not constructed)");
+    GridDev g;
+    if (int rc = check_range(grid, l_begin, l_end, g, "dg_sample_sdf")) return rc;
+    const uint64_t n = l_end - l_begin;
+    if (n == 0) return DG_OK;
+    if (!out_host) return fail(DG_ERR_INVALID, "dg_sample_sdf: output is NULL");
+    DevBuf<double> d_out;
+    DG_CUDA(d_out.alloc(n));
+    // chunked so that the D2H copy of chunk i overlaps the kernel of chunk i+1
+    cudaStream_t s_k, s_c;
+    DG_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+    DG_CUDA(cudaStreamCreateWithFlags(&s_c, cudaStreamNonBlocking));
+    const uint64_t chunk = 1ull << 22;
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> ev(n_chunks);
+    int rc = DG_OK;
+    const bool pinned = cudaHostRegister(out_host, n * sizeof(double), cudaHostRegisterDefault) == cudaSuccess;
+    if (!pinned) cudaGetLastError();
+    for (uint64_t c = 0; c < n_chunks && rc == DG_OK; c++) {
+        const uint64_t b = c * chunk, cnt = (b + chunk <= n) ? chunk : n - b;
+        cudaError_t e = k1_launch_sample_nodes(m->dev, g, sign, l_begin + b, cnt, d_out.p + b, s_k);
+        g_launches.fetch_add(1);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[c], s_k);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_c, ev[c], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_host + b, d_out.p + b, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_c);
+        if (e != cudaSuccess) rc = fail(DG_ERR_CUDA, "dg_sample_sdf: %s", cudaGetErrorString(e));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s_k), e2 = cudaStreamSynchronize(s_c);
+    if (rc == DG_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
+        rc = fail(DG_ERR_CUDA, "dg_sample_sdf: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    for (uint64_t c = 0; c < n_chunks; c++) if (ev[c]) cudaEventDestroy(ev[c]);
+    if (pinned) cudaHostUnregister(out_host);
+    cudaStreamDestroy(s_k); cudaStreamDestroy(s_c);
+    return rc;
+}
+
+int dg_node_positions(const dg_grid_desc* grid, uint64_t l_begin, uint64_t l_end, double* x_host)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = ensure_selftest()) return rc;
+    GridDev g;
+    if (int rc = check_range(grid, l_begin, l_end, g, "dg_node_positions")) return rc;
+    const uint64_t n = l_end - l_begin;
+    if (n == 0) return DG_OK;
+    if (!x_host) return fail(DG_ERR_INVALID, "dg_node_positions: output is NULL");
+    DevBuf<double> d_x;
+    DG_CUDA(d_x.alloc(3 * n));
+    DG_LAUNCH(k1_launch_node_positions(g, l_begin, n, d_x.p, nullptr));
+    DG_CUDA(cudaMemcpy(x_host, d_x.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return DG_OK;
+}
+
+int dg_build_cells(const uint32_t res[3], uint64_t c_begin, uint64_t c_end, uint32_t* cells_host)
+{
+    if (int rc = require_device()) return rc;
+    if (!res) return fail(DG_ERR_INVALID, "dg_build_cells: NULL argument");
+    dg_grid_desc d;
+    const double mn[3] = {0, 0, 0}, mx[3] = {1, 1, 1};
+    if (int rc = dg_grid_init(mn, mx, res, &d)) return rc;
+    GridDev g; const char* why = "";
+    if (!grid_to_dev(&d, g, &why)) return fail(DG_ERR_INVALID, "dg_build_cells: %s", why);
+    const uint64_t nc = (uint64_t)res[0] * res[1] * res[2];
+    if (c_begin > c_end || c_end > nc) return fail(DG_ERR_INVALID, "dg_build_cells: cell range out of bounds");
+    const uint64_t n = c_end - c_begin;
+    if (n == 0) return DG_OK;
+    if (!cells_host) return fail(DG_ERR_INVALID, "dg_build_cells: output is NULL");
+    const uint64_t chunk = 1ull << 22;          // 512 MiB of uint32 per chunk
+    DevBuf<unsigned> d_cells;
+    DG_CUDA(d_cells.alloc(32 * (n < chunk ? n : chunk)));
+    for (uint64_t b = 0; b < n; b += chunk) {
+        const uint64_t cnt = (b + chunk <= n) ? chunk : n - b;
+        DG_LAUNCH(k1_launch_build_cells(g, c_begin + b, cnt, d_cells.p, nullptr));
+        DG_CUDA(cudaMemcpy(cells_host + 32 * b, d_cells.p, 32 * cnt * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    }
+    return DG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fields / K2
+static int field_common(const dg_grid_desc* grid, uint64_t n_nodes, dg_field** out, dg_field*& f)
+{
+    if (!out) return fail(DG_ERR_INVALID, "dg_field_create: out is NULL");
+    *out = nullptr;
+    if (int rc = require_device()) return rc;
+    if (int rc = ensure_selftest()) return rc;
+    GridDev g; const char* why = "";
+    if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_field_create: %s", why);
+    uint64_t nn = 0;
+    if (int rc = dg_grid_num_nodes(grid->resolution, &nn)) return rc;
+    (void)n_nodes;
+    f = new (std::nothrow) dg_field();
+    if (!f) return fail(DG_ERR_NOMEM, "dg_field_create: out of host memory");
+    f->desc = *grid; f->dev.g = g;
+    return DG_OK;
+}
+
+static int field_finish(dg_field* f, const double* d_nodes, const unsigned* d_cells, cudaStream_t stream)
+{
+    cudaError_t e = cudaGetDevice(&f->device);
+    if (e == cudaSuccess) e = f->d_packed.alloc(32 * (f->n_cells_kept ? f->n_cells_kept : 1));
+    if (e == cudaSuccess && f->n_cells_kept == 0) e = cudaMemsetAsync(f->d_packed.p, 0, 32 * sizeof(double), stream);
+    if (e == cudaSuccess) e = f->d_tab.alloc(f->dev.g.n[0] + f->dev.g.n[1] + f->dev.g.n[2]);
+    if (e == cudaSuccess) { e = k2_launch_pack(f->dev.g, d_nodes, d_cells, f->n_cells_kept, f->d_packed.p, stream); g_launches.fetch_add(1); }
+    if (e == cudaSuccess) { e = k2_launch_axis_tables(f->dev.g, f->d_tab.p, stream); g_launches.fetch_add(1); }
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? DG_ERR_NOMEM : DG_ERR_CUDA, "dg_field_create: %s", cudaGetErrorString(e));
+    f->dev.packed = f->d_packed.p;
+    f->dev.cell_map = f->d_cell_map.p;
+    f->dev.tab = f->d_tab.p;
+    return DG_OK;
+}
+
+int dg_field_create(const dg_grid_desc* grid, const double* nodes, uint64_t n_nodes, const uint32_t* cells, uint64_t n_cells_kept,
+                    const uint32_t* cell_map, dg_field** out)
+{
+    dg_field* f = nullptr;
+    if (int rc = field_common(grid, n_nodes, out, f)) return rc;
+    auto bail = [&](int rc) { delete f; return rc; };
+    const uint64_t n_cells = (uint64_t)grid->resolution[0] * grid->resolution[1] * grid->resolution[2];
+    if (!nodes && n_nodes) return bail(fail(DG_ERR_INVALID, "dg_field_create: nodes is NULL"));
+    if (!cells && n_cells_kept != n_cells) return bail(fail(DG_ERR_INVALID, "dg_field_create: cells == NULL requires n_cells_kept == nx*ny*nz"));
+    if (!cells) {
+        uint64_t nn = 0; dg_grid_num_nodes(grid->resolution, &nn);
+        if (n_nodes != nn) return bail(fail(DG_ERR_INVALID, "dg_field_create: closed-form cells need all %llu nodes (got %llu)",
+                                            (unsigned long long)nn, (unsigned long long)n_nodes));
+    } else {
+        for (uint64_t i = 0; i < 32 * n_cells_kept; i++)
+            if (cells[i] >= n_nodes) return bail(fail(DG_ERR_INVALID, "dg_field_create: cell table references node %u >= n_nodes", cells[i]));
+    }
+    if (cell_map)
+        for (uint64_t i = 0; i < n_cells; i++)
+            if (cell_map[i] != UINT32_MAX && cell_map[i] >= n_cells_kept)
+                return bail(fail(DG_ERR_INVALID, "dg_field_create: cell_map entry %u >= n_cells_kept", cell_map[i]));
+    f->n_nodes = n_nodes; f->n_cells_kept = n_cells_kept;
+    DevBuf<double> d_nodes;
+    DevBuf<unsigned> d_cells;
+    cudaError_t e = d_nodes.alloc(n_nodes);
+    if (e == cudaSuccess) e = cudaMemcpy(d_nodes.p, nodes, n_nodes * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && cells) {
+        e = d_cells.alloc(32 * n_cells_kept);
+        if (e == cudaSuccess) e = cudaMemcpy(d_cells.p, cells, 32 * n_cells_kept * sizeof(unsigned), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && cell_map) {
+        e = f->d_cell_map.alloc(n_cells);
+        if (e == cudaSuccess) e = cudaMemcpy(f->d_cell_map.p, cell_map, n_cells * sizeof(unsigned), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) return bail(fail(e == cudaErrorMemoryAllocation ? DG_ERR_NOMEM : DG_ERR_CUDA, "dg_field_create: %s", cudaGetErrorString(e)));
+    if (int rc = field_finish(f, d_nodes.p, cells ? d_cells.p : nullptr, nullptr)) return bail(rc);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return bail(fail(DG_ERR_CUDA, "dg_field_create: %s", cudaGetErrorString(e)));
+    *out = f;
+    return DG_OK;
+}
+
+int dg_field_create_device(const dg_grid_desc* grid, const double* d_nodes, uint64_t n_nodes, void* stream, dg_field** out)
+{
+    dg_field* f = nullptr;
+    if (int rc = field_common(grid, n_nodes, out, f)) return rc;
+    uint64_t nn = 0; dg_grid_num_nodes(grid->resolution, &nn);
+    if (!d_nodes || n_nodes != nn) { delete f; return fail(DG_ERR_INVALID, "dg_field_create_device: need all %llu node coefficients", (unsigned long long)nn); }
+    f->n_nodes = n_nodes;
+    f->n_cells_kept = (uint64_t)grid->resolution[0] * grid->resolution[1] * grid->resolution[2];
+    if (int rc = field_finish(f, d_nodes, nullptr, (cudaStream_t)stream)) { delete f; return rc; }
+    *out = f;
+    return DG_OK;
+}
+
+int dg_field_destroy(dg_field* f)
+{
+    delete f;
+    return DG_OK;
+}
+
+int dg_field_info(const dg_field* f, uint64_t info[4])
+{
+    if (!f || !info) return fail(DG_ERR_INVALID, "dg_field_info: NULL argument");
+    info[0] = f->n_nodes; info[1] = f->n_cells_kept;
+    info[2] = f->d_packed.bytes() + f->d_cell_map.bytes() + f->d_tab.bytes(); info[3] = 0;
+    return DG_OK;
+}
+
+int dg_interpolate_batch_device(const dg_field* f, const double* d_x, uint64_t n, double* d_phi, double* d_grad, void* stream)
+{
+    if (!f) return fail(DG_ERR_INVALID, "dg_interpolate_batch: field is NULL");
+    if (n && (!d_x || !d_phi)) return fail(DG_ERR_INVALID, "dg_interpolate_batch: x / phi is NULL");
+    DG_LAUNCH(k2_launch_interpolate(f->dev, d_x, n, d_phi, d_grad, (cudaStream_t)stream));
+    return DG_OK;
+}
+
+int dg_interpolate_batch(const dg_field* f, const double* x, uint64_t n, double* phi, double* grad)
+{
+    if (!f) return fail(DG_ERR_INVALID, "dg_interpolate_batch: field is NULL");
+    if (n == 0) return DG_OK;
+    if (!x || !phi) return fail(DG_ERR_INVALID, "dg_interpolate_batch: x / phi is NULL");
+    DevBuf<double> d_x, d_phi, d_grad;
+    DG_CUDA(d_x.alloc(3 * n));
+    DG_CUDA(d_phi.alloc(n));
+    if (grad) DG_CUDA(d_grad.alloc(3 * n));
+    DG_CUDA(cudaMemcpy(d_x.p, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    if (int rc = dg_interpolate_batch_device(f, d_x.p, n, d_phi.p, grad ? d_grad.p : nullptr, nullptr)) return rc;
+    DG_CUDA(cudaMemcpy(phi, d_phi.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (grad) DG_CUDA(cudaMemcpy(grad, d_grad.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return DG_OK;
+}
+
+int dg_shape_functions(const double* xi, uint64_t n, double* N, double* dN)
+{
+    if (int rc = require_device()) return rc;
+    if (int rc = ensure_selftest()) return rc;
+    if (n == 0) return DG_OK;
+    if (!xi || !N) return fail(DG_ERR_INVALID, "dg_shape_functions: NULL argument");
+    DevBuf<double> d_xi, d_N, d_dN;
+    DG_CUDA(d_xi.alloc(3 * n));
+    DG_CUDA(d_N.alloc(32 * n));
+    if (dN) DG_CUDA(d_dN.alloc(96 * n));
+    DG_CUDA(cudaMemcpy(d_xi.p, xi, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    DG_LAUNCH(k2_launch_shape_functions(d_xi.p, n, d_N.p, dN ? d_dN.p : nullptr, nullptr));
+    DG_CUDA(cudaMemcpy(N, d_N.p, 32 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dN) DG_CUDA(cudaMemcpy(dN, d_dN.p, 96 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return DG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+int dg_density_map_device(const dg_field* f, double h, double rho0, int no_reduction, uint64_t l_begin, uint64_t l_end, double* d_out,
+                          void* stream)
+{
+    if (!f) return fail(DG_ERR_INVALID, "dg_density_map: field is NULL");
+    GridDev g;
+    if (int rc = check_range(&f->desc, l_begin, l_end, g, "dg_density_map")) return rc;
+    if (!(h > 0.0)) return fail(DG_ERR_INVALID, "dg_density_map: smoothing length must be > 0");
+    if (l_end > l_begin && !d_out) return fail(DG_ERR_INVALID, "dg_density_map: output is NULL");
+    DG_LAUNCH(k3_launch_density(f->dev, h, rho0, no_reduction, l_begin, l_end - l_begin, d_out, (cudaStream_t)stream));
+    return DG_OK;
+}
+
+int dg_density_map(const dg_field* f, double h, double rho0, int no_reduction, uint64_t l_begin, uint64_t l_end, double* out_host)
+{
+    if (!f) return fail(DG_ERR_INVALID, "dg_density_map: field is NULL");
+    if (l_end < l_begin) return fail(DG_ERR_INVALID, "dg_density_map: bad range");
+    const uint64_t n = l_end - l_begin;
+    if (n && !out_host) return fail(DG_ERR_INVALID, "dg_density_map: output is NULL");
+    DevBuf<double> d_out;
+    DG_CUDA(d_out.alloc(n));
+    if (int rc = dg_density_map_device(f, h, rho0, no_reduction, l_begin, l_end, d_out.p, nullptr)) return rc;
+    if (n) DG_CUDA(cudaMemcpy(out_host, d_out.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return DG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+// Launch interface of the K1 kernels (k1_sdf.cu).  Host-callable, no kernel code here.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "bvh_build.h"
+#include "dg_device.cuh"
+
+namespace dgb {
+
+constexpr int K1_THREADS = 128;
+
+struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once by dg_mesh_create
+    const SpherePair* spheres = nullptr;
+    const LeafRecord* leaves = nullptr;
+    const PseudoNormals* normals = nullptr;
+    int n_tri = 0;
+    int stack_depth = 1;           // deferred-sibling slots per lane (= tree levels - 1, at least 1)
+};
+
+cudaError_t k1_configure(int stack_depth);
+cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double sign, uint64_t l_begin, uint64_t count,
+                                   double* d_out, cudaStream_t stream);
+cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t count, int is_signed, double* d_dist,
+                               double* d_near, int* d_ent, int* d_tri, cudaStream_t stream);
+cudaError_t k1_launch_node_positions(const GridDev& g, uint64_t l_begin, uint64_t count, double* d_x, cudaStream_t stream);
+cudaError_t k1_launch_build_cells(const GridDev& g, uint64_t c_begin, uint64_t count, unsigned* d_cells, cudaStream_t stream);
+cudaError_t k1_launch_fma_probe(double a, double b, double c, double* d_out, cudaStream_t stream);
+
+}  // namespace dgb
