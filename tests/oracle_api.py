@@ -140,7 +140,9 @@ class Oracle:
         nodes = _f64(nodes)
         cells = None if cells is None else _u32(cells)
         cell_map = None if cell_map is None else _u32(cell_map)
-        phi = np.empty(len(x)); g = np.empty((len(x), 3)) if grad else None
+        # the reference returns before touching *gradient for out-of-domain / removed cells (:981-982, :993-994): the
+        # caller's value survives.  The batch API defines that value as 0, so the oracle's buffer starts zeroed.
+        phi = np.empty(len(x)); g = np.zeros((len(x), 3)) if grad else None
         self.lib.orc_interpolate(_p(gd, _dp), _p(res, _u32p), _p(nodes, _dp), _p(cells, _u32p), _p(cell_map, _u32p),
                                  _p(x, _dp), C.c_uint64(len(x)), _p(phi, _dp), _p(g, _dp), C.c_int(nthreads))
         return phi, g
