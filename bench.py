@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Discregrid hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): SDF grid nodes/s of CubicLagrangeDiscreteGrid::addFunction with the GenerateSDF functor,
+on configs[1] "Stanford-bunny-class mesh (~70k triangles), 128^3 grid, fp64" -- synthetic closed mesh of that size
+(BASELINE.json north_star: "synthetic meshes/grids of the named shape"; /root/reference does not exist on the GPU box).
+A "step" = one full pass of the node loop over the 14,926,977 nodes.  N > 1: the node range is dealt in chunks to the
+ranks (strong scaling), followed by the all-gather of the coefficient array (discregrid_b200/distributed.py).
+The JSON line also carries the second half of the metric, interpolate()+gradient Mqueries/s (config 4: 10 M uniform
+random queries on a 256^3 SDF), under "interpolate".
+
+--impl reference: the reference's own CPU path (oracle/_ref = its unmodified TriangleMeshDistance.h compiled here, else
+the oracle port) on the host cores, same workload, each step a bounded sample of the node loop.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = {"mesh": "synthetic bumpy torus, 186x187 quads = 69,564 triangles / 34,782 vertices (bunny-class: bunny.obj has 69,630)",
+            "resolution": [128, 128, 128], "torus": (186, 187, 1.0, 0.4, 0.05, 7, 5)}
+INTERP = {"resolution": [256, 256, 256], "queries": 10_000_000, "seed": 0x5EED}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--resolution", type=int, default=0, help="override the SDF grid resolution (diagnostics)")
+    ap.add_argument("--interp-resolution", type=int, default=0, help="override the interpolate grid resolution (diagnostics)")
+    ap.add_argument("--no-interp", action="store_true", help="skip the interpolate half (diagnostics / profiling)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (diagnostics / profiling)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (diagnostics / profiling)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def splitmix_points(n, seed, lo, hi):
+    """u = (splitmix64(seed, counter = 3q + d) >> 11) * 2^-53, x_d = lo_d + u * (hi_d - lo_d)."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) + (np.arange(3 * n, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+    return lo + u.reshape(n, 3) * (hi - lo)
+
+
+def host_cpu_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return model, os.cpu_count()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample_rate(mesh, mn, mx, res, seconds, steps=1, warmup=0):
+    """Times the reference's CPU path on a strided sample of the node loop.  Returns (nodes/s list per step, info)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_api import Oracle, RefMesh, have_ref
+    orc = Oracle()
+    gd, r = orc.grid_desc(mn, mx, res)
+    n_nodes = orc.num_nodes(r)
+    threads = orc.max_threads()
+    kind = "reference" if have_ref() else "port"
+    m = RefMesh(mesh.vertices, mesh.faces) if kind == "reference" else orc.mesh(mesh.vertices, mesh.faces)
+
+    def run(ids):
+        # node positions by the oracle's indexToNodePosition (untimed), then the node-loop body on all host threads
+        x = _positions(orc, gd, r, ids)
+        t0 = time.perf_counter()
+        if kind == "reference":
+            m.sample_points(x)
+        else:
+            m.distance(x)
+        return time.perf_counter() - t0
+
+    # calibrate on 20k strided nodes, then size the sample for ~`seconds`
+    probe = np.linspace(0, n_nodes - 1, 20_000).astype(np.int64)
+    dt = run(probe)
+    n_sample = int(min(n_nodes, max(20_000, seconds / max(dt, 1e-6) * len(probe))))
+    ids = np.linspace(0, n_nodes - 1, n_sample).astype(np.int64)
+    rates = []
+    for it in range(warmup + steps):
+        dt = run(ids)
+        if it >= warmup:
+            rates.append(n_sample / dt)
+    model, ncpu = host_cpu_info()
+    info = {"kind": kind, "cores": threads, "cpu_model": model, "logical_cpus": ncpu,
+            "sample": f"{n_sample} of {n_nodes} nodes, evenly strided over the node index space, OpenMP schedule(static), "
+                      f"{'reference TriangleMeshDistance.h (oracle/_ref)' if kind == 'reference' else 'oracle port'}"}
+    return rates, info
+
+
+def _positions(orc, gd, r, ids):
+    """positions of arbitrary node ids via the oracle's indexToNodePosition on the covering ranges (cheap)."""
+    lo, hi = int(ids.min()), int(ids.max()) + 1
+    if hi - lo <= 4 * len(ids) or hi - lo <= 20_000_000:
+        return np.ascontiguousarray(orc.node_positions(gd, r, lo, hi)[ids - lo])
+    return np.concatenate([orc.node_positions(gd, r, int(l), int(l) + 1) for l in ids])
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    res = [args.resolution] * 3 if args.resolution else WORKLOAD["resolution"]
+
+    import discregrid_b200 as dg           # fails loudly if the CUDA library is not built
+    from discregrid_b200 import _capi as capi
+    from discregrid_b200.distributed import make_sharding, allgather_rows
+
+    mesh = dg.bumpy_torus(*WORKLOAD["torus"])
+    mn, mx = dg.generate_sdf_domain(mesh.vertices)
+    desc = dg.grid_desc(mn, mx, res)
+    n_nodes = C.c_uint64()
+    capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(n_nodes)))
+    n_nodes = n_nodes.value
+    config = {"workload": f"GenerateSDF addFunction: {WORKLOAD['mesh']}; {res[0]}x{res[1]}x{res[2]} grid = {n_nodes} nodes; "
+                          "GenerateSDF-padded domain; fp64 bit-exact with the reference",
+              "mesh_triangles": int(mesh.nFaces()), "grid": res, "nodes": n_nodes,
+              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"node-chunks x{world}"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rates, info = cpu_sample_rate(mesh, mn, mx, res, args.cpu_seconds / 2, steps=args.steps, warmup=min(args.warmup, 1))
+        v = float(np.mean(rates))
+        n_sample = int(info["sample"].split()[0])
+        line = {"impl": "reference", "metric": "SDF grid nodes/sec (addFunction)", "value": v, "unit": "nodes/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_sample / v, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": dict(info, value=v, unit="nodes/s"),
+                "e2e": {"value": v, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    capi.check(capi.lib.dg_set_device(local_rank))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    md = dg.TriangleMeshDistance(mesh)
+    mesh_info = md.info()
+    sh = make_sharding(n_nodes, world)
+    full = torch.empty(sh.padded, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    my_chunks = [(j, b, e) for (j, b, e) in sh.chunks_of(rank)]
+    stream = torch.cuda.current_stream()
+
+    def sdf_step():
+        sp = C.c_void_p(stream.cuda_stream)
+        for (_j, b, e) in my_chunks:
+            if e > b:
+                capi.check(capi.lib.dg_sample_sdf_device(md.handle, C.byref(desc), 1.0, b, e, C.c_void_p(full.data_ptr() + 8 * b), sp))
+        allgather_rows(full, sh)
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        times = []
+        barrier()
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush.fill_(1)                                  # L2 flush, outside the event pair
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step_fn(); e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        barrier()
+        wall = time.perf_counter() - wall0
+        return [max_over_ranks(t) for t in times], wall
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = dg.kernel_launch_count()
+    sdf_ms, sdf_wall = timed(sdf_step, args.steps, args.warmup)
+    launches = (dg.kernel_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = float(np.mean(sdf_ms))
+    value = n_nodes / (ms_step * 1e-3)
+
+    # kernel-only time of K1 on this rank (no collective): what the roofline object refers to
+    def k1_only():
+        sp = C.c_void_p(stream.cuda_stream)
+        for (_j, b, e) in my_chunks:
+            if e > b:
+                capi.check(capi.lib.dg_sample_sdf_device(md.handle, C.byref(desc), 1.0, b, e, C.c_void_p(full.data_ptr() + 8 * b), sp))
+    k1_ms, _ = timed(k1_only, max(3, args.steps // 2), 1)
+    k1_ms = float(np.mean(k1_ms))
+    my_nodes = sum(e - b for (_j, b, e) in my_chunks)
+    n_launch = sum(1 for (_j, b, e) in my_chunks if e > b)
+    peaks, peak_src = measured_peaks()
+    k1_alg_bytes = 8.0 * my_nodes + mesh_info["device_bytes"]          # 8 B/node written + mesh records read once
+    k1_gbs = k1_alg_bytes / (k1_ms * 1e-3) / 1e9
+    roofline = {"kernel": "sdf_sample_nodes_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": k1_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": k1_alg_bytes / max(1, n_launch), "launches_per_step": n_launch,
+                "avg_launch_ms": k1_ms / max(1, n_launch),
+                "note": "K1 is NOT HBM-bound: BVH + triangle records are L2-resident and compulsory HBM traffic is 8 B/node "
+                        "(SURVEY 8d); it is bound by divergent fp64 ALU work and L1/L2 latency -- grade it on nodes/s"}
+
+    # ---------------------------------------------------------------- e2e: C-ABI with HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        outs = [np.empty(max(0, e - b)) for (_j, b, e) in my_chunks]
+
+        def e2e_step():
+            for (_j, b, e), o in zip(my_chunks, outs):
+                if e > b:
+                    capi.check(capi.lib.dg_sample_sdf(md.handle, C.byref(desc), 1.0, b, e, capi.ptr(o, capi.F64P)))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, args.steps // 2)
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) / n_e2e)
+        e2e = {"value": n_nodes / dt, "unit": "nodes/s", "h2d_bytes_per_step": C.sizeof(capi.GridDesc) * n_launch,
+               "d2h_bytes_per_step": 8 * n_nodes, "ms_per_step": dt * 1e3,
+               "api": "dg_sample_sdf(mesh, grid, sign, l_begin, l_end, out_host): kernel + D2H of the coefficient array into a "
+                      "pageable host buffer; the mesh/BVH was uploaded once by dg_mesh_create (as TriangleMeshDistance is built "
+                      "once, outside addFunction's timer, in the reference)",
+               "mesh_upload": {"host_build_ms": mesh_info["build_us"] / 1e3, "h2d_ms": mesh_info["upload_us"] / 1e3,
+                               "h2d_bytes": mesh_info["device_bytes"]}}
+
+    # ---------------------------------------------------------------- interpolate half of the metric (config 4)
+    interp = None
+    if not args.no_interp:
+        ires = [args.interp_resolution] * 3 if args.interp_resolution else INTERP["resolution"]
+        idesc = dg.grid_desc(mn, mx, ires)
+        nn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(idesc.resolution, C.byref(nn))); nn = nn.value
+        coeffs = torch.empty(nn, dtype=torch.float64, device=dev)
+        sp = C.c_void_p(stream.cuda_stream)
+        t0 = time.perf_counter()
+        capi.check(capi.lib.dg_sample_sdf_device(md.handle, C.byref(idesc), 1.0, 0, nn, C.c_void_p(coeffs.data_ptr()), sp))
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+        fh = C.c_void_p()
+        capi.check(capi.lib.dg_field_create_device(C.byref(idesc), C.c_void_p(coeffs.data_ptr()), nn, sp, C.byref(fh)))
+        torch.cuda.synchronize()
+        del coeffs
+        nq = INTERP["queries"]
+        q_lo = (nq * rank) // world; q_hi = (nq * (rank + 1)) // world
+        xh = splitmix_points(nq, INTERP["seed"], mn, mx)[q_lo:q_hi]
+        xh_t = torch.from_numpy(np.ascontiguousarray(xh)).pin_memory()
+        xd = xh_t.to(dev)
+        phi = torch.empty(q_hi - q_lo, dtype=torch.float64, device=dev)
+        grad = torch.empty((q_hi - q_lo, 3), dtype=torch.float64, device=dev)
+
+        def interp_step(with_grad=True):
+            capi.check(capi.lib.dg_interpolate_batch_device(fh, C.c_void_p(xd.data_ptr()), q_hi - q_lo, C.c_void_p(phi.data_ptr()),
+                                                            C.c_void_p(grad.data_ptr()) if with_grad else None, sp))
+        ig_ms, _ = timed(lambda: interp_step(True), 20, 3)
+        iv_ms, _ = timed(lambda: interp_step(False), 20, 3)
+        ig_ms, iv_ms = float(np.mean(ig_ms)), float(np.mean(iv_ms))
+        alg = 312.0 * (q_hi - q_lo)
+        gbs = alg / (ig_ms * 1e-3) / 1e9
+        # e2e through the host API
+        xq = np.ascontiguousarray(xh); ph = np.empty(len(xq)); gh = np.empty((len(xq), 3))
+        for _ in range(2):
+            capi.check(capi.lib.dg_interpolate_batch(fh, capi.ptr(xq, capi.F64P), len(xq), capi.ptr(ph, capi.F64P), capi.ptr(gh, capi.F64P)))
+        barrier(); t0 = time.perf_counter()
+        for _ in range(5):
+            capi.check(capi.lib.dg_interpolate_batch(fh, capi.ptr(xq, capi.F64P), len(xq), capi.ptr(ph, capi.F64P), capi.ptr(gh, capi.F64P)))
+        dt = max_over_ranks((time.perf_counter() - t0) / 5)
+        interp = {"metric": "interpolate()+gradient Mqueries/s", "value": nq / (ig_ms * 1e-3) / 1e6, "unit": "Mqueries/s",
+                  "value_only_mqps": nq / (iv_ms * 1e-3) / 1e6, "ms_per_launch": ig_ms, "queries": nq,
+                  "config": {"workload": f"10M splitmix64 uniform queries (seed 0x5EED) on the {ires[0]}^3 SDF of the same mesh "
+                                         f"({nn} nodes; packed cell blocks {16 * ires[0] * ires[1] * ires[2] * 16 / 1e9:.2f} GB >> L2)",
+                             "field_build_s": build_s},
+                  "roofline": {"kernel": "interpolate_kernel<true> (K2)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                               "algorithmic_bytes_per_query": 312},
+                  "e2e": {"value": nq / dt / 1e6, "unit": "Mqueries/s", "h2d_bytes_per_step": 24 * nq, "d2h_bytes_per_step": 32 * nq,
+                          "api": "dg_interpolate_batch(field, x_host, n, phi_host, grad_host)"}}
+        capi.lib.dg_field_destroy(fh)
+
+    # ---------------------------------------------------------------- CPU baseline, rank 0, N = 1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rates, info = cpu_sample_rate(mesh, mn, mx, res, args.cpu_seconds)
+        cpu = dict(info, value=float(np.mean(rates)), unit="nodes/s")
+
+    if rank == 0:
+        line = {"metric": "SDF grid nodes/sec (addFunction)", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp,
+                "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

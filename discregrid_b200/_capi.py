@@ -42,6 +42,7 @@ SIGNATURES = {
     "dg_abi_version": (C.c_int, []),
     "dg_last_error": (C.c_char_p, []),
     "dg_device_count": (C.c_int, []),
+    "dg_set_device": (C.c_int, [C.c_int]),
     "dg_selftest": (C.c_int, []),
     "dg_kernel_launch_count": (C.c_uint64, []),
     "dg_kernel_launch_count_reset": (None, []),

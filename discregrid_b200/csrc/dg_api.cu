@@ -151,6 +151,13 @@ int dg_device_count(void)
     return n;
 }
 
+int dg_set_device(int device)
+{
+    if (int rc = require_device()) return rc;
+    DG_CUDA(cudaSetDevice(device));
+    return DG_OK;
+}
+
 int dg_selftest(void)
 {
     if (int rc = require_device()) return rc;

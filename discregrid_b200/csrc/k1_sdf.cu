@@ -117,10 +117,15 @@ __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec, 
     return d2;
 }
 
-// _query (TriangleMeshDistance.h:514-562), iterative.  stack_rng/stack_d point at this lane's column of the
-// block's shared-memory stack; consecutive depths are `stride` elements apart.
+// _query (TriangleMeshDistance.h:514-562), iterative and WARP-SYNCHRONOUS: all 32 lanes of the warp call this
+// together (`alive` = lane has a query).  Every lane walks its own reference order with its own stack, but the warp
+// executes one phase at a time, chosen by ballot: an "internal" phase (two sphere tests, push / descend / prune) for
+// the lanes sitting at an internal node, or a "leaf" phase (point-triangle test, accept, pop) for the lanes sitting at
+// a leaf.  The phase with more (cost-weighted) lanes runs; the others idle for that iteration.  This keeps the
+// expensive straight-line blocks converged instead of letting 32 private loops drift apart.
+// stack_rng/stack_d point at this lane's column of the block's shared-memory stack ([depth][lane], conflict-free).
 __device__ __forceinline__ QueryResult nearest_triangle(const SpherePair* __restrict__ spheres,
-                                                        const LeafRecord* __restrict__ leaves, int n_tri,
+                                                        const LeafRecord* __restrict__ leaves, int n_tri, bool alive,
                                                         double px, double py, double pz,
                                                         uint2* stack_rng, double* stack_d, int stride)
 {
@@ -129,53 +134,60 @@ __device__ __forceinline__ QueryResult nearest_triangle(const SpherePair* __rest
     double best = DBL_MAX;             // result.distance
     double best_sq = best * best;      // result.distance * result.distance (= +inf initially), :528
     int b = 0, e = n_tri, sp = 0;
-    for (;;) {
-        bool descend;
-        if (e - b == 1) {                                                   // leaf (:517-534)
-            double s, t; int ent;
-            const double d2 = tri_dist2(leaves + b, px, py, pz, s, t, ent);
-            if (d2 < best_sq) {
-                best = sqrt(d2);
-                best_sq = best * best;
-                res.s = s; res.t = t; res.pos = b; res.entity = ent;
-            }
-            descend = false;
-        } else {                                                            // internal (:537-561)
-            const int m = (b + e) >> 1;
-            const double* sp8 = reinterpret_cast<const double*>(spheres + m);
-            const double2 a0 = ldg2(sp8), a1 = ldg2(sp8 + 2), a2 = ldg2(sp8 + 4), a3 = ldg2(sp8 + 6);
-            const double lx = px - a0.x, ly = py - a0.y, lz = pz - a1.x;
-            const double rx = px - a2.x, ry = py - a2.y, rz = pz - a3.x;
-            const double d_left = sqrt(lx * lx + ly * ly + lz * lz) - a1.y;     // :539
-            const double d_right = sqrt(rx * rx + ry * ry + rz * rz) - a3.y;    // :540
-            const bool left_first = d_left < d_right;                           // :542
-            const double d_first = left_first ? d_left : d_right;
-            const double d_second = left_first ? d_right : d_left;
-            const int fb = left_first ? b : m, fe = left_first ? m : e;
-            const int sb = left_first ? m : b, se = left_first ? e : m;
-            if (d_first < best) {                      // visit first now; second is re-tested when popped (:545-551)
-                stack_rng[sp * stride] = make_uint2((unsigned)sb, (unsigned)se);
-                stack_d[sp * stride] = d_second;
-                sp++;
-                b = fb; e = fe; descend = true;
-            } else if (d_second < best) {              // only reachable through NaNs; kept for fidelity
-                b = sb; e = se; descend = true;
-            } else {
-                descend = false;
+    // pops deferred siblings until one passes the reference's second test `d < result.distance` (:549, :557)
+    auto pop = [&]() {
+        for (;;) {
+            if (sp == 0) { alive = false; return; }
+            sp--;
+            if (stack_d[sp * stride] < best) {
+                const uint2 r = stack_rng[sp * stride];
+                b = (int)r.x; e = (int)r.y;
+                return;
             }
         }
-        if (!descend) {
-            bool found = false;
-            while (sp > 0) {
-                sp--;
-                const double d = stack_d[sp * stride];
-                if (d < best) {                        // the reference's second `if`, with the updated best
-                    const uint2 r = stack_rng[sp * stride];
-                    b = (int)r.x; e = (int)r.y; found = true;
-                    break;
+    };
+    for (;;) {
+        const bool at_leaf = alive && (e - b == 1);
+        const bool at_node = alive && (e - b > 1);
+        const unsigned m_leaf = __ballot_sync(0xffffffffu, at_leaf);
+        const unsigned m_node = __ballot_sync(0xffffffffu, at_node);
+        if ((m_leaf | m_node) == 0u) break;
+        if (K1_NODE_WEIGHT * __popc(m_node) >= K1_LEAF_WEIGHT * __popc(m_leaf)) {
+            if (at_node) {                                                      // internal (:537-561)
+                const int m = (b + e) >> 1;
+                const double* sp8 = reinterpret_cast<const double*>(spheres + m);
+                const double2 a0 = ldg2(sp8), a1 = ldg2(sp8 + 2), a2 = ldg2(sp8 + 4), a3 = ldg2(sp8 + 6);
+                const double lx = px - a0.x, ly = py - a0.y, lz = pz - a1.x;
+                const double rx = px - a2.x, ry = py - a2.y, rz = pz - a3.x;
+                const double d_left = sqrt(lx * lx + ly * ly + lz * lz) - a1.y;     // :539
+                const double d_right = sqrt(rx * rx + ry * ry + rz * rz) - a3.y;    // :540
+                const bool left_first = d_left < d_right;                           // :542
+                const double d_first = left_first ? d_left : d_right;
+                const double d_second = left_first ? d_right : d_left;
+                const int fb = left_first ? b : m, fe = left_first ? m : e;
+                const int sb = left_first ? m : b, se = left_first ? e : m;
+                if (d_first < best) {                  // visit first now; second is re-tested when popped (:545-551)
+                    stack_rng[sp * stride] = make_uint2((unsigned)sb, (unsigned)se);
+                    stack_d[sp * stride] = d_second;
+                    sp++;
+                    b = fb; e = fe;
+                } else if (d_second < best) {          // only reachable through NaNs; kept for fidelity
+                    b = sb; e = se;
+                } else {
+                    pop();
                 }
             }
-            if (!found) break;
+        } else {
+            if (at_leaf) {                                                      // leaf (:517-534)
+                double s, t; int ent;
+                const double d2 = tri_dist2(leaves + b, px, py, pz, s, t, ent);
+                if (d2 < best_sq) {
+                    best = sqrt(d2);
+                    best_sq = best * best;
+                    res.s = s; res.t = t; res.pos = b; res.entity = ent;
+                }
+                pop();
+            }
         }
     }
     res.dist = best;
@@ -211,24 +223,55 @@ __device__ __forceinline__ void finish_query(const LeafRecord* __restrict__ leav
 
 extern __shared__ __align__(16) unsigned char k1_smem[];
 
-// addFunction node loop: out[l - l_begin] = sign * signed_distance(indexToNodePosition(l)).distance
+// addFunction node loop: out[l - l_begin] = sign * signed_distance(indexToNodePosition(l)).distance.
+// Thread mapping: the node array is four row-major 3-D arrays (vertices, x-, y-, z-edge nodes; K1Segment).  A warp
+// owns a 4 x 4 x 2 brick (fast x mid x slow) of one of them and a 128-thread block four bricks side by side along the
+// fast axis, so the 32 queries of a warp are spatial neighbours: they visit nearly the same tree nodes (L1 hits) and
+// take similar numbers of steps.  Whole slow-planes are covered; nodes outside [l_begin, l_end) are masked.
 __global__ void __launch_bounds__(K1_THREADS)
 sdf_sample_nodes_kernel(const SpherePair* __restrict__ spheres, const LeafRecord* __restrict__ leaves,
-                        const PseudoNormals* __restrict__ normals, int n_tri, int stack_depth, GridDev g, double sign,
-                        unsigned l_begin, unsigned long long count, double* __restrict__ out)
+                        const PseudoNormals* __restrict__ normals, int n_tri, int stack_depth, GridDev g, K1Work w, double sign,
+                        double* __restrict__ out)
 {
     double* stack_d = reinterpret_cast<double*>(k1_smem);
     uint2* stack_rng = reinterpret_cast<uint2*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(double));
-    const unsigned long long idx = (unsigned long long)blockIdx.x * K1_THREADS + threadIdx.x;
-    if (idx >= count) return;
-    const unsigned l = l_begin + (unsigned)idx;
-    double px, py, pz;
-    node_position(g, l, px, py, pz);
-    const QueryResult r = nearest_triangle(spheres, leaves, n_tri, px, py, pz, stack_rng + threadIdx.x,
+    // which segment does this block belong to (<= 4, uniform per block)
+    int sg = 0;
+#pragma unroll
+    for (int k = 1; k < 4; k++) if (k < w.nseg && blockIdx.x >= w.seg[k].block_begin) sg = k;
+    const K1Segment& S = w.seg[sg];
+    unsigned t = blockIdx.x - S.block_begin;
+    const unsigned tf = t % S.tiles_f; t /= S.tiles_f;
+    const unsigned tm = t % S.tiles_m; const unsigned ts = t / S.tiles_m;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned f = tf * 16u + warp * 4u + (lane & 3u);
+    const unsigned m = tm * 4u + ((lane >> 2) & 3u);
+    const unsigned sl = S.s0 + ts * 2u + (lane >> 4);
+    const unsigned l = S.l_base + (sl * S.Dm + m) * S.Df + f;
+    const bool alive = (f < S.Df) && (m < S.Dm) && (sl < S.s1) && (l >= w.l_begin) && (l < w.l_end);
+
+    // indexToNodePosition (cubic_lagrange_discrete_grid.cpp:604-665) from the array coordinates
+    unsigned i, j, k;
+    int axis = S.kind - 1;                  // -1 vertex, 0/1/2 edge axis
+    const unsigned par = f & 1u, fh = f >> 1;
+    if (S.kind == 0) { i = f; j = m; k = sl; }
+    else if (S.kind == 1) { i = fh; j = m; k = sl; }
+    else if (S.kind == 2) { i = sl; k = m; j = fh; }
+    else { j = sl; i = m; k = fh; }
+    double px = g.mn[0] + g.cell[0] * (double)i;
+    double py = g.mn[1] + g.cell[1] * (double)j;
+    double pz = g.mn[2] + g.cell[2] * (double)k;
+    const double fr = (1.0 + (double)par) / 3.0;
+    if (axis == 0) px = px + fr * g.cell[0];
+    else if (axis == 1) py = py + fr * g.cell[1];
+    else if (axis == 2) pz = pz + fr * g.cell[2];
+
+    const QueryResult r = nearest_triangle(spheres, leaves, n_tri, alive, px, py, pz, stack_rng + threadIdx.x,
                                            stack_d + threadIdx.x, K1_THREADS);
+    if (!alive) return;
     double dist, qx, qy, qz; int tri;
     finish_query(leaves, normals, r, px, py, pz, true, dist, qx, qy, qz, tri);
-    out[idx] = (sign == 1.0) ? dist : sign * dist;     // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
+    out[l - w.l_begin] = (sign == 1.0) ? dist : sign * dist;     // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
 }
 
 // batched TriangleMeshDistance::{signed,unsigned}_distance on arbitrary points
@@ -242,10 +285,12 @@ mesh_distance_kernel(const SpherePair* __restrict__ spheres, const LeafRecord* _
     double* stack_d = reinterpret_cast<double*>(k1_smem);
     uint2* stack_rng = reinterpret_cast<uint2*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(double));
     const unsigned long long idx = (unsigned long long)blockIdx.x * K1_THREADS + threadIdx.x;
-    if (idx >= count) return;
-    const double px = pts[3 * idx], py = pts[3 * idx + 1], pz = pts[3 * idx + 2];
-    const QueryResult r = nearest_triangle(spheres, leaves, n_tri, px, py, pz, stack_rng + threadIdx.x,
+    const bool alive = idx < count;
+    const unsigned long long ix = alive ? idx : 0ull;
+    const double px = pts[3 * ix], py = pts[3 * ix + 1], pz = pts[3 * ix + 2];
+    const QueryResult r = nearest_triangle(spheres, leaves, n_tri, alive, px, py, pz, stack_rng + threadIdx.x,
                                            stack_d + threadIdx.x, K1_THREADS);
+    if (!alive) return;
     double dist, qx, qy, qz; int tri;
     finish_query(leaves, normals, r, px, py, pz, is_signed != 0, dist, qx, qy, qz, tri);
     if (dist_out) dist_out[idx] = dist;
@@ -289,13 +334,38 @@ cudaError_t k1_configure(int stack_depth)
     return cudaFuncSetAttribute(mesh_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// Splits [l_begin, l_begin+count) into the (at most four) node arrays it touches and tiles whole slow-planes of each.
 cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double sign, uint64_t l_begin, uint64_t count,
                                    double* d_out, cudaStream_t stream)
 {
     if (count == 0) return cudaSuccess;
-    const unsigned blocks = (unsigned)((count + K1_THREADS - 1) / K1_THREADS);
+    const uint64_t l_end = l_begin + count;
+    const unsigned nx = g.n[0], ny = g.n[1], nz = g.n[2];
+    // {base, Ds, Dm, Df} of the four row-major node arrays (cubic_lagrange_discrete_grid.cpp:618-662)
+    const uint64_t base[5] = {0, g.nv, (uint64_t)g.nv + 2ull * g.ne_x, (uint64_t)g.nv + 2ull * (g.ne_x + (uint64_t)g.ne_y),
+                              (uint64_t)g.nv + 2ull * ((uint64_t)g.ne_x + g.ne_y + g.ne_z)};
+    const unsigned dims[4][3] = {{nz + 1, ny + 1, nx + 1}, {nz + 1, ny + 1, 2 * nx}, {nx + 1, nz + 1, 2 * ny}, {ny + 1, nx + 1, 2 * nz}};
+    K1Work w;
+    w.nseg = 0; w.l_begin = (unsigned)l_begin; w.l_end = (unsigned)l_end;
+    unsigned blocks = 0;
+    for (int k = 0; k < 4; k++) {
+        const uint64_t a = l_begin > base[k] ? l_begin : base[k];
+        const uint64_t b = l_end < base[k + 1] ? l_end : base[k + 1];
+        if (a >= b) continue;
+        K1Segment& S = w.seg[w.nseg++];
+        S.kind = k; S.l_base = (unsigned)base[k];
+        S.Ds = dims[k][0]; S.Dm = dims[k][1]; S.Df = dims[k][2];
+        const uint64_t plane = (uint64_t)S.Dm * S.Df;
+        S.s0 = (unsigned)((a - base[k]) / plane);
+        S.s1 = (unsigned)((b - 1 - base[k]) / plane) + 1;
+        S.tiles_f = (S.Df + 15) / 16; S.tiles_m = (S.Dm + 3) / 4;
+        const unsigned tiles_s = (S.s1 - S.s0 + 1) / 2;
+        S.block_begin = blocks;
+        blocks += S.tiles_f * S.tiles_m * tiles_s;
+    }
+    for (int k = w.nseg; k < 4; k++) { w.seg[k] = w.seg[0]; w.seg[k].block_begin = 0xffffffffu; }
     sdf_sample_nodes_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(
-        m.spheres, m.leaves, m.normals, m.n_tri, m.stack_depth, g, sign, (unsigned)l_begin, (unsigned long long)count, d_out);
+        m.spheres, m.leaves, m.normals, m.n_tri, m.stack_depth, g, w, sign, d_out);
     return cudaGetLastError();
 }
 

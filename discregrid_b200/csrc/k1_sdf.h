@@ -8,6 +8,26 @@
 namespace dgb {
 
 constexpr int K1_THREADS = 128;
+// phase choice of the warp-synchronous traversal: run the internal phase when
+// K1_NODE_WEIGHT * #lanes_at_internal_nodes >= K1_LEAF_WEIGHT * #lanes_at_leaves
+#ifndef K1_NODE_WEIGHT
+#define K1_NODE_WEIGHT 1
+#endif
+#ifndef K1_LEAF_WEIGHT
+#define K1_LEAF_WEIGHT 1
+#endif
+
+// One of the four row-major 3-D node arrays of the grid (vertex nodes, x-/y-/z-edge nodes), restricted to the
+// slow-planes [s0, s1) that a node range touches.  l = l_base + (s*Dm + m)*Df + f.
+struct K1Segment {
+    unsigned l_base, Ds, Dm, Df, s0, s1, tiles_f, tiles_m, block_begin;
+    int kind;                      // 0 vertex (s,m,f)=(k,j,i); 1 x-edge (k,j,2i+b); 2 y-edge (i,k,2j+b); 3 z-edge (j,i,2k+b)
+};
+struct K1Work {
+    K1Segment seg[4];
+    int nseg;
+    unsigned l_begin, l_end;
+};
 
 struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once by dg_mesh_create
     const SpherePair* spheres = nullptr;

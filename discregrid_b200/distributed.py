@@ -1,0 +1,54 @@
+"""Multi-GPU sharding of the addFunction node loop: one process per GPU, torch.distributed for the plumbing.
+
+Nodes are independent (cubic_lagrange_discrete_grid.cpp:806-817 is an embarrassingly parallel loop; OpenMP already
+splits it statically), so the node index space [0, n) is cut into `rows * world` equal chunks dealt round-robin:
+rank r owns chunks r, r + world, r + 2*world, ...  Round-robin (rather than one contiguous slab per rank) evens out
+the spatially varying cost of the nearest-triangle query (far-from-surface nodes prune worse).  Row j of the deal
+is gathered by ONE all-gather whose output is the contiguous slice [j*world*chunk, (j+1)*world*chunk) of the full
+coefficient array -- so the gathered array is already in the reference's node order and no permutation pass is
+needed.  The only exchange step on the path is this all-gather of 8-byte coefficients (NCCL over NVLink on the GPU
+box, gloo in the CPU tests).
+"""
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class NodeSharding:
+    n: int            # number of nodes
+    world: int
+    rows: int
+    chunk: int        # nodes per chunk (last chunks may be short / empty)
+
+    @property
+    def padded(self):
+        return self.rows * self.world * self.chunk
+
+    def chunks_of(self, rank):
+        """[(row, l_begin, l_end)] owned by `rank` (ranges clipped to n; may be empty)."""
+        out = []
+        for j in range(self.rows):
+            b = (j * self.world + rank) * self.chunk
+            out.append((j, min(b, self.n), min(b + self.chunk, self.n)))
+        return out
+
+
+def make_sharding(n, world, rows=8, align=1024):
+    """Equal chunks of a size that is a multiple of `align` nodes (keeps every chunk 8 KiB-aligned in the fp64 array)."""
+    if world == 1:
+        rows = 1
+    per = -(-n // (rows * world))
+    chunk = -(-per // align) * align
+    return NodeSharding(n, world, rows, chunk)
+
+
+def allgather_rows(full, sharding, group=None):
+    """`full`: 1-D tensor of `sharding.padded` elements in which this rank has filled its own chunks.
+    After the call every rank holds all chunks.  One collective per row; each lands in its final position."""
+    import torch.distributed as dist
+    if sharding.world == 1:
+        return
+    rank = dist.get_rank(group)
+    w, c = sharding.world, sharding.chunk
+    for j in range(sharding.rows):
+        row = full[j * w * c:(j + 1) * w * c]
+        dist.all_gather_into_tensor(row, row[rank * c:(rank + 1) * c].clone() if row.device.type == "cpu" else row[rank * c:(rank + 1) * c], group=group)

@@ -74,6 +74,8 @@ DG_API int         dg_abi_version(void);
 DG_API const char* dg_last_error(void);
 /* Number of CUDA devices visible (0 if none / no driver). */
 DG_API int         dg_device_count(void);
+/* cudaSetDevice for this library's CUDA runtime instance (call it with LOCAL_RANK in a one-process-per-GPU job). */
+DG_API int         dg_set_device(int device);
 /* Runs the device self-test (FMA-contraction probe + trivial kernel) on the current device. */
 DG_API int         dg_selftest(void);
 /* Kernels launched by this library in this process since load / last reset (all streams). */
