@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdiscregrid_b200.so")
+# DISCREGRID_B200_LIB: tuning builds of the same library (tools/build_variants.py); never a different implementation
+LIB_PATH = os.environ.get("DISCREGRID_B200_LIB") or os.path.join(_HERE, "lib", "libdiscregrid_b200.so")
 
 DG_OK, DG_ERR_INVALID, DG_ERR_NO_DEVICE, DG_ERR_CUDA, DG_ERR_NOMEM, DG_ERR_SELFTEST = 0, -1, -2, -3, -4, -5
 DBL_MAX = 1.7976931348623157e308

@@ -80,7 +80,7 @@ struct Builder {
 bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err)
 {
     if (!Vd || !F || nT == 0 || nV == 0) { *err = "empty triangle list or vertex list"; return false; }
-    if (nT > (uint64_t)0x3fffffff || nV > (uint64_t)0x7fffffff) { *err = "mesh too large (int32 indices as in the reference)"; return false; }
+    if (nT >= (1ull << 26) || nV > (uint64_t)0x7fffffff) { *err = "mesh too large (< 2^26 triangles; int32 vertex indices as in the reference)"; return false; }
     for (uint64_t i = 0; i < 3 * nT; i++) if (F[i] >= nV) { *err = "triangle index out of range"; return false; }
     const P3* V = reinterpret_cast<const P3*>(Vd);
     const int T = (int)nT;

@@ -38,6 +38,13 @@ __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterp
 // point_triangle_sq_unsigned (TriangleMeshDistance.h:564-820) on a precomputed record.  Returns d2 and the
 // (s, t, entity) the reference would use for nearest_point (:818); the point itself is only needed for the
 // final winner, so it is reconstructed after the traversal.
+//
+// The reference is a 7-region decision tree whose leaves are only SEVEN distinct outcomes -- V0, V1, V2, E01, E02,
+// E12, F -- each of them several times.  Run as written, 32 lanes scatter over ~20 short branches and the warp pays
+// for all of them.  Here the decision tree is evaluated as pure predicate logic (same comparisons, same order, so
+// NaNs fall the same way) producing the outcome code, and the arithmetic is done ONCE for the whole warp: one
+// division (E01: -b0/a00, E02: -b1/a11, E12: numer/denom), one quadratic form (E12 and F), selected per lane.
+// Every value a lane finally uses is produced by exactly the reference's operations in the reference's order.
 __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec, double px, double py, double pz,
                                             double& s_out, double& t_out, int& ent_out)
 {
@@ -54,144 +61,48 @@ __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec, 
     const double b0 = dx * e0x + dy * e0y + dz * e0z;                  // :572
     const double b1 = dx * e1x + dy * e1y + dz * e1z;                  // :573
     const double c = dx * dx + dy * dy + dz * dz;                      // :574
-    double s = a01 * b1 - a11 * b0;                                    // :576
-    double t = a01 * b0 - a00 * b1;                                    // :577
+    const double s0 = a01 * b1 - a11 * b0;                             // :576
+    const double t0 = a01 * b0 - a00 * b1;                             // :577
+
+    // ---- outcome code (0..6 = V0 V1 V2 E01 E12 E02 F), predicate logic only
+    const bool lower = (s0 + t0 <= det);                               // :581
+    const bool sneg = (s0 < 0), tneg = (t0 < 0);
+    const double tmp1_2 = a11 + b1, tmp0_2 = a01 + b0;                 // region 2 (:688-689)
+    const double tmp1_6 = a00 + b0, tmp0_6 = a01 + b1;                 // region 6 (:735-736)
+    const double numer_2 = tmp1_2 - tmp0_2, numer_6 = tmp1_6 - tmp0_6; // :692, :739
+    const double numer_1 = tmp1_2 - a01 - b0;                          // region 1: a11 + b1 - a01 - b0 (:782)
+    const int chain_b1 = (b1 >= 0) ? 0 : ((-b1 >= a11) ? 2 : 5);      // V0 / V2 / E02 (:606-623, :629-646)
+    const int chain_b0 = (b0 >= 0) ? 0 : ((-b0 >= a00) ? 1 : 3);      // V0 / V1 / E01 (:652-669)
+    const int ent_r4 = (b0 < 0) ? ((-b0 >= a00) ? 1 : 3) : chain_b1;   // :587-624
+    const int ent_r2 = (tmp1_2 > tmp0_2) ? ((numer_2 >= denom) ? 1 : 4) : ((tmp1_2 <= 0) ? 2 : ((b1 >= 0) ? 0 : 5));   // :690-731
+    const int ent_r6 = (tmp1_6 > tmp0_6) ? ((numer_6 >= denom) ? 2 : 4) : ((tmp1_6 <= 0) ? 1 : ((b0 >= 0) ? 0 : 3));   // :737-778
+    const int ent_r1 = (numer_1 <= 0) ? 2 : ((numer_1 >= denom) ? 1 : 4);                                               // :783-808
+    const int ent = lower ? (sneg ? (tneg ? ent_r4 : chain_b1) : (tneg ? chain_b0 : 6))
+                          : (sneg ? ent_r2 : (tneg ? ent_r6 : ent_r1));
+    const bool region6 = !lower && !sneg && tneg;
+    const double numer = sneg ? numer_2 : (tneg ? numer_6 : numer_1);  // only read when ent == 4 (upper regions)
+
+    // ---- one division for the three edge outcomes
+    const double num = (ent == 3) ? -b0 : ((ent == 5) ? -b1 : ((ent == 4) ? numer : 0.0));
+    const double den = (ent == 3) ? a00 : ((ent == 5) ? a11 : ((ent == 4) ? denom : 1.0));
+    const double q = num / den;
+    // ---- (s, t) of the nearest point
+    double s, t;
+    if (ent == 6) { s = s0 * inv_det; t = t0 * inv_det; }              // :675-677
+    else if (ent == 4) { s = region6 ? 1 - q : q; t = region6 ? q : 1 - q; }   // :704-705, :751-752, :803-804
+    else { s = (ent == 1) ? 1.0 : ((ent == 3) ? q : 0.0); t = (ent == 2) ? 1.0 : ((ent == 5) ? q : 0.0); }
+    // ---- d2
+    const double quad = s * (a00 * s + a01 * t + 2 * b0) + t * (a01 * s + a11 * t + 2 * b1) + c;   // :678, :706, :753, :805
     double d2;
-    int ent;
-    // the three vertex / three edge outcomes, written once (each appears several times in the reference)
-#define DG_V0() { ent = 0; s = 0; t = 0; d2 = c; }
-#define DG_V1() { ent = 1; s = 1; t = 0; d2 = a00 + 2 * b0 + c; }
-#define DG_V2() { ent = 2; s = 0; t = 1; d2 = a11 + 2 * b1 + c; }
-#define DG_E01() { ent = 3; t = 0; s = -b0 / a00; d2 = b0 * s + c; }
-#define DG_E02() { ent = 5; s = 0; t = -b1 / a11; d2 = b1 * t + c; }
-#define DG_QUAD() (s * (a00 * s + a01 * t + 2 * b0) + t * (a01 * s + a11 * t + 2 * b1) + c)
-    if (s + t <= det) {
-        if (s < 0) {
-            if (t < 0) {                                // region 4 (:585-625)
-                if (b0 < 0) { if (-b0 >= a00) DG_V1() else DG_E01() }
-                else { if (b1 >= 0) DG_V0() else if (-b1 >= a11) DG_V2() else DG_E02() }
-            } else {                                    // region 3 (:626-647)
-                if (b1 >= 0) DG_V0() else if (-b1 >= a11) DG_V2() else DG_E02()
-            }
-        } else if (t < 0) {                             // region 5 (:649-670)
-            if (b0 >= 0) DG_V0() else if (-b0 >= a00) DG_V1() else DG_E01()
-        } else {                                        // region 0 (:671-680)
-            ent = 6;
-            s *= inv_det; t *= inv_det;
-            d2 = DG_QUAD();
-        }
-    } else {
-        if (s < 0) {                                    // region 2 (:686-732)
-            const double tmp0 = a01 + b0, tmp1 = a11 + b1;
-            if (tmp1 > tmp0) {
-                const double numer = tmp1 - tmp0;
-                if (numer >= denom) DG_V1()
-                else { ent = 4; s = numer / denom; t = 1 - s; d2 = DG_QUAD(); }
-            } else {
-                if (tmp1 <= 0) DG_V2() else if (b1 >= 0) DG_V0() else DG_E02()
-            }
-        } else if (t < 0) {                             // region 6 (:733-779)
-            const double tmp0 = a01 + b1, tmp1 = a00 + b0;
-            if (tmp1 > tmp0) {
-                const double numer = tmp1 - tmp0;
-                if (numer >= denom) DG_V2()
-                else { ent = 4; t = numer / denom; s = 1 - t; d2 = DG_QUAD(); }
-            } else {
-                if (tmp1 <= 0) DG_V1() else if (b0 >= 0) DG_V0() else DG_E01()
-            }
-        } else {                                        // region 1 (:780-809)
-            const double numer = a11 + b1 - a01 - b0;
-            if (numer <= 0) DG_V2()
-            else if (numer >= denom) DG_V1()
-            else { ent = 4; s = numer / denom; t = 1 - s; d2 = DG_QUAD(); }
-        }
-    }
-#undef DG_V0
-#undef DG_V1
-#undef DG_V2
-#undef DG_E01
-#undef DG_E02
-#undef DG_QUAD
-    if (d2 < 0) d2 = 0;                                 // :812-816
+    if (ent >= 6 || ent == 4) d2 = quad;
+    else if (ent == 0) d2 = c;                                         // :610
+    else if (ent == 1) d2 = a00 + 2 * b0 + c;                          // :594
+    else if (ent == 2) d2 = a11 + 2 * b1 + c;                          // :616
+    else if (ent == 3) d2 = b0 * q + c;                                // :600
+    else d2 = b1 * q + c;                                              // :622
+    if (d2 < 0) d2 = 0;                                                // :812-816
     s_out = s; t_out = t; ent_out = ent;
     return d2;
-}
-
-// _query (TriangleMeshDistance.h:514-562), iterative and WARP-SYNCHRONOUS: all 32 lanes of the warp call this
-// together (`alive` = lane has a query).  Every lane walks its own reference order with its own stack, but the warp
-// executes one phase at a time, chosen by ballot: an "internal" phase (two sphere tests, push / descend / prune) for
-// the lanes sitting at an internal node, or a "leaf" phase (point-triangle test, accept, pop) for the lanes sitting at
-// a leaf.  The phase with more (cost-weighted) lanes runs; the others idle for that iteration.  This keeps the
-// expensive straight-line blocks converged instead of letting 32 private loops drift apart.
-// stack_rng/stack_d point at this lane's column of the block's shared-memory stack ([depth][lane], conflict-free).
-__device__ __forceinline__ QueryResult nearest_triangle(const SpherePair* __restrict__ spheres,
-                                                        const LeafRecord* __restrict__ leaves, int n_tri, bool alive,
-                                                        double px, double py, double pz,
-                                                        uint2* stack_rng, double* stack_d, int stride)
-{
-    QueryResult res;
-    res.dist = DBL_MAX; res.s = 0; res.t = 0; res.pos = -1; res.entity = 0;
-    double best = DBL_MAX;             // result.distance
-    double best_sq = best * best;      // result.distance * result.distance (= +inf initially), :528
-    int b = 0, e = n_tri, sp = 0;
-    // pops deferred siblings until one passes the reference's second test `d < result.distance` (:549, :557)
-    auto pop = [&]() {
-        for (;;) {
-            if (sp == 0) { alive = false; return; }
-            sp--;
-            if (stack_d[sp * stride] < best) {
-                const uint2 r = stack_rng[sp * stride];
-                b = (int)r.x; e = (int)r.y;
-                return;
-            }
-        }
-    };
-    for (;;) {
-        const bool at_leaf = alive && (e - b == 1);
-        const bool at_node = alive && (e - b > 1);
-        const unsigned m_leaf = __ballot_sync(0xffffffffu, at_leaf);
-        const unsigned m_node = __ballot_sync(0xffffffffu, at_node);
-        if ((m_leaf | m_node) == 0u) break;
-        if (K1_NODE_WEIGHT * __popc(m_node) >= K1_LEAF_WEIGHT * __popc(m_leaf)) {
-            if (at_node) {                                                      // internal (:537-561)
-                const int m = (b + e) >> 1;
-                const double* sp8 = reinterpret_cast<const double*>(spheres + m);
-                const double2 a0 = ldg2(sp8), a1 = ldg2(sp8 + 2), a2 = ldg2(sp8 + 4), a3 = ldg2(sp8 + 6);
-                const double lx = px - a0.x, ly = py - a0.y, lz = pz - a1.x;
-                const double rx = px - a2.x, ry = py - a2.y, rz = pz - a3.x;
-                const double d_left = sqrt(lx * lx + ly * ly + lz * lz) - a1.y;     // :539
-                const double d_right = sqrt(rx * rx + ry * ry + rz * rz) - a3.y;    // :540
-                const bool left_first = d_left < d_right;                           // :542
-                const double d_first = left_first ? d_left : d_right;
-                const double d_second = left_first ? d_right : d_left;
-                const int fb = left_first ? b : m, fe = left_first ? m : e;
-                const int sb = left_first ? m : b, se = left_first ? e : m;
-                if (d_first < best) {                  // visit first now; second is re-tested when popped (:545-551)
-                    stack_rng[sp * stride] = make_uint2((unsigned)sb, (unsigned)se);
-                    stack_d[sp * stride] = d_second;
-                    sp++;
-                    b = fb; e = fe;
-                } else if (d_second < best) {          // only reachable through NaNs; kept for fidelity
-                    b = sb; e = se;
-                } else {
-                    pop();
-                }
-            }
-        } else {
-            if (at_leaf) {                                                      // leaf (:517-534)
-                double s, t; int ent;
-                const double d2 = tri_dist2(leaves + b, px, py, pz, s, t, ent);
-                if (d2 < best_sq) {
-                    best = sqrt(d2);
-                    best_sq = best * best;
-                    res.s = s; res.t = t; res.pos = b; res.entity = ent;
-                }
-                pop();
-            }
-        }
-    }
-    res.dist = best;
-    return res;
 }
 
 // nearest_point (TriangleMeshDistance.h:818) and the pseudonormal sign (:274-305)
@@ -221,6 +132,106 @@ __device__ __forceinline__ void finish_query(const LeafRecord* __restrict__ leav
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// _query (TriangleMeshDistance.h:514-562), iterative and WARP-SYNCHRONOUS.
+//
+// All 32 lanes of a warp call this together, each with its own query (`alive`).  Every lane walks the tree in the
+// reference's own order with its own stack of deferred siblings, but the warp executes ONE PHASE per iteration, chosen
+// by ballot so that each straight-line block runs converged:
+//   NODE : lanes at an internal node: two sphere tests, then descend + defer the sibling, or prune
+//   LEAF : lanes at a leaf: point-triangle test, accept if strictly closer
+//   POP  : lanes that pruned / finished a leaf: re-test deferred siblings (`d < result.distance`, :549/:557)
+// The phase holding the largest cost-weighted share of lanes runs; the other lanes idle for that iteration.  All lanes
+// start at the root together and -- being 32 adjacent grid nodes -- take mostly the same decisions, so the phases stay
+// largely aligned.  (Letting a finished lane start its next query immediately was tried and is ~1.6x SLOWER: lanes
+// then sit at unrelated depths of the tree and both phase alignment and cache sharing are lost.)
+//
+// Stack entry = 12 bytes: the sibling's sphere distance (fp64) + its leaf range packed in 32 bits.  A node at depth k
+// covers either floor(T/2^k) or that + 1 leaves (halving splits), so (begin, depth, +1 flag) identifies the range.
+// Layout [depth][lane] in shared memory: conflict-free whatever depth each lane is at.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned pack_range(int b, int e, int depth, int n_tri)
+{
+    return (unsigned)b | ((unsigned)depth << 26) | ((unsigned)((e - b) - (n_tri >> depth)) << 31);
+}
+
+__device__ __forceinline__ QueryResult nearest_triangle(const SpherePair* __restrict__ spheres,
+                                                        const LeafRecord* __restrict__ leaves, int n_tri, bool alive,
+                                                        double px, double py, double pz,
+                                                        unsigned* stack_rng, double* stack_d, int stride)
+{
+    enum { NODE = 0, LEAF = 1, POP = 2, DONE = 3 };
+    QueryResult res;
+    res.dist = DBL_MAX; res.s = 0; res.t = 0; res.pos = -1; res.entity = 0;
+    double best = DBL_MAX;             // result.distance
+    double best_sq = best * best;      // result.distance * result.distance (= +inf initially), :528
+    int b = 0, e = n_tri, depth = 0, sp = 0;
+    int state = alive ? ((n_tri == 1) ? LEAF : NODE) : DONE;
+    for (;;) {
+        const unsigned m_node = __ballot_sync(0xffffffffu, state == NODE);
+        const unsigned m_leaf = __ballot_sync(0xffffffffu, state == LEAF);
+        const unsigned m_pop = __ballot_sync(0xffffffffu, state == POP);
+        if ((m_node | m_leaf | m_pop) == 0u) break;
+        const int w_node = K1_NODE_WEIGHT * __popc(m_node), w_leaf = K1_LEAF_WEIGHT * __popc(m_leaf), w_pop = K1_POP_WEIGHT * __popc(m_pop);
+        if (w_pop >= w_node && w_pop >= w_leaf) {
+            if (state == POP) {
+#pragma unroll 1
+                for (int attempt = 0; attempt < K1_POP_TRIES; attempt++) {
+                    if (sp == 0) { state = DONE; break; }
+                    sp--;
+                    if (stack_d[sp * stride] < best) {             // the reference's second `if`, with the updated best
+                        const unsigned r = stack_rng[sp * stride];
+                        b = (int)(r & 0x03ffffffu);
+                        depth = (int)((r >> 26) & 31u);
+                        e = b + (n_tri >> depth) + (int)(r >> 31);
+                        state = (e - b == 1) ? LEAF : NODE;
+                        break;
+                    }
+                }
+            }
+        } else if (w_node >= w_leaf) {
+            if (state == NODE) {                                                // internal (:537-561)
+                const int m = (b + e) >> 1;
+                const double* sp8 = reinterpret_cast<const double*>(spheres + m);
+                const double2 a0 = ldg2(sp8), a1 = ldg2(sp8 + 2), a2 = ldg2(sp8 + 4), a3 = ldg2(sp8 + 6);
+                const double lx = px - a0.x, ly = py - a0.y, lz = pz - a1.x;
+                const double rx = px - a2.x, ry = py - a2.y, rz = pz - a3.x;
+                const double d_left = sqrt(lx * lx + ly * ly + lz * lz) - a1.y;     // :539
+                const double d_right = sqrt(rx * rx + ry * ry + rz * rz) - a3.y;    // :540
+                const bool left_first = d_left < d_right;                           // :542
+                const double d_first = left_first ? d_left : d_right;
+                const double d_second = left_first ? d_right : d_left;
+                depth++;
+                if (d_first < best) {                  // visit first now; second is re-tested when popped (:545-551)
+                    stack_rng[sp * stride] = left_first ? pack_range(m, e, depth, n_tri) : pack_range(b, m, depth, n_tri);
+                    stack_d[sp * stride] = d_second;
+                    sp++;
+                    if (left_first) e = m; else b = m;
+                    state = (e - b == 1) ? LEAF : NODE;
+                } else if (d_second < best) {          // only reachable through NaNs; kept for fidelity
+                    if (left_first) b = m; else e = m;
+                    state = (e - b == 1) ? LEAF : NODE;
+                } else {
+                    state = POP;
+                }
+            }
+        } else {
+            if (state == LEAF) {                                                // leaf (:517-534)
+                double s, t; int ent;
+                const double d2 = tri_dist2(leaves + b, px, py, pz, s, t, ent);
+                if (d2 < best_sq) {
+                    best = sqrt(d2);
+                    best_sq = best * best;
+                    res.s = s; res.t = t; res.pos = b; res.entity = ent;
+                }
+                state = POP;
+            }
+        }
+    }
+    res.dist = best;
+    return res;
+}
+
 extern __shared__ __align__(16) unsigned char k1_smem[];
 
 // addFunction node loop: out[l - l_begin] = sign * signed_distance(indexToNodePosition(l)).distance.
@@ -228,13 +239,13 @@ extern __shared__ __align__(16) unsigned char k1_smem[];
 // owns a 4 x 4 x 2 brick (fast x mid x slow) of one of them and a 128-thread block four bricks side by side along the
 // fast axis, so the 32 queries of a warp are spatial neighbours: they visit nearly the same tree nodes (L1 hits) and
 // take similar numbers of steps.  Whole slow-planes are covered; nodes outside [l_begin, l_end) are masked.
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 sdf_sample_nodes_kernel(const SpherePair* __restrict__ spheres, const LeafRecord* __restrict__ leaves,
                         const PseudoNormals* __restrict__ normals, int n_tri, int stack_depth, GridDev g, K1Work w, double sign,
                         double* __restrict__ out)
 {
     double* stack_d = reinterpret_cast<double*>(k1_smem);
-    uint2* stack_rng = reinterpret_cast<uint2*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(double));
+    unsigned* stack_rng = reinterpret_cast<unsigned*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(double));
     // which segment does this block belong to (<= 4, uniform per block)
     int sg = 0;
 #pragma unroll
@@ -252,7 +263,6 @@ sdf_sample_nodes_kernel(const SpherePair* __restrict__ spheres, const LeafRecord
 
     // indexToNodePosition (cubic_lagrange_discrete_grid.cpp:604-665) from the array coordinates
     unsigned i, j, k;
-    int axis = S.kind - 1;                  // -1 vertex, 0/1/2 edge axis
     const unsigned par = f & 1u, fh = f >> 1;
     if (S.kind == 0) { i = f; j = m; k = sl; }
     else if (S.kind == 1) { i = fh; j = m; k = sl; }
@@ -262,9 +272,9 @@ sdf_sample_nodes_kernel(const SpherePair* __restrict__ spheres, const LeafRecord
     double py = g.mn[1] + g.cell[1] * (double)j;
     double pz = g.mn[2] + g.cell[2] * (double)k;
     const double fr = (1.0 + (double)par) / 3.0;
-    if (axis == 0) px = px + fr * g.cell[0];
-    else if (axis == 1) py = py + fr * g.cell[1];
-    else if (axis == 2) pz = pz + fr * g.cell[2];
+    if (S.kind == 1) px = px + fr * g.cell[0];
+    else if (S.kind == 2) py = py + fr * g.cell[1];
+    else if (S.kind == 3) pz = pz + fr * g.cell[2];
 
     const QueryResult r = nearest_triangle(spheres, leaves, n_tri, alive, px, py, pz, stack_rng + threadIdx.x,
                                            stack_d + threadIdx.x, K1_THREADS);
@@ -274,8 +284,8 @@ sdf_sample_nodes_kernel(const SpherePair* __restrict__ spheres, const LeafRecord
     out[l - w.l_begin] = (sign == 1.0) ? dist : sign * dist;     // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
 }
 
-// batched TriangleMeshDistance::{signed,unsigned}_distance on arbitrary points
-__global__ void __launch_bounds__(K1_THREADS)
+// batched TriangleMeshDistance::{signed,unsigned}_distance on arbitrary points (a warp = 32 consecutive points)
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 mesh_distance_kernel(const SpherePair* __restrict__ spheres, const LeafRecord* __restrict__ leaves,
                      const PseudoNormals* __restrict__ normals, int n_tri, int stack_depth,
                      const double* __restrict__ pts, unsigned long long count, int is_signed,
@@ -283,7 +293,7 @@ mesh_distance_kernel(const SpherePair* __restrict__ spheres, const LeafRecord* _
                      int* __restrict__ tri_out)
 {
     double* stack_d = reinterpret_cast<double*>(k1_smem);
-    uint2* stack_rng = reinterpret_cast<uint2*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(double));
+    unsigned* stack_rng = reinterpret_cast<unsigned*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(double));
     const unsigned long long idx = (unsigned long long)blockIdx.x * K1_THREADS + threadIdx.x;
     const bool alive = idx < count;
     const unsigned long long ix = alive ? idx : 0ull;
@@ -324,7 +334,7 @@ __global__ void fma_probe_kernel(double a, double b, double c, double* out) { ou
 
 }  // namespace
 
-static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(double) + sizeof(uint2)); }
+static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(double) + sizeof(unsigned)); }
 
 cudaError_t k1_configure(int stack_depth)
 {

@@ -8,13 +8,21 @@
 namespace dgb {
 
 constexpr int K1_THREADS = 128;
-// phase choice of the warp-synchronous traversal: run the internal phase when
-// K1_NODE_WEIGHT * #lanes_at_internal_nodes >= K1_LEAF_WEIGHT * #lanes_at_leaves
+// phase choice of the warp-synchronous traversal: the phase with the largest weight * #lanes runs
 #ifndef K1_NODE_WEIGHT
-#define K1_NODE_WEIGHT 1
+#define K1_NODE_WEIGHT 2
 #endif
 #ifndef K1_LEAF_WEIGHT
-#define K1_LEAF_WEIGHT 1
+#define K1_LEAF_WEIGHT 3
+#endif
+#ifndef K1_POP_WEIGHT
+#define K1_POP_WEIGHT 4
+#endif
+#ifndef K1_POP_TRIES
+#define K1_POP_TRIES 4          // deferred siblings re-tested per POP phase and lane
+#endif
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 8         // 128-thread blocks per SM the register allocation must allow
 #endif
 
 // One of the four row-major 3-D node arrays of the grid (vertex nodes, x-/y-/z-edge nodes), restricted to the
