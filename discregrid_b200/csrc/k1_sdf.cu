@@ -77,29 +77,42 @@ __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec, 
     const int ent_r2 = (tmp1_2 > tmp0_2) ? ((numer_2 >= denom) ? 1 : 4) : ((tmp1_2 <= 0) ? 2 : ((b1 >= 0) ? 0 : 5));   // :690-731
     const int ent_r6 = (tmp1_6 > tmp0_6) ? ((numer_6 >= denom) ? 2 : 4) : ((tmp1_6 <= 0) ? 1 : ((b0 >= 0) ? 0 : 3));   // :737-778
     const int ent_r1 = (numer_1 <= 0) ? 2 : ((numer_1 >= denom) ? 1 : 4);                                               // :783-808
-    const int ent = lower ? (sneg ? (tneg ? ent_r4 : chain_b1) : (tneg ? chain_b0 : 6))
-                          : (sneg ? ent_r2 : (tneg ? ent_r6 : ent_r1));
+    // `pin` = empty asm that makes the value opaque: the compiler must materialise it here and can neither specialise
+    // the code below per outcome (it otherwise re-creates one divergent branch per outcome, each with its own division)
+    // nor move it.  It emits no instruction.
+#if K1_LEAF_PIN
+#define DG_PIN_I(v) asm volatile("" : "+r"(v))
+#define DG_PIN_D(v) asm volatile("" : "+d"(v))
+#else
+#define DG_PIN_I(v)
+#define DG_PIN_D(v)
+#endif
+    int ent = lower ? (sneg ? (tneg ? ent_r4 : chain_b1) : (tneg ? chain_b0 : 6))
+                    : (sneg ? ent_r2 : (tneg ? ent_r6 : ent_r1));
+    DG_PIN_I(ent);
     const bool region6 = !lower && !sneg && tneg;
     const double numer = sneg ? numer_2 : (tneg ? numer_6 : numer_1);  // only read when ent == 4 (upper regions)
 
     // ---- one division for the three edge outcomes
-    const double num = (ent == 3) ? -b0 : ((ent == 5) ? -b1 : ((ent == 4) ? numer : 0.0));
-    const double den = (ent == 3) ? a00 : ((ent == 5) ? a11 : ((ent == 4) ? denom : 1.0));
-    const double q = num / den;
+    double num = (ent == 3) ? -b0 : ((ent == 5) ? -b1 : ((ent == 4) ? numer : 0.0));
+    double den = (ent == 3) ? a00 : ((ent == 5) ? a11 : ((ent == 4) ? denom : 1.0));
+    DG_PIN_D(num); DG_PIN_D(den);
+    double q = num / den;
+    DG_PIN_D(q);
     // ---- (s, t) of the nearest point
-    double s, t;
-    if (ent == 6) { s = s0 * inv_det; t = t0 * inv_det; }              // :675-677
-    else if (ent == 4) { s = region6 ? 1 - q : q; t = region6 ? q : 1 - q; }   // :704-705, :751-752, :803-804
-    else { s = (ent == 1) ? 1.0 : ((ent == 3) ? q : 0.0); t = (ent == 2) ? 1.0 : ((ent == 5) ? q : 0.0); }
+    const double sF = s0 * inv_det, tF = t0 * inv_det;                 // :675-677 (read when ent == 6)
+    const double omq = 1 - q;                                          // :705, :752, :804 (read when ent == 4)
+    double s = (ent == 6) ? sF : ((ent == 4) ? (region6 ? omq : q) : ((ent == 1) ? 1.0 : ((ent == 3) ? q : 0.0)));
+    double t = (ent == 6) ? tF : ((ent == 4) ? (region6 ? q : omq) : ((ent == 2) ? 1.0 : ((ent == 5) ? q : 0.0)));
+    DG_PIN_D(s); DG_PIN_D(t);
     // ---- d2
-    const double quad = s * (a00 * s + a01 * t + 2 * b0) + t * (a01 * s + a11 * t + 2 * b1) + c;   // :678, :706, :753, :805
-    double d2;
-    if (ent >= 6 || ent == 4) d2 = quad;
-    else if (ent == 0) d2 = c;                                         // :610
-    else if (ent == 1) d2 = a00 + 2 * b0 + c;                          // :594
-    else if (ent == 2) d2 = a11 + 2 * b1 + c;                          // :616
-    else if (ent == 3) d2 = b0 * q + c;                                // :600
-    else d2 = b1 * q + c;                                              // :622
+    double quad = s * (a00 * s + a01 * t + 2 * b0) + t * (a01 * s + a11 * t + 2 * b1) + c;   // :678, :706, :753, :805
+    double dv1 = a00 + 2 * b0 + c, dv2 = a11 + 2 * b1 + c;            // :594, :616
+    double de1 = b0 * q + c, de2 = b1 * q + c;                         // :600, :622
+    DG_PIN_D(quad); DG_PIN_D(dv1); DG_PIN_D(dv2); DG_PIN_D(de1); DG_PIN_D(de2);
+    double d2 = (ent == 6 || ent == 4) ? quad : ((ent == 0) ? c : ((ent == 1) ? dv1 : ((ent == 2) ? dv2 : ((ent == 3) ? de1 : de2))));
+#undef DG_PIN_I
+#undef DG_PIN_D
     if (d2 < 0) d2 = 0;                                                // :812-816
     s_out = s; t_out = t; ent_out = ent;
     return d2;
@@ -168,28 +181,18 @@ __device__ __forceinline__ QueryResult nearest_triangle(const SpherePair* __rest
     int b = 0, e = n_tri, depth = 0, sp = 0;
     int state = alive ? ((n_tri == 1) ? LEAF : NODE) : DONE;
     for (;;) {
-        const unsigned m_node = __ballot_sync(0xffffffffu, state == NODE);
-        const unsigned m_leaf = __ballot_sync(0xffffffffu, state == LEAF);
-        const unsigned m_pop = __ballot_sync(0xffffffffu, state == POP);
-        if ((m_node | m_leaf | m_pop) == 0u) break;
-        const int w_node = K1_NODE_WEIGHT * __popc(m_node), w_leaf = K1_LEAF_WEIGHT * __popc(m_leaf), w_pop = K1_POP_WEIGHT * __popc(m_pop);
-        if (w_pop >= w_node && w_pop >= w_leaf) {
-            if (state == POP) {
-#pragma unroll 1
-                for (int attempt = 0; attempt < K1_POP_TRIES; attempt++) {
-                    if (sp == 0) { state = DONE; break; }
-                    sp--;
-                    if (stack_d[sp * stride] < best) {             // the reference's second `if`, with the updated best
-                        const unsigned r = stack_rng[sp * stride];
-                        b = (int)(r & 0x03ffffffu);
-                        depth = (int)((r >> 26) & 31u);
-                        e = b + (n_tri >> depth) + (int)(r >> 31);
-                        state = (e - b == 1) ? LEAF : NODE;
-                        break;
-                    }
-                }
-            }
-        } else if (w_node >= w_leaf) {
+        // two ballots carry the 2-bit state of all 32 lanes
+        const unsigned bit0 = __ballot_sync(0xffffffffu, state & 1), bit1 = __ballot_sync(0xffffffffu, state & 2);
+        if ((bit0 & bit1) == 0xffffffffu) break;                               // every lane DONE
+        const int n_node = __popc(~(bit0 | bit1)), n_leaf = __popc(bit0 & ~bit1);
+#if !K1_POP_MERGED
+        const int n_pop = __popc(~bit0 & bit1);
+        const bool pop_phase = K1_POP_WEIGHT * n_pop >= K1_NODE_WEIGHT * n_node && K1_POP_WEIGHT * n_pop >= K1_LEAF_WEIGHT * n_leaf;
+#else
+        const bool pop_phase = false;
+#endif
+        if (pop_phase) {
+        } else if (n_node != 0 && K1_NODE_WEIGHT * n_node >= K1_LEAF_WEIGHT * n_leaf) {
             if (state == NODE) {                                                // internal (:537-561)
                 const int m = (b + e) >> 1;
                 const double* sp8 = reinterpret_cast<const double*>(spheres + m);
@@ -215,7 +218,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const SpherePair* __rest
                     state = POP;
                 }
             }
-        } else {
+        } else if (n_leaf != 0) {
             if (state == LEAF) {                                                // leaf (:517-534)
                 double s, t; int ent;
                 const double d2 = tri_dist2(leaves + b, px, py, pz, s, t, ent);
@@ -225,6 +228,24 @@ __device__ __forceinline__ QueryResult nearest_triangle(const SpherePair* __rest
                     res.s = s; res.t = t; res.pos = b; res.entity = ent;
                 }
                 state = POP;
+            }
+        }
+        // deferred siblings: the reference's second `if (d < result.distance)` (:549, :557) with the updated best.
+        // Runs at the end of every iteration for the lanes that need it (those that just pruned / finished a leaf, and
+        // those still looking), so popping never costs an iteration of its own unless nobody else can move.
+        if (state == POP && (K1_POP_MERGED || pop_phase)) {
+#pragma unroll 1
+            for (int attempt = 0; attempt < K1_POP_TRIES; attempt++) {
+                if (sp == 0) { state = DONE; break; }
+                sp--;
+                if (stack_d[sp * stride] < best) {
+                    const unsigned r = stack_rng[sp * stride];
+                    b = (int)(r & 0x03ffffffu);
+                    depth = (int)((r >> 26) & 31u);
+                    e = b + (n_tri >> depth) + (int)(r >> 31);
+                    state = (e - b == 1) ? LEAF : NODE;
+                    break;
+                }
             }
         }
     }
@@ -255,7 +276,7 @@ sdf_sample_nodes_kernel(const SpherePair* __restrict__ spheres, const LeafRecord
     const unsigned tf = t % S.tiles_f; t /= S.tiles_f;
     const unsigned tm = t % S.tiles_m; const unsigned ts = t / S.tiles_m;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned f = tf * 16u + warp * 4u + (lane & 3u);
+    const unsigned f = tf * (unsigned)(K1_THREADS / 8) + warp * 4u + (lane & 3u);
     const unsigned m = tm * 4u + ((lane >> 2) & 3u);
     const unsigned sl = S.s0 + ts * 2u + (lane >> 4);
     const unsigned l = S.l_base + (sl * S.Dm + m) * S.Df + f;
@@ -368,7 +389,7 @@ cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double 
         const uint64_t plane = (uint64_t)S.Dm * S.Df;
         S.s0 = (unsigned)((a - base[k]) / plane);
         S.s1 = (unsigned)((b - 1 - base[k]) / plane) + 1;
-        S.tiles_f = (S.Df + 15) / 16; S.tiles_m = (S.Dm + 3) / 4;
+        S.tiles_f = (S.Df + K1_THREADS / 8 - 1) / (K1_THREADS / 8); S.tiles_m = (S.Dm + 3) / 4;
         const unsigned tiles_s = (S.s1 - S.s0 + 1) / 2;
         S.block_begin = blocks;
         blocks += S.tiles_f * S.tiles_m * tiles_s;

@@ -7,7 +7,10 @@
 
 namespace dgb {
 
-constexpr int K1_THREADS = 128;
+#ifndef K1_THREADS_PER_BLOCK
+#define K1_THREADS_PER_BLOCK 64
+#endif
+constexpr int K1_THREADS = K1_THREADS_PER_BLOCK;
 // phase choice of the warp-synchronous traversal: the phase with the largest weight * #lanes runs
 #ifndef K1_NODE_WEIGHT
 #define K1_NODE_WEIGHT 2
@@ -21,8 +24,14 @@ constexpr int K1_THREADS = 128;
 #ifndef K1_POP_TRIES
 #define K1_POP_TRIES 4          // deferred siblings re-tested per POP phase and lane
 #endif
+#ifndef K1_POP_MERGED
+#define K1_POP_MERGED 0         // 1: POP lanes re-test siblings at the end of every iteration; 0: POP is a phase of its own
+#endif
+#ifndef K1_LEAF_PIN
+#define K1_LEAF_PIN 0           // 1: force the single-division branch-free leaf arithmetic (see tri_dist2)
+#endif
 #ifndef K1_MIN_BLOCKS
-#define K1_MIN_BLOCKS 8         // 128-thread blocks per SM the register allocation must allow
+#define K1_MIN_BLOCKS (1024 / K1_THREADS_PER_BLOCK)   // blocks per SM the register allocation must allow (32 warps)
 #endif
 
 // One of the four row-major 3-D node arrays of the grid (vertex nodes, x-/y-/z-edge nodes), restricted to the
