@@ -36,7 +36,7 @@ class TriangleMesh:
         with open(path, "w") as fh:
             fh.write("g default\n")
             for p in self.vertices:
-                fh.write(f"v {p[0]!r} {p[1]!r} {p[2]!r}\n")
+                fh.write(f"v {float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n")
             for t in self.faces:
                 fh.write(f"f {t[0] + 1} {t[1] + 1} {t[2] + 1}\n")
 
