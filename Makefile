@@ -14,8 +14,26 @@ LIB      := discregrid_b200/lib/libdiscregrid_b200.so
 CU       := k1_sdf k2_interp k3_density dg_api
 HDRS     := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/discregrid_b200.h
 
-all: lib oracle
+all: lib cpp oracle
 lib: $(LIB)
+
+# C++ facade (cpp/include/Discregrid/*: the reference's class API over the C-ABI) -- the reference tools and a checker.
+# Eigen3 is not installed in this image: cpp/eigen_min is used unless EIGEN3_INCLUDE_DIR points at the real one.
+EIGEN3_INCLUDE_DIR ?= cpp/eigen_min
+CPPBIN   := build/bin
+CPPFLAGS := -std=c++11 -O2 -ffp-contract=off -I$(EIGEN3_INCLUDE_DIR) -Icpp/include -Iinclude
+CPPLINK  := -Ldiscregrid_b200/lib -ldiscregrid_b200 -Wl,-rpath,'$$ORIGIN/../../discregrid_b200/lib'
+CPPHDRS  := $(wildcard cpp/include/Discregrid/* cpp/include/Discregrid/*/*) include/discregrid_b200.h
+cpp: $(CPPBIN)/GenerateSDF $(CPPBIN)/GenerateDensityMap $(CPPBIN)/facade_check
+$(CPPBIN)/GenerateSDF: cpp/cmd/generate_sdf.cpp $(CPPHDRS) $(LIB)
+	@mkdir -p $(CPPBIN)
+	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK)
+$(CPPBIN)/GenerateDensityMap: cpp/cmd/generate_density_map.cpp $(CPPHDRS) $(LIB)
+	@mkdir -p $(CPPBIN)
+	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK)
+$(CPPBIN)/facade_check: cpp/cmd/facade_check.cpp $(CPPHDRS) $(LIB)
+	@mkdir -p $(CPPBIN)
+	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK)
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -34,4 +52,4 @@ oracle:
 clean:
 	rm -rf build $(LIB)
 	$(MAKE) -C oracle clean
-.PHONY: all lib oracle clean
+.PHONY: all lib cpp oracle clean

@@ -182,7 +182,7 @@ def main():
 
     import discregrid_b200 as dg           # fails loudly if the CUDA library is not built
     from discregrid_b200 import _capi as capi
-    from discregrid_b200.distributed import make_sharding, allgather_rows
+    from discregrid_b200.distributed import make_sharding, allgather_rows, ShardedSdfSampler
 
     mesh = dg.bumpy_torus(*WORKLOAD["torus"])
     mn, mx = dg.generate_sdf_domain(mesh.vertices)
@@ -193,7 +193,7 @@ def main():
     config = {"workload": f"GenerateSDF addFunction: {WORKLOAD['mesh']}; {res[0]}x{res[1]}x{res[2]} grid = {n_nodes} nodes; "
                           "GenerateSDF-padded domain; fp64 bit-exact with the reference",
               "mesh_triangles": int(mesh.nFaces()), "grid": res, "nodes": n_nodes,
-              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"node-chunks x{world}"}
+              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"node-chunks x{world}" + ("" if world == 1 else ", 8 round-robin chunks per rank on 4 streams + per-row NCCL all-gather")}
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -217,6 +217,7 @@ def main():
     torch.cuda.set_device(local_rank)
     capi.check(capi.lib.dg_set_device(local_rank))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -239,12 +240,10 @@ def main():
     my_chunks = [(j, b, e) for (j, b, e) in sh.chunks_of(rank)]
     stream = torch.cuda.current_stream()
 
+    sampler = ShardedSdfSampler(md, desc, sh, rank)
+
     def sdf_step():
-        sp = C.c_void_p(stream.cuda_stream)
-        for (_j, b, e) in my_chunks:
-            if e > b:
-                capi.check(capi.lib.dg_sample_sdf_device(md.handle, C.byref(desc), 1.0, b, e, C.c_void_p(full.data_ptr() + 8 * b), sp))
-        allgather_rows(full, sh)
+        sampler.step(full)
 
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
@@ -274,10 +273,7 @@ def main():
 
     # kernel-only time of K1 on this rank (no collective): what the roofline object refers to
     def k1_only():
-        sp = C.c_void_p(stream.cuda_stream)
-        for (_j, b, e) in my_chunks:
-            if e > b:
-                capi.check(capi.lib.dg_sample_sdf_device(md.handle, C.byref(desc), 1.0, b, e, C.c_void_p(full.data_ptr() + 8 * b), sp))
+        sampler.launch(full)
     k1_ms, _ = timed(k1_only, max(3, args.steps // 2), 1)
     k1_ms = float(np.mean(k1_ms))
     my_nodes = sum(e - b for (_j, b, e) in my_chunks)

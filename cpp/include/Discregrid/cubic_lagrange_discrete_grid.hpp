@@ -1,0 +1,311 @@
+// Discregrid::CubicLagrangeDiscreteGrid -- the reference's public surface and members
+// (discregrid/include/Discregrid/cubic_lagrange_discrete_grid.hpp:8-72) with the hot path on the B200:
+//
+//   addFunction(MeshSignedDistanceFunction)  -> dg_sample_sdf   (K1)   replaces the OpenMP node loop :806-831
+//   addFunction(DensityMapFunction)          -> dg_density_map  (K3)   (GenerateDensityMap's functor + predicate)
+//   interpolate(field, x, grad*)             -> dg_interpolate_batch (K2), also batched: interpolate(field, n, x, phi, grad)
+//   connectivity table of addFunction        -> dg_build_cells  (GPU)  replaces the serial loop :833-886
+//
+// m_nodes / m_cells / m_cell_map hold exactly what the reference would have produced, so save()/load() stay
+// byte-compatible (.cdf/.cdm, :678-778) and reduceField() (host bookkeeping, restated from :1065-1174) keeps working.
+// Device copies of fields are caches owned by this object, dropped by addFunction / load / reduceField.
+//
+// addFunction takes the reference's opaque std::function.  Functors of the two types the reference's own tools build are
+// recognised with std::function::target<>() and run on the GPU.  Any other callable cannot run on a GPU: it throws
+// std::invalid_argument unless DISCREGRID_B200_ALLOW_HOST_CALLBACK is defined, in which case YOUR callback is invoked
+// once per node on the host (node positions still come from the GPU); that path is never part of any reported number.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <set>
+#include <stdexcept>
+#include "discrete_grid.hpp"
+#include "geometry/TriangleMeshDistance.h"
+#include "discregrid_b200.h"
+
+#if defined(__GNUC__) && !defined(__clang__)
+#define DG_NO_CONTRACT __attribute__((optimize("fp-contract=off")))
+#else
+#define DG_NO_CONTRACT
+#endif
+
+namespace Discregrid {
+
+class CubicLagrangeDiscreteGrid;
+
+// GenerateDensityMap's density functor + sample predicate (cmd/generate_density_map/main.cpp:96-133) as a recognisable type
+struct DensityMapFunction {
+    const CubicLagrangeDiscreteGrid* grid;
+    unsigned int sdf_field_id;
+    double smoothing_length, rest_density;
+    bool no_reduction;
+    double operator()(Eigen::Vector3d const&) const { throw std::logic_error("DensityMapFunction is evaluated by addFunction on the GPU"); }
+};
+
+class CubicLagrangeDiscreteGrid : public DiscreteGrid {
+public:
+    CubicLagrangeDiscreteGrid(std::string const& filename) { load(filename); }
+    CubicLagrangeDiscreteGrid(Eigen::AlignedBox3d const& domain, std::array<unsigned int, 3> const& resolution) : DiscreteGrid(domain, resolution) {}
+    CubicLagrangeDiscreteGrid(const CubicLagrangeDiscreteGrid&) = delete;
+    CubicLagrangeDiscreteGrid& operator=(const CubicLagrangeDiscreteGrid&) = delete;
+    ~CubicLagrangeDiscreteGrid() override { invalidate(); }
+
+    // ---- save / load: byte layout of cubic_lagrange_discrete_grid.cpp:678-719 / 721-778 (serialize.hpp:12-25)
+    void save(std::string const& filename) const override
+    {
+        std::ofstream out(filename, std::ios::binary);
+        auto put = [&](const void* p, std::size_t n) { out.write(static_cast<const char*>(p), (std::streamsize)n); };
+        put(m_domain.min().data(), 24); put(m_domain.max().data(), 24);
+        put(m_resolution.data(), 12); put(m_cell_size.data(), 24); put(m_inv_cell_size.data(), 24);
+        put(&m_n_cells, 8); put(&m_n_fields, 8);
+        std::size_t n = m_nodes.size(); put(&n, 8);
+        for (auto const& v : m_nodes) { n = v.size(); put(&n, 8); put(v.data(), 8 * n); }
+        n = m_cells.size(); put(&n, 8);
+        for (auto const& v : m_cells) { n = v.size(); put(&n, 8); put(v.data(), 128 * n); }
+        n = m_cell_map.size(); put(&n, 8);
+        for (auto const& v : m_cell_map) { n = v.size(); put(&n, 8); put(v.data(), 4 * n); }
+    }
+    void load(std::string const& filename) override
+    {
+        invalidate();
+        std::ifstream in(filename, std::ios::binary);
+        if (!in.good()) { std::cerr << "ERROR: Discrete grid can not be loaded. Input file does not exist!" << std::endl; return; }
+        auto get = [&](void* p, std::size_t n) { in.read(static_cast<char*>(p), (std::streamsize)n); };
+        get(m_domain.min().data(), 24); get(m_domain.max().data(), 24);
+        get(m_resolution.data(), 12); get(m_cell_size.data(), 24); get(m_inv_cell_size.data(), 24);
+        get(&m_n_cells, 8); get(&m_n_fields, 8);
+        std::size_t n = 0; get(&n, 8); m_nodes.resize(n);
+        for (auto& v : m_nodes) { get(&n, 8); v.resize(n); get(v.data(), 8 * n); }
+        get(&n, 8); m_cells.resize(n);
+        for (auto& v : m_cells) { get(&n, 8); v.resize(n); get(v.data(), 128 * n); }
+        get(&n, 8); m_cell_map.resize(n);
+        for (auto& v : m_cell_map) { get(&n, 8); v.resize(n); get(v.data(), 4 * n); }
+    }
+
+    // ---- addFunction (cubic_lagrange_discrete_grid.cpp:780-899)
+    unsigned int addFunction(ContinuousFunction const& func, bool verbose = false, SamplePredicate const& pred = nullptr) override
+    {
+        const dg_grid_desc d = desc();
+        std::uint64_t n_nodes = 0;
+        check(dg_grid_num_nodes(d.resolution, &n_nodes));
+        std::vector<double> coeffs(n_nodes);
+        if (auto const* sdf = func.target<MeshSignedDistanceFunction>()) {
+            if (pred) throw std::invalid_argument("addFunction: a sample predicate is only supported with DensityMapFunction");
+            check(dg_sample_sdf(sdf->md->handle(), &d, sdf->sign, 0, n_nodes, coeffs.data()));
+        } else if (auto const* dm = func.target<DensityMapFunction>()) {
+            check(dg_density_map(dm->grid->deviceField(dm->sdf_field_id), dm->smoothing_length, dm->rest_density, dm->no_reduction ? 1 : 0,
+                                 0, n_nodes, coeffs.data()));
+        } else {
+#ifdef DISCREGRID_B200_ALLOW_HOST_CALLBACK
+            std::vector<double> x(3 * n_nodes);
+            check(dg_node_positions(&d, 0, n_nodes, x.data()));
+            for (std::uint64_t l = 0; l < n_nodes; l++) {
+                const Eigen::Vector3d p(x[3 * l], x[3 * l + 1], x[3 * l + 2]);
+                coeffs[l] = (!pred || pred(p)) ? func(p) : std::numeric_limits<double>::max();
+            }
+#else
+            (void)pred;
+            throw std::invalid_argument("CubicLagrangeDiscreteGrid::addFunction: only MeshSignedDistanceFunction / DensityMapFunction run on the GPU "
+                                        "(define DISCREGRID_B200_ALLOW_HOST_CALLBACK to have other callables invoked per node on the host)");
+#endif
+        }
+        if (verbose) std::cout << "Construction: " << n_nodes << " nodes sampled on the GPU" << std::endl;
+        return addSampledFunction(std::move(coeffs));
+    }
+    // appends a field from node values + the closed-form connectivity (:833-886, built on the GPU) + identity cell map (:888-891)
+    unsigned int addSampledFunction(std::vector<double> coeffs)
+    {
+        invalidate();
+        m_nodes.push_back(std::move(coeffs));
+        m_cells.emplace_back(m_n_cells);
+        check(dg_build_cells(m_resolution.data(), 0, m_n_cells, reinterpret_cast<std::uint32_t*>(m_cells.back().data())));
+        m_cell_map.emplace_back(m_n_cells);
+        std::iota(m_cell_map.back().begin(), m_cell_map.back().end(), 0u);
+        return static_cast<unsigned int>(m_n_fields++);
+    }
+
+    std::size_t nCells() const { return m_n_cells; }
+
+    // ---- interpolate (cubic_lagrange_discrete_grid.cpp:977-1063), scalar form kept for source compatibility
+    double interpolate(unsigned int field_id, Eigen::Vector3d const& xi, Eigen::Vector3d* gradient = nullptr) const override
+    {
+        double phi = 0.0, g[3] = {0, 0, 0};
+        // the reference leaves *gradient untouched when it returns DBL_MAX before the loop (:981-982, :993-994)
+        check(dg_interpolate_batch(deviceField(field_id), xi.data(), 1, &phi, gradient ? g : nullptr));
+        if (gradient && !(phi == std::numeric_limits<double>::max() && !in_kept_cell(field_id, xi))) *gradient = Eigen::Vector3d(g[0], g[1], g[2]);
+        return phi;
+    }
+    // batched form (new; the one to use): x = n x 3, phi = n, grad = n x 3 or nullptr
+    void interpolate(unsigned int field_id, std::size_t n, const double* x, double* phi, double* grad = nullptr) const
+    {
+        check(dg_interpolate_batch(deviceField(field_id), x, n, phi, grad));
+    }
+
+    // ---- split API (:901-975): shape functions on the GPU (dg_shape_functions), index algebra on the host
+    DG_NO_CONTRACT bool determineShapeFunctions(unsigned int field_id, Eigen::Vector3d const& x, std::array<unsigned int, 32>& cell, Eigen::Vector3d& c0,
+                                                Eigen::Matrix<double, 32, 1>& N, Eigen::Matrix<double, 32, 3>* dN = nullptr) const override
+    {
+        if (!m_domain.contains(x)) return false;
+        unsigned mi[3];
+        for (int d = 0; d < 3; d++) {
+            mi[d] = static_cast<unsigned int>((x[d] - m_domain.min()[d]) * m_inv_cell_size[d]);
+            if (mi[d] >= m_resolution[d]) mi[d] = m_resolution[d] - 1;
+        }
+        const unsigned i = multiToSingleIndex({{mi[0], mi[1], mi[2]}});
+        const unsigned i_ = m_cell_map[field_id][i];
+        if (i_ == std::numeric_limits<unsigned int>::max()) return false;
+        double xi[3];
+        for (int d = 0; d < 3; d++) {
+            const double lo = m_domain.min()[d] + static_cast<double>(mi[d]) * m_cell_size[d];
+            const double hi = lo + m_cell_size[d];
+            const double denom = hi - lo;
+            c0[d] = 2.0 / denom;
+            const double c1 = (hi + lo) / denom;
+            xi[d] = c0[d] * x[d] - c1;
+        }
+        cell = m_cells[field_id][i_];
+        double Nb[32], dNb[96];
+        check(dg_shape_functions(xi, 1, Nb, dN ? dNb : nullptr));
+        for (int j = 0; j < 32; j++) N[j] = Nb[j];
+        if (dN) for (int j = 0; j < 32; j++) for (int d = 0; d < 3; d++) (*dN)(j, d) = dNb[3 * j + d];
+        return true;
+    }
+    DG_NO_CONTRACT double interpolate(unsigned int field_id, Eigen::Vector3d const&, const std::array<unsigned int, 32>& cell, const Eigen::Vector3d& c0,
+                                      const Eigen::Matrix<double, 32, 1>& N, Eigen::Vector3d* gradient = nullptr, Eigen::Matrix<double, 32, 3>* dN = nullptr) const override
+    {
+        double phi = 0.0;
+        if (gradient) gradient->setZero();
+        for (unsigned j = 0; j < 32u; ++j) {
+            const double c = m_nodes[field_id][cell[j]];
+            if (c == std::numeric_limits<double>::max()) { if (gradient) gradient->setZero(); return std::numeric_limits<double>::max(); }
+            phi = phi + c * N[j];
+            if (gradient) for (int d = 0; d < 3; d++) (*gradient)[d] = (*gradient)[d] + c * (*dN)(j, d);
+        }
+        if (gradient) for (int d = 0; d < 3; d++) (*gradient)[d] = (*gradient)[d] * c0[d];
+        return phi;
+    }
+
+    // ---- reduceField (:1065-1174): host bookkeeping, same resulting members (kept cells in order, surviving nodes
+    // compacted by swap-with-last from the back, then sorted by the Morton value of their position)
+    void reduceField(unsigned int field_id, Predicate pred) override;
+
+    void forEachCell(unsigned int, std::function<void(unsigned int, Eigen::AlignedBox3d const&, unsigned int)> const& cb) const
+    {
+        const unsigned n = m_resolution[0] * m_resolution[1] * m_resolution[2];
+        for (unsigned i = 0; i < n; ++i) cb(i, subdomain(i), 0);
+    }
+
+    // ---- accessors used by tools / tests
+    std::vector<double> const& nodeData(unsigned int f) const { return m_nodes[f]; }
+    std::vector<std::array<unsigned int, 32>> const& cellData(unsigned int f) const { return m_cells[f]; }
+    std::vector<unsigned int> const& cellMap(unsigned int f) const { return m_cell_map[f]; }
+    std::size_t nFields() const { return m_n_fields; }
+    dg_grid_desc desc() const
+    {
+        dg_grid_desc d; std::memset(&d, 0, sizeof d);
+        for (int k = 0; k < 3; k++) { d.domain_min[k] = m_domain.min()[k]; d.domain_max[k] = m_domain.max()[k]; d.resolution[k] = m_resolution[k];
+                                      d.cell_size[k] = m_cell_size[k]; d.inv_cell_size[k] = m_inv_cell_size[k]; }
+        return d;
+    }
+    const dg_field* deviceField(unsigned int field_id) const
+    {
+        auto it = m_dev.find(field_id);
+        if (it != m_dev.end()) return it->second;
+        const dg_grid_desc d = desc();
+        dg_field* f = nullptr;
+        check(dg_field_create(&d, m_nodes.at(field_id).data(), m_nodes[field_id].size(), reinterpret_cast<const std::uint32_t*>(m_cells[field_id].data()),
+                              m_cells[field_id].size(), m_cell_map[field_id].data(), &f));
+        m_dev[field_id] = f;
+        return f;
+    }
+
+private:
+    std::vector<std::vector<double>> m_nodes;
+    std::vector<std::vector<std::array<unsigned int, 32>>> m_cells;
+    std::vector<std::vector<unsigned int>> m_cell_map;
+    mutable std::map<unsigned int, dg_field*> m_dev;
+
+    static void check(int rc) { if (rc != DG_OK) throw std::runtime_error(std::string("discregrid_b200: ") + dg_last_error()); }
+    void invalidate() { for (auto& kv : m_dev) dg_field_destroy(kv.second); m_dev.clear(); }
+    bool in_kept_cell(unsigned int field_id, Eigen::Vector3d const& x) const
+    {
+        if (!m_domain.contains(x)) return false;
+        unsigned mi[3];
+        for (int d = 0; d < 3; d++) { mi[d] = static_cast<unsigned int>((x[d] - m_domain.min()[d]) * m_inv_cell_size[d]); if (mi[d] >= m_resolution[d]) mi[d] = m_resolution[d] - 1; }
+        return m_cell_map[field_id][multiToSingleIndex({{mi[0], mi[1], mi[2]}})] != std::numeric_limits<unsigned int>::max();
+    }
+    // Z-order key of reduceField.  The reference's morton_lut (src/data/z_sort_table.hpp:119-134) shifts its first stage by
+    // 48 and then by 24 bits, so the top byte of each coordinate falls off the 64-bit word: the key interleaves only the
+    // LOW 16 BITS of x, y, z (x at bit 0).  Reproduced as is -- the node order in a reduced .cdm depends on it.
+    static std::uint64_t morton3(std::uint32_t x, std::uint32_t y, std::uint32_t z)
+    {
+        auto spread = [](std::uint64_t v) { v &= 0xffff; v = (v | v << 16) & 0x0000ff0000ffull; v = (v | v << 8) & 0x00f00f00f00full;
+                                            v = (v | v << 4) & 0x0c30c30c30c3ull; v = (v | v << 2) & 0x249249249249ull; return v; };
+        return spread(x) | (spread(y) << 1) | (spread(z) << 2);
+    }
+};
+
+inline void CubicLagrangeDiscreteGrid::reduceField(unsigned int field_id, Predicate pred)
+{
+    invalidate();
+    auto& coeffs = m_nodes[field_id];
+    auto& cells = m_cells[field_id];
+    const dg_grid_desc d = desc();
+    std::vector<double> pos(3 * coeffs.size());
+    check(dg_node_positions(&d, 0, coeffs.size(), pos.data()));              // indexToNodePosition for every node (:604-665)
+    const double dbl_max = std::numeric_limits<double>::max();
+    std::vector<char> keep(coeffs.size());
+    for (std::size_t l = 0; l < coeffs.size(); ++l)
+        keep[l] = pred(Eigen::Vector3d(pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]), coeffs[l]) && coeffs[l] != dbl_max;
+    auto& cell_map = m_cell_map[field_id];
+    cell_map.assign(m_n_cells, 0u);
+    std::vector<std::array<unsigned int, 32>> kept;
+    for (std::size_t i = 0; i < cells.size(); ++i) {                          // a cell survives if any of its nodes does
+        bool any = false;
+        for (auto v : cells[i]) any = any || keep[v];
+        if (any) { kept.push_back(cells[i]); cell_map[i] = static_cast<unsigned int>(kept.size() - 1); }
+        else cell_map[i] = std::numeric_limits<unsigned int>::max();
+    }
+    cells.swap(kept);
+    // Morton key of every node position: zValue(x, 4 * min(inv_cell)) (:583-601, :1114)
+    const double inv = 4.0 * std::min(std::min(m_inv_cell_size[0], m_inv_cell_size[1]), m_inv_cell_size[2]);
+    std::vector<std::uint64_t> zval(coeffs.size());
+    for (std::size_t l = 0; l < coeffs.size(); ++l) {
+        std::uint32_t p[3];
+        for (int k = 0; k < 3; k++) {
+            const double xk = pos[3 * l + k];
+            const int key = (xk >= 0.0) ? static_cast<int>(inv * xk) : static_cast<int>(inv * xk) - 1;
+            p[k] = static_cast<std::uint32_t>(static_cast<std::int64_t>(key) - (std::numeric_limits<int>::lowest() + 1));
+        }
+        zval[l] = morton3(p[0], p[1], p[2]);
+    }
+    // nodes referenced by surviving cells, with back-references (cell, slot)
+    std::fill(keep.begin(), keep.end(), 0);
+    std::vector<std::set<std::pair<unsigned int, unsigned int>>> users(coeffs.size());
+    for (unsigned c = 0; c < cells.size(); ++c)
+        for (unsigned j = 0; j < 32; ++j) { keep[cells[c][j]] = 1; users[cells[c][j]].insert({c, j}); }
+    unsigned last = static_cast<unsigned>(coeffs.size() - 1);
+    for (int i = static_cast<int>(coeffs.size()) - 1; i >= 0; --i) {          // compaction by swap-with-last, from the back
+        if (keep[i]) continue;
+        std::swap(coeffs[i], coeffs[last]); std::swap(zval[i], zval[last]); std::swap(users[i], users[last]);
+        for (auto const& u : users[i]) cells[u.first][u.second] = static_cast<unsigned>(i);
+        for (auto const& u : users[last]) cells[u.first][u.second] = last;
+        last--;
+    }
+    coeffs.resize(last + 1); zval.resize(coeffs.size());
+    std::vector<unsigned int> order(coeffs.size());
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return zval[a] < zval[b]; });
+    for (unsigned i = 0; i < order.size(); ++i)
+        for (auto const& u : users[order[i]]) cells[u.first][u.second] = i;
+    std::vector<double> sorted(coeffs.size());
+    for (unsigned i = 0; i < order.size(); ++i) sorted[i] = coeffs[order[i]];
+    coeffs.swap(sorted);
+}
+
+}  // namespace Discregrid

@@ -66,7 +66,11 @@ class TriangleMeshDistance:
             capi.lib.dg_mesh_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def info(self):
         a = (C.c_uint64 * 8)()

@@ -52,3 +52,41 @@ def allgather_rows(full, sharding, group=None):
     for j in range(sharding.rows):
         row = full[j * w * c:(j + 1) * w * c]
         dist.all_gather_into_tensor(row, row[rank * c:(rank + 1) * c].clone() if row.device.type == "cpu" else row[rank * c:(rank + 1) * c], group=group)
+
+
+class ShardedSdfSampler:
+    """addFunction's node loop for one rank of a one-process-per-GPU job: this rank's chunks are launched round-robin on a
+    few side streams (a K1 launch ends with a ~2 ms tail of long-running warps; concurrent launches hide each other's
+    tails), joined, then the rows are all-gathered.  Plumbing only: the kernels are the C-ABI's dg_sample_sdf_device."""
+
+    def __init__(self, md, desc, sharding, rank, n_streams=4):
+        import torch
+        self.md, self.desc, self.sh, self.rank = md, desc, sharding, rank
+        self.chunks = [(j, b, e) for (j, b, e) in sharding.chunks_of(rank) if e > b]
+        self.streams = [torch.cuda.Stream() for _ in range(min(n_streams, max(1, len(self.chunks))))] if len(self.chunks) > 1 else []
+
+    def launch(self, full, sign=1.0):
+        """enqueue this rank's kernels; `full` = fp64 CUDA tensor of sharding.padded elements; returns #launches"""
+        import ctypes as C
+        import torch
+        from . import _capi as capi
+        cur = torch.cuda.current_stream()
+        if not self.streams:
+            for (_j, b, e) in self.chunks:
+                capi.check(capi.lib.dg_sample_sdf_device(self.md.handle, C.byref(self.desc), sign, b, e,
+                                                         C.c_void_p(full.data_ptr() + 8 * b), C.c_void_p(cur.cuda_stream)))
+            return len(self.chunks)
+        for st in self.streams:
+            st.wait_stream(cur)
+        for k, (_j, b, e) in enumerate(self.chunks):
+            st = self.streams[k % len(self.streams)]
+            capi.check(capi.lib.dg_sample_sdf_device(self.md.handle, C.byref(self.desc), sign, b, e,
+                                                     C.c_void_p(full.data_ptr() + 8 * b), C.c_void_p(st.cuda_stream)))
+        for st in self.streams:
+            cur.wait_stream(st)
+        return len(self.chunks)
+
+    def step(self, full, sign=1.0, group=None):
+        n = self.launch(full, sign)
+        allgather_rows(full, self.sh, group)
+        return n
