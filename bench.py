@@ -240,10 +240,10 @@ def main():
     my_chunks = [(j, b, e) for (j, b, e) in sh.chunks_of(rank)]
     stream = torch.cuda.current_stream()
 
-    sampler = ShardedSdfSampler(md, desc, sh, rank)
+    sdf_sampler = ShardedSdfSampler(md, desc, sh, rank)
 
     def sdf_step():
-        sampler.step(full)
+        sdf_sampler.step(full)
 
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
@@ -273,7 +273,7 @@ def main():
 
     # kernel-only time of K1 on this rank (no collective): what the roofline object refers to
     def k1_only():
-        sampler.launch(full)
+        sdf_sampler.launch(full)
     k1_ms, _ = timed(k1_only, max(3, args.steps // 2), 1)
     k1_ms = float(np.mean(k1_ms))
     my_nodes = sum(e - b for (_j, b, e) in my_chunks)

@@ -80,7 +80,7 @@ struct Builder {
 bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err)
 {
     if (!Vd || !F || nT == 0 || nV == 0) { *err = "empty triangle list or vertex list"; return false; }
-    if (nT >= (1ull << 26) || nV > (uint64_t)0x7fffffff) { *err = "mesh too large (< 2^26 triangles; int32 vertex indices as in the reference)"; return false; }
+    if (nT >= (1ull << 25) || nV > (uint64_t)0x7fffffff) { *err = "mesh too large (< 2^25 triangles; int32 vertex indices as in the reference)"; return false; }
     for (uint64_t i = 0; i < 3 * nT; i++) if (F[i] >= nV) { *err = "triangle index out of range"; return false; }
     const P3* V = reinterpret_cast<const P3*>(Vd);
     const int T = (int)nT;
@@ -133,6 +133,21 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
     }
     out.flags = 0;
     for (const auto& kv : edges) { if (kv.second.count == 1) out.flags |= 1; else if (kv.second.count > 2) out.flags |= 2; }
+
+    // ---- fp32 shadow of the sphere pairs (filter only), relative to the bounding-box centre
+    {
+        double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (uint64_t i = 0; i < nV; i++) for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], Vd[3 * i + d]); hi[d] = std::max(hi[d], Vd[3 * i + d]); }
+        out.half_extent = 0;
+        for (int d = 0; d < 3; d++) { out.center[d] = 0.5 * (lo[d] + hi[d]); out.half_extent = std::max(out.half_extent, std::max(hi[d] - out.center[d], out.center[d] - lo[d])); }
+        out.spheres_f.assign(nT, SpherePairF());
+        for (uint64_t m = 0; m < nT; m++) {
+            const SpherePair& sp = out.spheres[m];
+            SpherePairF& f = out.spheres_f[m];
+            for (int d = 0; d < 3; d++) { f.lc[d] = (float)(sp.lc[d] - out.center[d]); f.rc[d] = (float)(sp.rc[d] - out.center[d]); }
+            f.lr = (float)sp.lr; f.rr = (float)sp.rr;
+        }
+    }
 
     // ---- device records in leaf order
     out.leaves.assign(nT, LeafRecord());

@@ -27,6 +27,14 @@ struct alignas(64) SpherePair {   // children of the internal node whose split p
 };
 static_assert(sizeof(SpherePair) == 64, "SpherePair must be 64 bytes");
 
+// fp32 shadow of SpherePair, relative to HostBvh::center: used only to FILTER traversal decisions (k1_sdf.cu); every decision
+// the fp32 interval cannot certify is re-taken from the fp64 record, so results do not depend on these values.
+struct alignas(32) SpherePairF {
+    float lc[3], lr;
+    float rc[3], rr;
+};
+static_assert(sizeof(SpherePairF) == 32, "SpherePairF must be 32 bytes");
+
 struct alignas(128) LeafRecord {
     double v0[3];
     double e0[3];
@@ -44,6 +52,9 @@ static_assert(sizeof(PseudoNormals) == 168, "PseudoNormals must be 168 bytes");
 struct HostBvh {
     uint64_t n_vertices = 0, n_triangles = 0;
     std::vector<SpherePair> spheres;        // [T]  (index 0 unused)
+    std::vector<SpherePairF> spheres_f;     // [T]  fp32 shadow, relative to `center`
+    double center[3] = {0, 0, 0};           // bounding-box centre of the vertices
+    double half_extent = 0;                 // max |v - center|_inf over the vertices
     std::vector<LeafRecord> leaves;         // [T]
     std::vector<PseudoNormals> normals;     // [T]
     std::vector<int32_t> order;             // leaf position -> triangle id

@@ -163,55 +163,159 @@ __device__ __forceinline__ void finish_query(const LeafRecord* __restrict__ leav
 // covers either floor(T/2^k) or that + 1 leaves (halving splits), so (begin, depth, +1 flag) identifies the range.
 // Layout [depth][lane] in shared memory: conflict-free whatever depth each lane is at.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned pack_range(int b, int e, int depth, int n_tri)
+// Stack entry = 8 bytes: the sibling's sphere distance rounded to fp32 + its leaf range packed in 32 bits.  A node at depth k
+// covers either floor(T/2^k) or that + 1 leaves (halving splits), so (begin, depth, +1 flag) identifies the range; bit 31
+// says whether the entry is its parent's LEFT child (needed to find its fp64 sphere again when the fp32 value cannot decide).
+__device__ __forceinline__ unsigned pack_range(int b, int e, int depth, int n_tri, bool is_left)
 {
-    return (unsigned)b | ((unsigned)depth << 26) | ((unsigned)((e - b) - (n_tri >> depth)) << 31);
+    return (unsigned)b | ((unsigned)depth << 25) | ((unsigned)((e - b) - (n_tri >> depth)) << 30) | ((unsigned)is_left << 31);
 }
 
-__device__ __forceinline__ QueryResult nearest_triangle(const SpherePair* __restrict__ spheres,
-                                                        const LeafRecord* __restrict__ leaves, int n_tri, bool alive,
-                                                        double px, double py, double pz,
-                                                        unsigned* stack_rng, double* stack_d, int stride)
+// fp64 sphere distance exactly as the reference computes it (TriangleMeshDistance.h:539-540)
+__device__ __forceinline__ double sphere_dist(double px, double py, double pz, double cx, double cy, double cz, double r)
+{
+    const double x = px - cx, y = py - cy, z = pz - cz;
+    return sqrt(x * x + y * y + z * z) - r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP32 INTERVAL FILTER (K1_FILTER).  The traversal only needs the sphere distances for three yes/no questions:
+// which child is nearer (:542), is a child nearer than the best so far (:545-557).  Both are decided from an fp32 shadow
+// of the spheres whenever the fp32 interval [d_f - E, d_f + E] -- which provably contains the reference's fp64 value -- lies
+// entirely on one side; otherwise (ties, near-ties: a few per thousand) the lane recomputes that node in fp64 exactly as the
+// reference does.  The decision taken is therefore ALWAYS the reference's decision, and every number that reaches the
+// output (best, d2, s, t) is still computed in fp64 in the leaf test: results stay bit-identical.
+//   Error bound.  Coordinates are taken relative to the mesh centre and rounded to fp32: |err| <= 2^-24 Mq per coordinate,
+//   Mq = max(mesh half extent, |p - ctr|_inf).  With D = |p - c| <= 2 sqrt(3) Mq and r <= 2 sqrt(3) Mq the fp32 value of
+//   sqrt(dx^2+dy^2+dz^2) - r differs from the real one by < 2^-24 (sqrt(3) 2 Mq + 8 D + r) < 35 * 2^-24 Mq (sqrt.approx: 2 ulp);
+//   the reference's own fp64 rounding adds < 1e-15 Mq.  E = 64 * 2^-24 * Mq.
+// The fp64 chains (two IEEE square roots per node, ~10 cycles per dependent instruction) were the critical path of the kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct MeshDev {
+    const SpherePair* spheres;
+    const SpherePairF* spheres_f;
+    const LeafRecord* leaves;
+    double cx, cy, cz;
+    float half_extent;
+    int n_tri;
+};
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// _query (TriangleMeshDistance.h:514-562), iterative and WARP-SYNCHRONOUS.
+//
+// All 32 lanes of a warp call this together, each with its own query (`alive`).  Every lane walks the tree in the
+// reference's own order with its own stack of deferred siblings, but the warp executes ONE PHASE per iteration, chosen
+// by ballot so that each straight-line block runs converged:
+//   NODE : lanes at an internal node: two sphere tests, then descend + defer the sibling, or prune
+//   LEAF : lanes at a leaf: point-triangle test, accept if strictly closer
+//   POP  : lanes that pruned / finished a leaf: re-test deferred siblings (`d < result.distance`, :549/:557)
+// The phase holding the largest cost-weighted share of lanes runs; the other lanes idle for that iteration.  All lanes
+// start at the root together and -- being 32 adjacent grid nodes -- take mostly the same decisions, so the phases stay
+// largely aligned.  (Letting a finished lane start its next query immediately was tried and is ~1.6x SLOWER: lanes
+// then sit at unrelated depths of the tree and both phase alignment and cache sharing are lost.)
+// Stack layout [depth][lane] in shared memory: conflict-free whatever depth each lane is at.
+__device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool alive, double px, double py, double pz,
+                                                        unsigned* stack_rng, float* stack_d, int stride)
 {
     enum { NODE = 0, LEAF = 1, POP = 2, DONE = 3 };
+    const int n_tri = M.n_tri;
     QueryResult res;
     res.dist = DBL_MAX; res.s = 0; res.t = 0; res.pos = -1; res.entity = 0;
     double best = DBL_MAX;             // result.distance
     double best_sq = best * best;      // result.distance * result.distance (= +inf initially), :528
+    float best_lo = __double2float_rd(best), best_hi = __double2float_ru(best);   // fp32 bracket of best
+    // query point relative to the mesh centre, in fp32, and the interval half-width for this query
+    const float qx = (float)(px - M.cx), qy = (float)(py - M.cy), qz = (float)(pz - M.cz);
+    const float Mq = fmaxf(fmaxf(M.half_extent, fabsf(qx)), fmaxf(fabsf(qy), fabsf(qz)));
+    // beyond ~1e18 the fp32 squares overflow: switch the filter off for such a query (E = inf leaves every test undecided)
+    const float E = (Mq < 1.0e18f) ? __fmul_ru(Mq, 3.814697265625e-06f) : __int_as_float(0x7f800000);     // 64 * 2^-24 * Mq
+    const float E2 = E + E;
     int b = 0, e = n_tri, depth = 0, sp = 0;
     int state = alive ? ((n_tri == 1) ? LEAF : NODE) : DONE;
     for (;;) {
         // two ballots carry the 2-bit state of all 32 lanes
         const unsigned bit0 = __ballot_sync(0xffffffffu, state & 1), bit1 = __ballot_sync(0xffffffffu, state & 2);
         if ((bit0 & bit1) == 0xffffffffu) break;                               // every lane DONE
-        const int n_node = __popc(~(bit0 | bit1)), n_leaf = __popc(bit0 & ~bit1);
-#if !K1_POP_MERGED
-        const int n_pop = __popc(~bit0 & bit1);
+        const int n_node = __popc(~(bit0 | bit1)), n_leaf = __popc(bit0 & ~bit1), n_pop = __popc(~bit0 & bit1);
         const bool pop_phase = K1_POP_WEIGHT * n_pop >= K1_NODE_WEIGHT * n_node && K1_POP_WEIGHT * n_pop >= K1_LEAF_WEIGHT * n_leaf;
-#else
-        const bool pop_phase = false;
-#endif
         if (pop_phase) {
+            if (state == POP) {
+                // deferred siblings: the reference's second `if (d < result.distance)` (:549, :557) with the updated best
+#pragma unroll 1
+                for (int attempt = 0; attempt < K1_POP_TRIES; attempt++) {
+                    if (sp == 0) { state = DONE; break; }
+                    sp--;
+                    const float df = stack_d[sp * stride];
+                    bool visit = (df + E < best_lo);                           // certainly d < best
+                    const bool skip = (df - E >= best_hi);                     // certainly d >= best
+                    if (!K1_FILTER || !(visit || skip)) {                      // undecided in fp32: the reference's fp64 value
+                        const unsigned r = stack_rng[sp * stride];
+                        const int rb = (int)(r & 0x01ffffffu), rd = (int)((r >> 25) & 31u);
+                        const int re = rb + (n_tri >> rd) + (int)((r >> 30) & 1u);
+                        const bool is_left = (r >> 31) != 0u;
+                        const double* s8 = reinterpret_cast<const double*>(M.spheres + (is_left ? re : rb)) + (is_left ? 0 : 4);
+                        const double2 c0 = ldg2(s8), c1 = ldg2(s8 + 2);
+                        visit = sphere_dist(px, py, pz, c0.x, c0.y, c1.x, c1.y) < best;
+                    }
+                    if (visit) {
+                        const unsigned r = stack_rng[sp * stride];
+                        b = (int)(r & 0x01ffffffu);
+                        depth = (int)((r >> 25) & 31u);
+                        e = b + (n_tri >> depth) + (int)((r >> 30) & 1u);
+                        state = (e - b == 1) ? LEAF : NODE;
+                        break;
+                    }
+                }
+            }
         } else if (n_node != 0 && K1_NODE_WEIGHT * n_node >= K1_LEAF_WEIGHT * n_leaf) {
             if (state == NODE) {                                                // internal (:537-561)
                 const int m = (b + e) >> 1;
-                const double* sp8 = reinterpret_cast<const double*>(spheres + m);
-                const double2 a0 = ldg2(sp8), a1 = ldg2(sp8 + 2), a2 = ldg2(sp8 + 4), a3 = ldg2(sp8 + 6);
-                const double lx = px - a0.x, ly = py - a0.y, lz = pz - a1.x;
-                const double rx = px - a2.x, ry = py - a2.y, rz = pz - a3.x;
-                const double d_left = sqrt(lx * lx + ly * ly + lz * lz) - a1.y;     // :539
-                const double d_right = sqrt(rx * rx + ry * ry + rz * rz) - a3.y;    // :540
-                const bool left_first = d_left < d_right;                           // :542
-                const double d_first = left_first ? d_left : d_right;
-                const double d_second = left_first ? d_right : d_left;
+                bool left_first, go_first, go_second = false;
+                float d_second_f;
+                bool decided = false;
+#if K1_FILTER
+                {
+                    const float4* f4 = reinterpret_cast<const float4*>(M.spheres_f + m);
+                    const float4 l4 = __ldg(f4), r4 = __ldg(f4 + 1);
+                    const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
+                    const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
+                    const float dl = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) - l4.w;
+                    const float dr = sqrt_approx(fmaf(rz, rz, fmaf(ry, ry, rx * rx))) - r4.w;
+                    left_first = dl < dr;
+                    const float d_first_f = left_first ? dl : dr;
+                    d_second_f = left_first ? dr : dl;
+                    const bool order_sure = (d_first_f + E2 < d_second_f);      // |dl - dr| > 2E
+                    go_first = (d_first_f + E < best_lo);                       // certainly d_first < best
+                    const bool skip_first = (d_first_f - E >= best_hi);         // certainly d_first >= best (then d_second >= best too)
+                    decided = order_sure && (go_first || skip_first);
+                }
+#endif
+                if (!decided) {                                                 // fp64, exactly the reference
+                    const double* sp8 = reinterpret_cast<const double*>(M.spheres + m);
+                    const double2 a0 = ldg2(sp8), a1 = ldg2(sp8 + 2), a2 = ldg2(sp8 + 4), a3 = ldg2(sp8 + 6);
+                    const double d_left = sphere_dist(px, py, pz, a0.x, a0.y, a1.x, a1.y);      // :539
+                    const double d_right = sphere_dist(px, py, pz, a2.x, a2.y, a3.x, a3.y);     // :540
+                    left_first = d_left < d_right;                                            // :542
+                    const double d_first = left_first ? d_left : d_right;
+                    const double d_second = left_first ? d_right : d_left;
+                    go_first = d_first < best;                                                // :545 / :554
+                    go_second = !go_first && (d_second < best);     // only reachable through NaNs; kept for fidelity (:549 / :557)
+                    d_second_f = (float)d_second;                   // |rounding| <= 2^-24 |d| << E: the stored value stays a valid filter input
+                }
                 depth++;
-                if (d_first < best) {                  // visit first now; second is re-tested when popped (:545-551)
-                    stack_rng[sp * stride] = left_first ? pack_range(m, e, depth, n_tri) : pack_range(b, m, depth, n_tri);
-                    stack_d[sp * stride] = d_second;
+                if (go_first) {                        // visit first now; second is re-tested when popped (:545-551)
+                    stack_rng[sp * stride] = left_first ? pack_range(m, e, depth, n_tri, false) : pack_range(b, m, depth, n_tri, true);
+                    stack_d[sp * stride] = d_second_f;
                     sp++;
                     if (left_first) e = m; else b = m;
                     state = (e - b == 1) ? LEAF : NODE;
-                } else if (d_second < best) {          // only reachable through NaNs; kept for fidelity
+                } else if (go_second) {
                     if (left_first) b = m; else e = m;
                     state = (e - b == 1) ? LEAF : NODE;
                 } else {
@@ -221,31 +325,14 @@ __device__ __forceinline__ QueryResult nearest_triangle(const SpherePair* __rest
         } else if (n_leaf != 0) {
             if (state == LEAF) {                                                // leaf (:517-534)
                 double s, t; int ent;
-                const double d2 = tri_dist2(leaves + b, px, py, pz, s, t, ent);
+                const double d2 = tri_dist2(M.leaves + b, px, py, pz, s, t, ent);
                 if (d2 < best_sq) {
                     best = sqrt(d2);
                     best_sq = best * best;
+                    best_lo = __double2float_rd(best); best_hi = __double2float_ru(best);
                     res.s = s; res.t = t; res.pos = b; res.entity = ent;
                 }
                 state = POP;
-            }
-        }
-        // deferred siblings: the reference's second `if (d < result.distance)` (:549, :557) with the updated best.
-        // Runs at the end of every iteration for the lanes that need it (those that just pruned / finished a leaf, and
-        // those still looking), so popping never costs an iteration of its own unless nobody else can move.
-        if (state == POP && (K1_POP_MERGED || pop_phase)) {
-#pragma unroll 1
-            for (int attempt = 0; attempt < K1_POP_TRIES; attempt++) {
-                if (sp == 0) { state = DONE; break; }
-                sp--;
-                if (stack_d[sp * stride] < best) {
-                    const unsigned r = stack_rng[sp * stride];
-                    b = (int)(r & 0x03ffffffu);
-                    depth = (int)((r >> 26) & 31u);
-                    e = b + (n_tri >> depth) + (int)(r >> 31);
-                    state = (e - b == 1) ? LEAF : NODE;
-                    break;
-                }
             }
         }
     }
@@ -261,12 +348,11 @@ extern __shared__ __align__(16) unsigned char k1_smem[];
 // fast axis, so the 32 queries of a warp are spatial neighbours: they visit nearly the same tree nodes (L1 hits) and
 // take similar numbers of steps.  Whole slow-planes are covered; nodes outside [l_begin, l_end) are masked.
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
-sdf_sample_nodes_kernel(const SpherePair* __restrict__ spheres, const LeafRecord* __restrict__ leaves,
-                        const PseudoNormals* __restrict__ normals, int n_tri, int stack_depth, GridDev g, K1Work w, double sign,
+sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals, int stack_depth, GridDev g, K1Work w, double sign,
                         double* __restrict__ out)
 {
-    double* stack_d = reinterpret_cast<double*>(k1_smem);
-    unsigned* stack_rng = reinterpret_cast<unsigned*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(double));
+    float* stack_d = reinterpret_cast<float*>(k1_smem);
+    unsigned* stack_rng = reinterpret_cast<unsigned*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(float));
     // which segment does this block belong to (<= 4, uniform per block)
     int sg = 0;
 #pragma unroll
@@ -297,33 +383,30 @@ sdf_sample_nodes_kernel(const SpherePair* __restrict__ spheres, const LeafRecord
     else if (S.kind == 2) py = py + fr * g.cell[1];
     else if (S.kind == 3) pz = pz + fr * g.cell[2];
 
-    const QueryResult r = nearest_triangle(spheres, leaves, n_tri, alive, px, py, pz, stack_rng + threadIdx.x,
-                                           stack_d + threadIdx.x, K1_THREADS);
+    const QueryResult r = nearest_triangle(mesh, alive, px, py, pz, stack_rng + threadIdx.x, stack_d + threadIdx.x, K1_THREADS);
     if (!alive) return;
     double dist, qx, qy, qz; int tri;
-    finish_query(leaves, normals, r, px, py, pz, true, dist, qx, qy, qz, tri);
+    finish_query(mesh.leaves, normals, r, px, py, pz, true, dist, qx, qy, qz, tri);
     out[l - w.l_begin] = (sign == 1.0) ? dist : sign * dist;     // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
 }
 
 // batched TriangleMeshDistance::{signed,unsigned}_distance on arbitrary points (a warp = 32 consecutive points)
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
-mesh_distance_kernel(const SpherePair* __restrict__ spheres, const LeafRecord* __restrict__ leaves,
-                     const PseudoNormals* __restrict__ normals, int n_tri, int stack_depth,
+mesh_distance_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals, int stack_depth,
                      const double* __restrict__ pts, unsigned long long count, int is_signed,
                      double* __restrict__ dist_out, double* __restrict__ near_out, int* __restrict__ ent_out,
                      int* __restrict__ tri_out)
 {
-    double* stack_d = reinterpret_cast<double*>(k1_smem);
-    unsigned* stack_rng = reinterpret_cast<unsigned*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(double));
+    float* stack_d = reinterpret_cast<float*>(k1_smem);
+    unsigned* stack_rng = reinterpret_cast<unsigned*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(float));
     const unsigned long long idx = (unsigned long long)blockIdx.x * K1_THREADS + threadIdx.x;
     const bool alive = idx < count;
     const unsigned long long ix = alive ? idx : 0ull;
     const double px = pts[3 * ix], py = pts[3 * ix + 1], pz = pts[3 * ix + 2];
-    const QueryResult r = nearest_triangle(spheres, leaves, n_tri, alive, px, py, pz, stack_rng + threadIdx.x,
-                                           stack_d + threadIdx.x, K1_THREADS);
+    const QueryResult r = nearest_triangle(mesh, alive, px, py, pz, stack_rng + threadIdx.x, stack_d + threadIdx.x, K1_THREADS);
     if (!alive) return;
     double dist, qx, qy, qz; int tri;
-    finish_query(leaves, normals, r, px, py, pz, is_signed != 0, dist, qx, qy, qz, tri);
+    finish_query(mesh.leaves, normals, r, px, py, pz, is_signed != 0, dist, qx, qy, qz, tri);
     if (dist_out) dist_out[idx] = dist;
     if (near_out) { near_out[3 * idx] = qx; near_out[3 * idx + 1] = qy; near_out[3 * idx + 2] = qz; }
     if (ent_out) ent_out[idx] = r.entity;
@@ -355,7 +438,8 @@ __global__ void fma_probe_kernel(double a, double b, double c, double* out) { ou
 
 }  // namespace
 
-static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(double) + sizeof(unsigned)); }
+static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)); }
+static inline MeshDev mesh_dev(const DeviceBvh& m) { return MeshDev{m.spheres, m.spheres_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri}; }
 
 cudaError_t k1_configure(int stack_depth)
 {
@@ -396,7 +480,7 @@ cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double 
     }
     for (int k = w.nseg; k < 4; k++) { w.seg[k] = w.seg[0]; w.seg[k].block_begin = 0xffffffffu; }
     sdf_sample_nodes_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(
-        m.spheres, m.leaves, m.normals, m.n_tri, m.stack_depth, g, w, sign, d_out);
+        mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_out);
     return cudaGetLastError();
 }
 
@@ -406,8 +490,7 @@ cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t
     if (count == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((count + K1_THREADS - 1) / K1_THREADS);
     mesh_distance_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(
-        m.spheres, m.leaves, m.normals, m.n_tri, m.stack_depth, d_pts, (unsigned long long)count, is_signed, d_dist, d_near,
-        d_ent, d_tri);
+        mesh_dev(m), m.normals, m.stack_depth, d_pts, (unsigned long long)count, is_signed, d_dist, d_near, d_ent, d_tri);
     return cudaGetLastError();
 }
 

@@ -30,6 +30,9 @@ constexpr int K1_THREADS = K1_THREADS_PER_BLOCK;
 #ifndef K1_LEAF_PIN
 #define K1_LEAF_PIN 0           // 1: force the single-division branch-free leaf arithmetic (see tri_dist2)
 #endif
+#ifndef K1_FILTER
+#define K1_FILTER 1             // 1: fp32 interval filter for the sphere decisions (exact fp64 fallback); 0: all fp64
+#endif
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS (1024 / K1_THREADS_PER_BLOCK)   // blocks per SM the register allocation must allow (32 warps)
 #endif
@@ -50,6 +53,9 @@ struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once b
     const SpherePair* spheres = nullptr;
     const LeafRecord* leaves = nullptr;
     const PseudoNormals* normals = nullptr;
+    const SpherePairF* spheres_f = nullptr;   // fp32 filter shadow (relative to ctr)
+    double ctr[3] = {0, 0, 0};
+    float half_extent = 0.f;
     int n_tri = 0;
     int stack_depth = 1;           // deferred-sibling slots per lane (= tree levels - 1, at least 1)
 };
