@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-interp", action="store_true", help="skip the interpolate half (diagnostics / profiling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (diagnostics / profiling)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (diagnostics / profiling)")
+    ap.add_argument("--no-density", action="store_true", help="skip the density-map (K3) leg (diagnostics / profiling)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -366,6 +367,43 @@ def main():
                           "api": "dg_interpolate_batch(field, x_host, n, phi_host, grad_host)"}}
         capi.lib.dg_field_destroy(fh)
 
+    # ---------------------------------------------------------------- density map (config 5 kernel), N = 1 only
+    density = None
+    if world == 1 and not args.no_density:
+        sdf_sampler.launch(full); torch.cuda.synchronize()
+        fh = C.c_void_p()
+        sp = C.c_void_p(stream.cuda_stream)
+        capi.check(capi.lib.dg_field_create_device(C.byref(desc), C.c_void_p(full.data_ptr()), n_nodes, sp, C.byref(fh)))
+        dens = torch.empty(n_nodes, dtype=torch.float64, device=dev)
+        h_dm = 0.1 * float(np.max(mx - mn)) / 2.5            # the reference default h = 0.1 is for a ~2.5-unit dragon
+        def dm_step():
+            capi.check(capi.lib.dg_density_map_device(fh, h_dm, 1000.0, 0, 0, n_nodes, C.c_void_p(dens.data_ptr()), sp))
+        dm_ms, _ = timed(dm_step, 2, 1)
+        dm_ms = float(np.mean(dm_ms))
+        dens_h = dens.cpu().numpy()
+        active = int(((dens_h > 0) & (dens_h < 1e300)).sum())
+        density = {"metric": "GenerateDensityMap nodes/s (K3)", "value": n_nodes / (dm_ms * 1e-3), "unit": "nodes/s", "ms": dm_ms,
+                   "config": {"workload": f"density_func + predicate over the {res[0]}^3 SDF above, h = {h_dm:.4f}, rho0 = 1000, 16^3 Gauss points",
+                              "nodes_in_quadrature_branch": active}}
+        if not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from oracle_api import Oracle
+            orc = Oracle()
+            gd, r = orc.grid_desc(mn, mx, res)
+            coeff_h = full[:n_nodes].cpu().numpy()
+            t_cpu, n_cpu, ok = 0.0, 0, True
+            for k in range(8):                                 # eight 192-node windows spread over the node index space
+                l0 = int((k + 0.5) * n_nodes / 8); l1 = l0 + 192
+                t0 = time.perf_counter()
+                ref = orc.density_map(gd, r, coeff_h, h_dm, 1000.0, False, l0, l1)
+                t_cpu += time.perf_counter() - t0; n_cpu += l1 - l0
+                ok = ok and np.array_equal(ref.view(np.uint64), dens_h[l0:l1].view(np.uint64))
+            density["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "nodes/s", "kind": "port", "cores": orc.max_threads(),
+                                       "sample": f"{n_cpu} nodes in 8 windows, oracle/dg_oracle.cpp (the reference tool needs Eigen)",
+                                       "bit_exact_vs_gpu": bool(ok)}
+        capi.lib.dg_field_destroy(fh)
+        del dens
+
     # ---------------------------------------------------------------- CPU baseline, rank 0, N = 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -376,7 +414,7 @@ def main():
         line = {"metric": "SDF grid nodes/sec (addFunction)", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp,
+                "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "density_map": density,
                 "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms}}
         print(json.dumps(line))
     if world > 1:

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -376,6 +377,63 @@ int dg_sample_sdf_device(const dg_mesh* m, const dg_grid_desc* grid, double sign
     return DG_OK;
 }
 
+// Host-buffer path of K1.  Resources that are expensive to create per call (device scratch, two pinned staging buffers,
+// streams, events) live in a per-process pool.  The range is cut into a few kernel launches dealt to two streams (a K1
+// launch ends with a ~2 ms tail of long-running warps; the next launch fills the machine meanwhile); a third stream DMAs
+// finished chunks into the pinned double buffer while the CPU copies the previous piece into the caller's (pageable) memory.
+namespace {
+struct HostPathPool {
+    std::mutex mu;
+    int device = -1;
+    double* d_out = nullptr; size_t d_cap = 0;
+    double* stage[2] = {nullptr, nullptr};
+    cudaStream_t s_k[2] = {nullptr, nullptr}, s_c = nullptr;
+    cudaEvent_t dma_ev[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> chunk_ev;
+    static constexpr size_t kPiece = 4u << 20;          // doubles per staging buffer (32 MiB)
+    cudaError_t prepare(size_t n, size_t n_chunks)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev != device) { release(); device = dev; }
+        if (!s_c) {
+            for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&s_k[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_c, cudaStreamNonBlocking);
+            for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&dma_ev[i], cudaEventDisableTiming);
+            for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaMallocHost(reinterpret_cast<void**>(&stage[i]), kPiece * sizeof(double));
+            if (e != cudaSuccess) return e;
+        }
+        if (n > d_cap) {
+            if (d_out) cudaFree(d_out);
+            d_out = nullptr; d_cap = 0;
+            e = cudaMalloc(reinterpret_cast<void**>(&d_out), n * sizeof(double));
+            if (e != cudaSuccess) return e;
+            d_cap = n;
+        }
+        while (chunk_ev.size() < n_chunks) {
+            cudaEvent_t ev;
+            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            chunk_ev.push_back(ev);
+        }
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (d_out) cudaFree(d_out);
+        d_out = nullptr; d_cap = 0;
+        for (int i = 0; i < 2; i++) { if (stage[i]) cudaFreeHost(stage[i]); stage[i] = nullptr; if (s_k[i]) cudaStreamDestroy(s_k[i]); s_k[i] = nullptr;
+                                      if (dma_ev[i]) cudaEventDestroy(dma_ev[i]); dma_ev[i] = nullptr; }
+        if (s_c) cudaStreamDestroy(s_c);
+        s_c = nullptr;
+        for (auto ev : chunk_ev) cudaEventDestroy(ev);
+        chunk_ev.clear();
+    }
+};
+HostPathPool g_pool;
+}  // namespace
+
 int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* out_host)
 {
     if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf: mesh is NULL (not constructed)");
@@ -384,35 +442,33 @@ int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint6
     const uint64_t n = l_end - l_begin;
     if (n == 0) return DG_OK;
     if (!out_host) return fail(DG_ERR_INVALID, "dg_sample_sdf: output is NULL");
-    DevBuf<double> d_out;
-    DG_CUDA(d_out.alloc(n));
-    // chunked so that the D2H copy of chunk i overlaps the kernel of chunk i+1
-    cudaStream_t s_k, s_c;
-    DG_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-    DG_CUDA(cudaStreamCreateWithFlags(&s_c, cudaStreamNonBlocking));
-    const uint64_t chunk = 1ull << 22;
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    // kernel chunks: a handful, each a multiple of the staging piece so that pieces never straddle chunks
+    const uint64_t piece = HostPathPool::kPiece;
+    const uint64_t n_pieces = (n + piece - 1) / piece;
+    const uint64_t pieces_per_chunk = n_pieces <= 4 ? 1 : (n_pieces + 7) / 8;
+    const uint64_t chunk = pieces_per_chunk * piece;
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
-    std::vector<cudaEvent_t> ev(n_chunks);
-    int rc = DG_OK;
-    const bool pinned = cudaHostRegister(out_host, n * sizeof(double), cudaHostRegisterDefault) == cudaSuccess;
-    if (!pinned) cudaGetLastError();
-    for (uint64_t c = 0; c < n_chunks && rc == DG_OK; c++) {
+    DG_CUDA(g_pool.prepare(n, n_chunks));
+    for (uint64_t c = 0; c < n_chunks; c++) {
         const uint64_t b = c * chunk, cnt = (b + chunk <= n) ? chunk : n - b;
-        cudaError_t e = k1_launch_sample_nodes(m->dev, g, sign, l_begin + b, cnt, d_out.p + b, s_k);
-        g_launches.fetch_add(1);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventRecord(ev[c], s_k);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_c, ev[c], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_host + b, d_out.p + b, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_c);
-        if (e != cudaSuccess) rc = fail(DG_ERR_CUDA, "dg_sample_sdf: %s", cudaGetErrorString(e));
+        DG_LAUNCH(k1_launch_sample_nodes(m->dev, g, sign, l_begin + b, cnt, g_pool.d_out + b, g_pool.s_k[c & 1]));
+        DG_CUDA(cudaEventRecord(g_pool.chunk_ev[c], g_pool.s_k[c & 1]));
     }
-    cudaError_t e1 = cudaStreamSynchronize(s_k), e2 = cudaStreamSynchronize(s_c);
-    if (rc == DG_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
-        rc = fail(DG_ERR_CUDA, "dg_sample_sdf: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    for (uint64_t c = 0; c < n_chunks; c++) if (ev[c]) cudaEventDestroy(ev[c]);
-    if (pinned) cudaHostUnregister(out_host);
-    cudaStreamDestroy(s_k); cudaStreamDestroy(s_c);
-    return rc;
+    for (uint64_t i = 0; i <= n_pieces; i++) {
+        if (i < n_pieces) {
+            const uint64_t off = i * piece, cnt = (off + piece <= n) ? piece : n - off;
+            DG_CUDA(cudaStreamWaitEvent(g_pool.s_c, g_pool.chunk_ev[off / chunk], 0));
+            DG_CUDA(cudaMemcpyAsync(g_pool.stage[i & 1], g_pool.d_out + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, g_pool.s_c));
+            DG_CUDA(cudaEventRecord(g_pool.dma_ev[i & 1], g_pool.s_c));
+        }
+        if (i >= 1) {
+            const uint64_t off = (i - 1) * piece, cnt = (off + piece <= n) ? piece : n - off;
+            DG_CUDA(cudaEventSynchronize(g_pool.dma_ev[(i - 1) & 1]));
+            std::memcpy(out_host + off, g_pool.stage[(i - 1) & 1], cnt * sizeof(double));
+        }
+    }
+    return DG_OK;
 }
 
 int dg_node_positions(const dg_grid_desc* grid, uint64_t l_begin, uint64_t l_end, double* x_host)
