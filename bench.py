@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-interp", action="store_true", help="skip the interpolate half (diagnostics / profiling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (diagnostics / profiling)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (diagnostics / profiling)")
+    ap.add_argument("--no-target", action="store_true", help="skip the 256^3 / 100k-triangle target-config leg")
     ap.add_argument("--no-density", action="store_true", help="skip the density-map (K3) leg (diagnostics / profiling)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -367,6 +368,27 @@ def main():
                           "api": "dg_interpolate_batch(field, x_host, n, phi_host, grad_host)"}}
         capi.lib.dg_field_destroy(fh)
 
+    # ---------------------------------------------------------------- north-star target config: 256^3 grid, 100,000-triangle mesh
+    target = None
+    if not args.no_target:
+        tmesh = dg.bumpy_torus()                               # 250 x 200 quads = exactly 100,000 triangles
+        tmd = dg.TriangleMeshDistance(tmesh)
+        tmn, tmx = dg.generate_sdf_domain(tmesh.vertices)
+        tdesc = dg.grid_desc(tmn, tmx, [256, 256, 256])
+        tn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(tdesc.resolution, C.byref(tn))); tn = tn.value
+        tsh = make_sharding(tn, world)
+        tfull = torch.empty(tsh.padded, dtype=torch.float64, device=dev)
+        tsampler = ShardedSdfSampler(tmd, tdesc, tsh, rank)
+        t_ms, _ = timed(lambda: tsampler.step(tfull), 3, 1)
+        t_ms = float(np.mean(t_ms))
+        target = {"workload": "north_star target: 256^3 grid (118,425,857 nodes), synthetic bumpy torus with exactly 100,000 triangles, "
+                              "strong scaling over node chunks + all-gather", "ms_per_step": t_ms, "value": tn / (t_ms * 1e-3), "unit": "nodes/s",
+                  "n_gpus": world}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            rates, info = cpu_sample_rate(tmesh, tmn, tmx, [256, 256, 256], args.cpu_seconds)
+            target["cpu_baseline"] = dict(info, value=float(np.mean(rates)), unit="nodes/s")
+        del tfull, tsampler, tmd
+
     # ---------------------------------------------------------------- density map (config 5 kernel), N = 1 only
     density = None
     if world == 1 and not args.no_density:
@@ -414,7 +436,7 @@ def main():
         line = {"metric": "SDF grid nodes/sec (addFunction)", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "density_map": density,
+                "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "target_config": target, "density_map": density,
                 "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms}}
         print(json.dumps(line))
     if world > 1:

@@ -147,3 +147,46 @@ def test_edge_cases(dg, orc):
     with pytest.raises(dg.DiscregridError):
         dg.TriangleMeshDistance().signed_distance(x)                           # not constructed
     assert len(md.signed_distance(np.zeros((0, 3))).distance) == 0             # empty batch
+
+
+def test_full_size_config1_properties(dg, orc):
+    """BASELINE.json configs[1] size (128^3 = 14,926,977 nodes, ~70k triangles) through the C-ABI: size-independent properties
+    + oracle parity on a strided 60k-node sample (the oracle needs seconds for that, minutes for all nodes)."""
+    import ctypes as C
+    from discregrid_b200 import _capi as capi
+    mesh = dg.bumpy_torus(186, 187)                                # the bench workload
+    md = dg.TriangleMeshDistance(mesh)
+    mn, mx = dg.generate_sdf_domain(mesh.vertices)
+    res = (128, 128, 128)
+    g = dg.CubicLagrangeDiscreteGrid(mn, mx, res)
+    n = g.nNodes()
+    assert n == 14926977
+    g.addFunction(dg.MeshSignedDistance(md))
+    full = g.m_nodes[0]
+    assert np.isfinite(full).all() and (full < 0).any() and (full > 0).any()
+    # invert: -1.0 * d is exact, so the inverted field is the bitwise negation
+    inv = np.empty(n)
+    capi.check(capi.lib.dg_sample_sdf(md.handle, C.byref(g._desc), -1.0, 0, n, capi.ptr(inv, capi.F64P)))
+    assert bits_equal(inv, -full)
+    # determinism + sharding: 7 uneven ranges concatenate to the same bits
+    cuts = np.linspace(0, n, 8).astype(np.int64); cuts[3] += 12345
+    parts = []
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        out = np.empty(e - b)
+        capi.check(capi.lib.dg_sample_sdf(md.handle, C.byref(g._desc), 1.0, int(b), int(e), capi.ptr(out, capi.F64P)))
+        parts.append(out)
+    assert bits_equal(np.concatenate(parts), full)
+    # |grad| of a distance field is 1 a.e.: vertex nodes one cell apart differ by at most the cell size (Lipschitz-1)
+    nx = 129
+    v = full[:nx ** 3].reshape(nx, nx, nx)                        # [k][j][i]
+    assert np.abs(np.diff(v, axis=2)).max() <= g.m_cell_size[0] * (1 + 1e-12)
+    assert np.abs(np.diff(v, axis=1)).max() <= g.m_cell_size[1] * (1 + 1e-12)
+    assert np.abs(np.diff(v, axis=0)).max() <= g.m_cell_size[2] * (1 + 1e-12)
+    # oracle parity on a strided sample through the point-query API and the node positions
+    ids = np.linspace(0, n - 1, 60000).astype(np.int64)
+    gd, r = orc.grid_desc(mn, mx, res)
+    x = np.concatenate([orc.node_positions(gd, r, int(l), int(l) + 1) for l in ids[:200]])
+    assert bits_equal(x, g.nodePositions()[ids[:200]])
+    xs = g.nodePositions()[ids]
+    want = orc.mesh(mesh.vertices, mesh.faces).distance(xs)[0]
+    assert bits_equal(full[ids], want)
