@@ -276,7 +276,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
         } else if (n_node != 0 && K1_NODE_WEIGHT * n_node >= K1_LEAF_WEIGHT * n_leaf) {
             if (state == NODE) {                                                // internal (:537-561)
                 const int m = (b + e) >> 1;
-                bool left_first, go_first, go_second = false;
+                bool left_first, go_first, go_second = false, defer = true;
                 float d_second_f;
                 bool decided = false;
 #if K1_FILTER
@@ -294,6 +294,9 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     go_first = (d_first_f + E < best_lo);                       // certainly d_first < best
                     const bool skip_first = (d_first_f - E >= best_hi);         // certainly d_first >= best (then d_second >= best too)
                     decided = order_sure && (go_first || skip_first);
+                    // a sibling that is already certainly not nearer than the best can never pass its re-test (best only
+                    // shrinks): the reference would pop it and skip it (:549/:557), so it is not stacked at all
+                    defer = !(d_second_f - E >= best_hi);
                 }
 #endif
                 if (!decided) {                                                 // fp64, exactly the reference
@@ -307,12 +310,16 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     go_first = d_first < best;                                                // :545 / :554
                     go_second = !go_first && (d_second < best);     // only reachable through NaNs; kept for fidelity (:549 / :557)
                     d_second_f = (float)d_second;                   // |rounding| <= 2^-24 |d| << E: the stored value stays a valid filter input
+                    defer = K1_SKIP_HOPELESS ? (d_second < best) : true;
                 }
+                if (!K1_SKIP_HOPELESS) defer = true;
                 depth++;
                 if (go_first) {                        // visit first now; second is re-tested when popped (:545-551)
-                    stack_rng[sp * stride] = left_first ? pack_range(m, e, depth, n_tri, false) : pack_range(b, m, depth, n_tri, true);
-                    stack_d[sp * stride] = d_second_f;
-                    sp++;
+                    if (defer) {
+                        stack_rng[sp * stride] = left_first ? pack_range(m, e, depth, n_tri, false) : pack_range(b, m, depth, n_tri, true);
+                        stack_d[sp * stride] = d_second_f;
+                        sp++;
+                    }
                     if (left_first) e = m; else b = m;
                     state = (e - b == 1) ? LEAF : NODE;
                 } else if (go_second) {

@@ -33,6 +33,9 @@ constexpr int K1_THREADS = K1_THREADS_PER_BLOCK;
 #ifndef K1_FILTER
 #define K1_FILTER 1             // 1: fp32 interval filter for the sphere decisions (exact fp64 fallback); 0: all fp64
 #endif
+#ifndef K1_SKIP_HOPELESS
+#define K1_SKIP_HOPELESS 1      // do not stack a sibling whose sphere is already certainly farther than the best
+#endif
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS (1024 / K1_THREADS_PER_BLOCK)   // blocks per SM the register allocation must allow (32 warps)
 #endif
