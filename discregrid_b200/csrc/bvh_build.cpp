@@ -31,7 +31,8 @@ struct Builder {
     inline P3 vert(int32_t tri, int k) const { return V[F[3 * (size_t)tri + k]]; }
 
     // bounding sphere of the node covering [b, e) in the CURRENT arrangement (TriangleMeshDistance.h:451-491)
-    void build(int b, int e, double sc[3], double& sr, int depth)
+    // also returns the axis-aligned box of the node's vertices in box[6] = {lo, hi}
+    void build(int b, int e, double sc[3], double& sr, double box[6], int depth)
     {
         out.max_depth = std::max(out.max_depth, depth);
         const int n = e - b;
@@ -41,6 +42,8 @@ struct Builder {
             const P3 ctr = {s.x / 3.0, s.y / 3.0, s.z / 3.0};
             sr = std::max(std::max(len(a - ctr), len(bb - ctr)), len(c - ctr));
             sc[0] = ctr.x; sc[1] = ctr.y; sc[2] = ctr.z;
+            box[0] = std::min(std::min(a.x, bb.x), c.x); box[1] = std::min(std::min(a.y, bb.y), c.y); box[2] = std::min(std::min(a.z, bb.z), c.z);
+            box[3] = std::max(std::max(a.x, bb.x), c.x); box[4] = std::max(std::max(a.y, bb.y), c.y); box[5] = std::max(std::max(a.z, bb.z), c.z);
             return;
         }
         double top[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, bot[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
@@ -54,6 +57,7 @@ struct Builder {
             }
         const double cnt = (double)(3 * n);
         ctr = {ctr.x / cnt, ctr.y / cnt, ctr.z / cnt};
+        for (int d = 0; d < 3; d++) { box[d] = bot[d]; box[3 + d] = top[d]; }
         const double diag[3] = {top[0] - bot[0], top[1] - bot[1], top[2] - bot[2]};
         int split = 0;                                       // std::max_element: first maximum
         if (diag[1] > diag[split]) split = 1;
@@ -70,8 +74,9 @@ struct Builder {
 
         const int m = (b + e) >> 1;
         SpherePair& sp = out.spheres[m];
-        build(b, m, sp.lc, sp.lr, depth + 1);
-        build(m, e, sp.rc, sp.rr, depth + 1);
+        double* bx = &out.boxes[12 * (size_t)m];
+        build(b, m, sp.lc, sp.lr, bx, depth + 1);
+        build(m, e, sp.rc, sp.rr, bx + 6, depth + 1);
     }
 };
 
@@ -94,8 +99,9 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
 
     Builder bld{V, F, out, out.order, {}};
     bld.keys.resize(nT);
-    double root_c[3], root_r;
-    bld.build(0, T, root_c, root_r, 1);      // root sphere is computed and unused, as in the reference (:125,357)
+    double root_c[3], root_r, root_box[6];
+    out.boxes.assign(12 * nT, 0.0);
+    bld.build(0, T, root_c, root_r, root_box, 1);      // root sphere is computed and unused, as in the reference (:125,357)
 
     // ---- pseudonormals (TriangleMeshDistance.h:359-420), in the reference's arrays first
     out.pn_tri.assign(3 * nT, 0.0); out.pn_edge.assign(9 * nT, 0.0); out.pn_vert.assign(3 * nV, 0.0);
@@ -147,6 +153,19 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
             for (int d = 0; d < 3; d++) { f.lc[d] = (float)(sp.lc[d] - out.center[d]); f.rc[d] = (float)(sp.rc[d] - out.center[d]); }
             f.lr = (float)sp.lr; f.rr = (float)sp.rr;
         }
+        // child boxes, rounded outward so that the fp32 box contains the fp64 one
+        out.boxes_f.assign(nT, BoxPairF());
+        auto down = [](double v) { float f = (float)v; return ((double)f > v) ? std::nextafterf(f, -INFINITY) : f; };
+        auto up = [](double v) { float f = (float)v; return ((double)f < v) ? std::nextafterf(f, INFINITY) : f; };
+        for (uint64_t m = 1; m < nT; m++) {
+            const double* bx = &out.boxes[12 * m];
+            BoxPairF& q = out.boxes_f[m];
+            for (int d = 0; d < 3; d++) {
+                q.l_lo[d] = down(bx[d] - out.center[d]); q.l_hi[d] = up(bx[3 + d] - out.center[d]);
+                q.r_lo[d] = down(bx[6 + d] - out.center[d]); q.r_hi[d] = up(bx[9 + d] - out.center[d]);
+            }
+        }
+        std::vector<double>().swap(out.boxes);
     }
 
     // ---- device records in leaf order

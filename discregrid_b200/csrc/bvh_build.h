@@ -35,6 +35,14 @@ struct alignas(32) SpherePairF {
 };
 static_assert(sizeof(SpherePairF) == 32, "SpherePairF must be 32 bytes");
 
+// fp32 axis-aligned boxes (relative to HostBvh::center, rounded OUTWARD) of the two children of an internal node: a second,
+// tighter lower bound used only to SKIP subtrees that provably cannot change the result (k1_sdf.cu, "hopeless" test).
+struct alignas(16) BoxPairF {
+    float l_lo[3], l_hi[3];
+    float r_lo[3], r_hi[3];
+};
+static_assert(sizeof(BoxPairF) == 48, "BoxPairF must be 48 bytes");
+
 struct alignas(128) LeafRecord {
     double v0[3];
     double e0[3];
@@ -53,6 +61,8 @@ struct HostBvh {
     uint64_t n_vertices = 0, n_triangles = 0;
     std::vector<SpherePair> spheres;        // [T]  (index 0 unused)
     std::vector<SpherePairF> spheres_f;     // [T]  fp32 shadow, relative to `center`
+    std::vector<BoxPairF> boxes_f;          // [T]  fp32 child boxes, relative to `center`, rounded outward
+    std::vector<double> boxes;              // [T][12] fp64 child boxes (build scratch)
     double center[3] = {0, 0, 0};           // bounding-box centre of the vertices
     double half_extent = 0;                 // max |v - center|_inf over the vertices
     std::vector<LeafRecord> leaves;         // [T]

@@ -194,6 +194,7 @@ __device__ __forceinline__ double sphere_dist(double px, double py, double pz, d
 struct MeshDev {
     const SpherePair* spheres;
     const SpherePairF* spheres_f;
+    const BoxPairF* boxes_f;
     const LeafRecord* leaves;
     double cx, cy, cz;
     float half_extent;
@@ -236,6 +237,14 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
     // beyond ~1e18 the fp32 squares overflow: switch the filter off for such a query (E = inf leaves every test undecided)
     const float E = (Mq < 1.0e18f) ? __fmul_ru(Mq, 3.814697265625e-06f) : __int_as_float(0x7f800000);     // 64 * 2^-24 * Mq
     const float E2 = E + E;
+    // BOX SKIP (K1_BOX_SKIP).  A subtree may be skipped when visiting it provably changes nothing: no triangle in it can be
+    // accepted, i.e. every d2 the reference would compute there is >= best_sq.  With L = (fp32 distance to the subtree's
+    // outward-rounded box) - E <= true distance to every triangle, the reference's d2 >= L^2 - 240 eps64 R^2 (fp64 rounding of
+    // its formula, R <= 7 Mq) and best_sq <= best^2 (1 + 2^-53): both slacks are below E * best once best >= 1e-6 Mq, so
+    // "box distance > best_hi + 2E" suffices; for queries practically on the surface (best < 1e-6 Mq) nothing is skipped.
+    // The running best only shrinks, so a subtree found hopeless stays hopeless and its deferred re-test can be dropped too.
+    const float tiny_best = 1.0e-6f * Mq;
+    float skip_sq = __int_as_float(0x7f800000);              // (best_hi + 2E)^2 rounded up; +inf = never skip
     int b = 0, e = n_tri, depth = 0, sp = 0;
     int state = alive ? ((n_tri == 1) ? LEAF : NODE) : DONE;
     for (;;) {
@@ -265,9 +274,18 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     }
                     if (visit) {
                         const unsigned r = stack_rng[sp * stride];
-                        b = (int)(r & 0x01ffffffu);
-                        depth = (int)((r >> 25) & 31u);
-                        e = b + (n_tri >> depth) + (int)((r >> 30) & 1u);
+                        const int rb = (int)(r & 0x01ffffffu), rd = (int)((r >> 25) & 31u);
+                        const int re = rb + (n_tri >> rd) + (int)((r >> 30) & 1u);
+#if K1_BOX_SKIP
+                        {   // the best has usually shrunk since this sibling was deferred: box test against the current best
+                            const bool is_left = (r >> 31) != 0u;
+                            const float* bx = reinterpret_cast<const float*>(M.boxes_f + (is_left ? re : rb)) + (is_left ? 0 : 6);
+                            const float gx = fmaxf(fmaxf(__ldg(bx) - qx, qx - __ldg(bx + 3)), 0.f), gy = fmaxf(fmaxf(__ldg(bx + 1) - qy, qy - __ldg(bx + 4)), 0.f),
+                                        gz = fmaxf(fmaxf(__ldg(bx + 2) - qz, qz - __ldg(bx + 5)), 0.f);
+                            if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) continue;   // visiting it could not change anything
+                        }
+#endif
+                        b = rb; depth = rd; e = re;
                         state = (e - b == 1) ? LEAF : NODE;
                         break;
                     }
@@ -297,6 +315,30 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     // a sibling that is already certainly not nearer than the best can never pass its re-test (best only
                     // shrinks): the reference would pop it and skip it (:549/:557), so it is not stacked at all
                     defer = !(d_second_f - E >= best_hi);
+#if K1_BOX_SKIP
+                    if (decided && go_first) {
+                        const float4* bx = reinterpret_cast<const float4*>(M.boxes_f + m);
+                        const float4 b0 = __ldg(bx), b1 = __ldg(bx + 1), b2 = __ldg(bx + 2);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
+                        const float lgx = fmaxf(fmaxf(b0.x - qx, qx - b0.w), 0.f), lgy = fmaxf(fmaxf(b0.y - qy, qy - b1.x), 0.f),
+                                    lgz = fmaxf(fmaxf(b0.z - qz, qz - b1.y), 0.f);
+                        const float rgx = fmaxf(fmaxf(b1.z - qx, qx - b2.y), 0.f), rgy = fmaxf(fmaxf(b1.w - qy, qy - b2.z), 0.f),
+                                    rgz = fmaxf(fmaxf(b2.x - qz, qz - b2.w), 0.f);
+                        // squared box distances rounded DOWN (a smaller value only skips less)
+                        const float l2 = __fmaf_rd(lgz, lgz, __fmaf_rd(lgy, lgy, __fmul_rd(lgx, lgx)));
+                        const float r2 = __fmaf_rd(rgz, rgz, __fmaf_rd(rgy, rgy, __fmul_rd(rgx, rgx)));
+                        const bool hopeless_first = (left_first ? l2 : r2) > skip_sq;
+                        const bool hopeless_second = (left_first ? r2 : l2) > skip_sq;
+                        if (hopeless_second) defer = false;
+                        if (hopeless_first) {
+                            // the first child would be visited without effect; what the reference does next is the re-test of the second
+                            const bool second_yes = (d_second_f + E < best_lo), second_no = (d_second_f - E >= best_hi);
+                            if (second_yes || second_no) {
+                                go_first = false;
+                                go_second = second_yes && !hopeless_second;
+                            }                                   // undecided re-test: simply do not use the shortcut
+                        }
+                    }
+#endif
                 }
 #endif
                 if (!decided) {                                                 // fp64, exactly the reference
@@ -337,6 +379,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     best = sqrt(d2);
                     best_sq = best * best;
                     best_lo = __double2float_rd(best); best_hi = __double2float_ru(best);
+                    { const float th = __fadd_ru(best_hi, E2); skip_sq = (K1_BOX_SKIP && best_lo >= tiny_best) ? __fmul_ru(th, th) : __int_as_float(0x7f800000); }
                     res.s = s; res.t = t; res.pos = b; res.entity = ent;
                 }
                 state = POP;
@@ -446,7 +489,7 @@ __global__ void fma_probe_kernel(double a, double b, double c, double* out) { ou
 }  // namespace
 
 static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)); }
-static inline MeshDev mesh_dev(const DeviceBvh& m) { return MeshDev{m.spheres, m.spheres_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri}; }
+static inline MeshDev mesh_dev(const DeviceBvh& m) { return MeshDev{m.spheres, m.spheres_f, m.boxes_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri}; }
 
 cudaError_t k1_configure(int stack_depth)
 {

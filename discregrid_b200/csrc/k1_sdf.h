@@ -33,6 +33,9 @@ constexpr int K1_THREADS = K1_THREADS_PER_BLOCK;
 #ifndef K1_FILTER
 #define K1_FILTER 1             // 1: fp32 interval filter for the sphere decisions (exact fp64 fallback); 0: all fp64
 #endif
+#ifndef K1_BOX_SKIP
+#define K1_BOX_SKIP 1           // skip subtrees whose box is certainly farther than the best (they cannot change the result)
+#endif
 #ifndef K1_SKIP_HOPELESS
 #define K1_SKIP_HOPELESS 1      // do not stack a sibling whose sphere is already certainly farther than the best
 #endif
@@ -57,6 +60,7 @@ struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once b
     const LeafRecord* leaves = nullptr;
     const PseudoNormals* normals = nullptr;
     const SpherePairF* spheres_f = nullptr;   // fp32 filter shadow (relative to ctr)
+    const BoxPairF* boxes_f = nullptr;         // fp32 child boxes (relative to ctr, rounded outward)
     double ctr[3] = {0, 0, 0};
     float half_extent = 0.f;
     int n_tri = 0;
