@@ -167,11 +167,8 @@ def cpu_sample_rate(mesh, mn, mx, res, seconds, steps=1, warmup=0):
 
 
 def _positions(orc, gd, r, ids):
-    """positions of arbitrary node ids via the oracle's indexToNodePosition on the covering ranges (cheap)."""
-    lo, hi = int(ids.min()), int(ids.max()) + 1
-    if hi - lo <= 4 * len(ids) or hi - lo <= 20_000_000:
-        return np.ascontiguousarray(orc.node_positions(gd, r, lo, hi)[ids - lo])
-    return np.concatenate([orc.node_positions(gd, r, int(l), int(l) + 1) for l in ids])
+    """positions of arbitrary node ids via the oracle's indexToNodePosition"""
+    return orc.node_positions_at(gd, r, ids)
 
 
 # ------------------------------------------------------------------------------------------------ main

@@ -6,6 +6,9 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <future>
+#include <thread>
 #include <unordered_map>
 
 namespace dgb {
@@ -27,6 +30,8 @@ struct Builder {
     std::vector<int32_t>& order;           // current arrangement of triangle ids (the reference sorts structs in place)
     struct Key { double k; int32_t id; };
     std::vector<Key> keys;                 // scratch for the sort (same comparisons => same permutation as the reference)
+    std::atomic<int> max_depth{0};
+    int par_levels = 0;                    // subtrees of the first `par_levels` levels are built by separate threads
 
     inline P3 vert(int32_t tri, int k) const { return V[F[3 * (size_t)tri + k]]; }
 
@@ -34,7 +39,7 @@ struct Builder {
     // also returns the axis-aligned box of the node's vertices in box[6] = {lo, hi}
     void build(int b, int e, double sc[3], double& sr, double box[6], int depth)
     {
-        out.max_depth = std::max(out.max_depth, depth);
+        { int cur = max_depth.load(std::memory_order_relaxed); while (depth > cur && !max_depth.compare_exchange_weak(cur, depth)) {} }
         const int n = e - b;
         if (n == 1) {
             const P3 a = vert(order[b], 0), bb = vert(order[b], 1), c = vert(order[b], 2);
@@ -75,8 +80,16 @@ struct Builder {
         const int m = (b + e) >> 1;
         SpherePair& sp = out.spheres[m];
         double* bx = &out.boxes[12 * (size_t)m];
-        build(b, m, sp.lc, sp.lr, bx, depth + 1);
-        build(m, e, sp.rc, sp.rr, bx + 6, depth + 1);
+        // the two subtrees touch disjoint ranges of `order`/`keys` and disjoint records: build them concurrently near the root.
+        // Every node is still processed by exactly the reference's sequence of operations, so the tree is unchanged.
+        if (depth <= par_levels && n >= 4096) {
+            auto left = std::async(std::launch::async, [&, b, m, depth, bx]() { build(b, m, sp.lc, sp.lr, bx, depth + 1); });
+            build(m, e, sp.rc, sp.rr, bx + 6, depth + 1);
+            left.get();
+        } else {
+            build(b, m, sp.lc, sp.lr, bx, depth + 1);
+            build(m, e, sp.rc, sp.rr, bx + 6, depth + 1);
+        }
     }
 };
 
@@ -97,11 +110,13 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
     out.order.resize(nT);
     for (int i = 0; i < T; i++) out.order[i] = i;
 
-    Builder bld{V, F, out, out.order, {}};
+    Builder bld{V, F, out, out.order};
     bld.keys.resize(nT);
+    { unsigned hw = std::thread::hardware_concurrency(); int lv = 0; while ((1u << (lv + 1)) <= hw && lv < 6) lv++; bld.par_levels = lv; }
     double root_c[3], root_r, root_box[6];
     out.boxes.assign(12 * nT, 0.0);
-    bld.build(0, T, root_c, root_r, root_box, 1);      // root sphere is computed and unused, as in the reference (:125,357)
+    bld.build(0, T, root_c, root_r, root_box, 1);
+    out.max_depth = bld.max_depth.load();      // root sphere is computed and unused, as in the reference (:125,357)
 
     // ---- pseudonormals (TriangleMeshDistance.h:359-420), in the reference's arrays first
     out.pn_tri.assign(3 * nT, 0.0); out.pn_edge.assign(9 * nT, 0.0); out.pn_vert.assign(3 * nV, 0.0);

@@ -506,13 +506,26 @@ int dg_build_cells(const uint32_t res[3], uint64_t c_begin, uint64_t c_end, uint
     const uint64_t n = c_end - c_begin;
     if (n == 0) return DG_OK;
     if (!cells_host) return fail(DG_ERR_INVALID, "dg_build_cells: output is NULL");
-    const uint64_t chunk = 1ull << 22;          // 512 MiB of uint32 per chunk
-    DevBuf<unsigned> d_cells;
-    DG_CUDA(d_cells.alloc(32 * (n < chunk ? n : chunk)));
-    for (uint64_t b = 0; b < n; b += chunk) {
-        const uint64_t cnt = (b + chunk <= n) ? chunk : n - b;
-        DG_LAUNCH(k1_launch_build_cells(g, c_begin + b, cnt, d_cells.p, nullptr));
-        DG_CUDA(cudaMemcpy(cells_host + 32 * b, d_cells.p, 32 * cnt * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    // same pooled double-buffer pipeline as dg_sample_sdf: the kernel fills one 32 MiB piece (256 Ki cells) of device scratch,
+    // the copy stream DMAs it into pinned memory while the CPU moves the previous piece into the caller's array
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    const uint64_t piece_cells = HostPathPool::kPiece * sizeof(double) / (32 * sizeof(uint32_t));    // cells per staging buffer
+    const uint64_t n_pieces = (n + piece_cells - 1) / piece_cells;
+    DG_CUDA(g_pool.prepare(2 * HostPathPool::kPiece, 2));                 // device scratch: two pieces
+    uint32_t* d_piece[2] = {reinterpret_cast<uint32_t*>(g_pool.d_out), reinterpret_cast<uint32_t*>(g_pool.d_out + HostPathPool::kPiece)};
+    for (uint64_t i = 0; i <= n_pieces; i++) {
+        if (i < n_pieces) {
+            const uint64_t off = i * piece_cells, cnt = (off + piece_cells <= n) ? piece_cells : n - off;
+            // piece i reuses device/pinned buffer i&1: its previous user (piece i-2) was fully consumed in iteration i-1
+            DG_LAUNCH(k1_launch_build_cells(g, c_begin + off, cnt, d_piece[i & 1], g_pool.s_c));
+            DG_CUDA(cudaMemcpyAsync(g_pool.stage[i & 1], d_piece[i & 1], cnt * 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_pool.s_c));
+            DG_CUDA(cudaEventRecord(g_pool.dma_ev[i & 1], g_pool.s_c));
+        }
+        if (i >= 1) {
+            const uint64_t off = (i - 1) * piece_cells, cnt = (off + piece_cells <= n) ? piece_cells : n - off;
+            DG_CUDA(cudaEventSynchronize(g_pool.dma_ev[(i - 1) & 1]));
+            std::memcpy(cells_host + 32 * off, g_pool.stage[(i - 1) & 1], cnt * 32 * sizeof(uint32_t));
+        }
     }
     return DG_OK;
 }

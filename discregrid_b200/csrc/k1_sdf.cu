@@ -77,10 +77,11 @@ __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec, 
     const int ent_r2 = (tmp1_2 > tmp0_2) ? ((numer_2 >= denom) ? 1 : 4) : ((tmp1_2 <= 0) ? 2 : ((b1 >= 0) ? 0 : 5));   // :690-731
     const int ent_r6 = (tmp1_6 > tmp0_6) ? ((numer_6 >= denom) ? 2 : 4) : ((tmp1_6 <= 0) ? 1 : ((b0 >= 0) ? 0 : 3));   // :737-778
     const int ent_r1 = (numer_1 <= 0) ? 2 : ((numer_1 >= denom) ? 1 : 4);                                               // :783-808
-    // `pin` = empty asm that makes the value opaque: the compiler must materialise it here and can neither specialise
-    // the code below per outcome (it otherwise re-creates one divergent branch per outcome, each with its own division)
-    // nor move it.  It emits no instruction.
-#if K1_LEAF_PIN
+    // `pin` = empty asm that makes a value opaque: the compiler must materialise it there and cannot specialise the code
+    // that follows per outcome (left alone it re-creates ~20 divergent branches, three of them with their own division).
+    // K1_LEAF_MODE 0: plain C (compiler's branches); 1: everything straight-line (every lane pays division + quadratic form);
+    // 2: predicate-only classification, then ONE guarded block with the division and ONE with the quadratic form.
+#if K1_LEAF_MODE
 #define DG_PIN_I(v) asm volatile("" : "+r"(v))
 #define DG_PIN_D(v) asm volatile("" : "+d"(v))
 #else
@@ -97,7 +98,13 @@ __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec, 
     double num = (ent == 3) ? -b0 : ((ent == 5) ? -b1 : ((ent == 4) ? numer : 0.0));
     double den = (ent == 3) ? a00 : ((ent == 5) ? a11 : ((ent == 4) ? denom : 1.0));
     DG_PIN_D(num); DG_PIN_D(den);
-    double q = num / den;
+    double q = 0.0;
+#if K1_LEAF_MODE == 2
+    if (ent >= 3 && ent <= 5)
+#endif
+    {
+        q = num / den;
+    }
     DG_PIN_D(q);
     // ---- (s, t) of the nearest point
     const double sF = s0 * inv_det, tF = t0 * inv_det;                 // :675-677 (read when ent == 6)
@@ -106,7 +113,13 @@ __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec, 
     double t = (ent == 6) ? tF : ((ent == 4) ? (region6 ? q : omq) : ((ent == 2) ? 1.0 : ((ent == 5) ? q : 0.0)));
     DG_PIN_D(s); DG_PIN_D(t);
     // ---- d2
-    double quad = s * (a00 * s + a01 * t + 2 * b0) + t * (a01 * s + a11 * t + 2 * b1) + c;   // :678, :706, :753, :805
+    double quad = 0.0;
+#if K1_LEAF_MODE == 2
+    if (ent == 4 || ent == 6)
+#endif
+    {
+        quad = s * (a00 * s + a01 * t + 2 * b0) + t * (a01 * s + a11 * t + 2 * b1) + c;   // :678, :706, :753, :805
+    }
     double dv1 = a00 + 2 * b0 + c, dv2 = a11 + 2 * b1 + c;            // :594, :616
     double de1 = b0 * q + c, de2 = b1 * q + c;                         // :600, :622
     DG_PIN_D(quad); DG_PIN_D(dv1); DG_PIN_D(dv2); DG_PIN_D(de1); DG_PIN_D(de2);

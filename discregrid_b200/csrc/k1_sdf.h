@@ -27,8 +27,8 @@ constexpr int K1_THREADS = K1_THREADS_PER_BLOCK;
 #ifndef K1_POP_MERGED
 #define K1_POP_MERGED 0         // 1: POP lanes re-test siblings at the end of every iteration; 0: POP is a phase of its own
 #endif
-#ifndef K1_LEAF_PIN
-#define K1_LEAF_PIN 0           // 1: force the single-division branch-free leaf arithmetic (see tri_dist2)
+#ifndef K1_LEAF_MODE
+#define K1_LEAF_MODE 0          // leaf arithmetic: 0 compiler's branches, 1 fully straight-line, 2 one guarded division + one guarded quadratic form
 #endif
 #ifndef K1_FILTER
 #define K1_FILTER 1             // 1: fp32 interval filter for the sphere decisions (exact fp64 fallback); 0: all fp64

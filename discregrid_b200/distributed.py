@@ -32,10 +32,12 @@ class NodeSharding:
         return out
 
 
-def make_sharding(n, world, rows=8, align=1024):
+def make_sharding(n, world, rows=None, align=1024):
     """Equal chunks of a size that is a multiple of `align` nodes (keeps every chunk 8 KiB-aligned in the fp64 array)."""
     if world == 1:
         rows = 1
+    elif rows is None:
+        rows = 8 if world <= 2 else 4      # measured: more rows = better balance but more launch tails / masked brick planes
     per = -(-n // (rows * world))
     chunk = -(-per // align) * align
     return NodeSharding(n, world, rows, chunk)

@@ -667,6 +667,13 @@ void orc_node_positions(const double* gd, const uint32_t* res, uint64_t l_begin,
 #pragma omp parallel for schedule(static)
     for (long long l = (long long)l_begin; l < (long long)l_end; l++) index_to_node_position(g, (unsigned)l, x + 3 * (l - l_begin));
 }
+// indexToNodePosition for an arbitrary list of node ids (bench.py's strided CPU sample)
+void orc_node_positions_at(const double* gd, const uint32_t* res, const uint64_t* ids, uint64_t n, double* x)
+{
+    const Grid g = mkgrid(gd, res);
+#pragma omp parallel for schedule(static)
+    for (long long q = 0; q < (long long)n; q++) index_to_node_position(g, (unsigned)ids[q], x + 3 * q);
+}
 // addFunction node loop (cubic_lagrange_discrete_grid.cpp:806-817) with func = sign * md.signed_distance(x).distance
 // (cmd/generate_sdf/main.cpp:97,101).  schedule(static) like the reference.  nthreads<=0 -> OpenMP default.
 void orc_sample_sdf(void* h, const double* gd, const uint32_t* res, double sign, uint64_t l_begin, uint64_t l_end,

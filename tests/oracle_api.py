@@ -121,6 +121,12 @@ class Oracle:
         self.lib.orc_node_positions(_p(gd, _dp), _p(res, _u32p), C.c_uint64(l0), C.c_uint64(l1), _p(x, _dp))
         return x
 
+    def node_positions_at(self, gd, res, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        x = np.empty((len(ids), 3))
+        self.lib.orc_node_positions_at(_p(gd, _dp), _p(res, _u32p), ids.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(len(ids)), _p(x, _dp))
+        return x
+
     def build_cells(self, res, c0=0, c1=None):
         res = _u32(res)
         if c1 is None:
