@@ -23,6 +23,24 @@ inline P3 unit(P3 a) { const double l = len(a); return {a.x / l, a.y / l, a.z / 
 inline P3 crs(P3 a, P3 b) { return {a.y * b.z - a.z * b.y, -a.x * b.z + a.z * b.x, a.x * b.y - a.y * b.x}; }
 inline double at(const P3& p, int d) { return d == 0 ? p.x : (d == 1 ? p.y : p.z); }
 
+// static partition of [0, n) over the hardware threads; fn(begin, end)
+template <class Fn>
+void parallel_for(uint64_t n, Fn fn)
+{
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > 32) nt = 32;
+    if (n < 4096 || nt == 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    const uint64_t per = (n + nt - 1) / nt;
+    for (unsigned k = 0; k < nt; k++) {
+        const uint64_t b = k * per, e = std::min(n, b + per);
+        if (b >= e) break;
+        th.emplace_back([=, &fn]() { fn(b, e); });
+    }
+    for (auto& t : th) t.join();
+}
+
 struct Builder {
     const P3* V;
     const uint32_t* F;
@@ -118,42 +136,98 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
     bld.build(0, T, root_c, root_r, root_box, 1);
     out.max_depth = bld.max_depth.load();      // root sphere is computed and unused, as in the reference (:125,357)
 
-    // ---- pseudonormals (TriangleMeshDistance.h:359-420), in the reference's arrays first
+    // ---- pseudonormals (TriangleMeshDistance.h:359-420), in the reference's arrays first.
+    // The reference accumulates into per-vertex / per-edge sums while looping over the triangles in index order (an
+    // unordered_map keyed by the vertex pair for the edges).  The same sums, term by term in the same order, are produced
+    // here from a vertex -> (triangle, slot) incidence list, which makes every stage a parallel loop.
     out.pn_tri.assign(3 * nT, 0.0); out.pn_edge.assign(9 * nT, 0.0); out.pn_vert.assign(3 * nV, 0.0);
     P3* pt = reinterpret_cast<P3*>(out.pn_tri.data());
     P3* pe = reinterpret_cast<P3*>(out.pn_edge.data());
     P3* pv = reinterpret_cast<P3*>(out.pn_vert.data());
-    struct EdgeAcc { P3 n; int count; };
-    std::unordered_map<uint64_t, EdgeAcc> edges;
-    edges.reserve(2 * nT);
-    auto key_of = [nV](uint32_t i, uint32_t j) { return (uint64_t)std::min(i, j) * nV + (uint64_t)std::max(i, j); };
-    auto add_edge = [&](uint32_t i, uint32_t j, P3 n) {
-        auto it = edges.find(key_of(i, j));
-        if (it == edges.end()) edges.emplace(key_of(i, j), EdgeAcc{n, 1});
-        else { it->second.n = it->second.n + n; it->second.count++; }
-    };
-    for (int i = 0; i < T; i++) {
-        const uint32_t* t = F + 3 * (size_t)i;
-        const P3 a = V[t[0]], b = V[t[1]], c = V[t[2]];
-        const P3 n = unit(crs(b - a, c - a));
-        pt[i] = n;
-        const double al0 = std::acos(std::abs(dot3(unit(b - a), unit(c - a))));
-        const double al1 = std::acos(std::abs(dot3(unit(a - b), unit(c - b))));
-        const double al2 = std::acos(std::abs(dot3(unit(b - c), unit(a - c))));
-        pv[t[0]] = pv[t[0]] + P3{al0 * n.x, al0 * n.y, al0 * n.z};
-        pv[t[1]] = pv[t[1]] + P3{al1 * n.x, al1 * n.y, al1 * n.z};
-        pv[t[2]] = pv[t[2]] + P3{al2 * n.x, al2 * n.y, al2 * n.z};
-        add_edge(t[0], t[1], n); add_edge(t[1], t[2], n); add_edge(t[0], t[2], n);
+    std::vector<double> angle(3 * nT);
+    parallel_for(nT, [&](uint64_t i0, uint64_t i1) {
+        for (uint64_t i = i0; i < i1; i++) {
+            const uint32_t* t = F + 3 * i;
+            const P3 a = V[t[0]], b = V[t[1]], c = V[t[2]];
+            pt[i] = unit(crs(b - a, c - a));                                                  // :394
+            angle[3 * i + 0] = std::acos(std::abs(dot3(unit(b - a), unit(c - a))));          // :398-400
+            angle[3 * i + 1] = std::acos(std::abs(dot3(unit(a - b), unit(c - b))));
+            angle[3 * i + 2] = std::acos(std::abs(dot3(unit(b - c), unit(a - c))));
+        }
+    });
+    // incidence list in (triangle, slot) order
+    std::vector<uint32_t> inc_begin(nV + 1, 0), inc(3 * nT);
+    for (uint64_t i = 0; i < 3 * nT; i++) inc_begin[F[i] + 1]++;
+    for (uint64_t v = 0; v < nV; v++) inc_begin[v + 1] += inc_begin[v];
+    {
+        std::vector<uint32_t> cursor(inc_begin.begin(), inc_begin.end() - 1);
+        for (uint64_t i = 0; i < 3 * nT; i++) inc[cursor[F[i]]++] = (uint32_t)i;              // entry = 3*triangle + slot
     }
-    for (uint64_t i = 0; i < nV; i++) pv[i] = unit(pv[i]);           // Vec3r::normalize: same divisions
-    for (int i = 0; i < T; i++) {
-        const uint32_t* t = F + 3 * (size_t)i;
-        pe[3 * i + 0] = unit(edges.find(key_of(t[0], t[1]))->second.n);
-        pe[3 * i + 1] = unit(edges.find(key_of(t[1], t[2]))->second.n);
-        pe[3 * i + 2] = unit(edges.find(key_of(t[0], t[2]))->second.n);
-    }
-    out.flags = 0;
-    for (const auto& kv : edges) { if (kv.second.count == 1) out.flags |= 1; else if (kv.second.count > 2) out.flags |= 2; }
+    parallel_for(nV, [&](uint64_t v0, uint64_t v1) {
+        for (uint64_t v = v0; v < v1; v++) {
+            P3 acc = {0, 0, 0};                                                               // :385
+            for (uint32_t k = inc_begin[v]; k < inc_begin[v + 1]; k++) {
+                const double al = angle[inc[k]];
+                const P3 n = pt[inc[k] / 3];
+                acc = acc + P3{al * n.x, al * n.y, al * n.z};                                 // :401-403
+            }
+            pv[v] = unit(acc);                                                                // :411-413 (same divisions)
+        }
+    });
+    std::atomic<int> flags{0};
+    parallel_for(nT, [&](uint64_t i0, uint64_t i1) {
+        int local = 0;
+        for (uint64_t i = i0; i < i1; i++) {
+            const uint32_t* t = F + 3 * i;
+            const uint32_t ea[3] = {t[0], t[1], t[0]}, eb[3] = {t[1], t[2], t[2]};           // E01, E12, E02 (:406-408, :417-419)
+            for (int s = 0; s < 3; s++) {
+                const uint32_t lo = std::min(ea[s], eb[s]), hi = std::max(ea[s], eb[s]);
+                P3 acc = {0, 0, 0};
+                int count = 0;
+                uint32_t prev_tri = 0xffffffffu;
+                for (uint32_t k = inc_begin[lo]; k < inc_begin[lo + 1]; k++) {               // triangles touching `lo`, in index order
+                    const uint32_t tri = inc[k] / 3;
+                    if (tri == prev_tri) continue;                                            // vertex repeated inside one triangle
+                    prev_tri = tri;
+                    const uint32_t* u = F + 3 * (size_t)tri;
+                    const uint32_t ua[3] = {u[0], u[1], u[0]}, ub[3] = {u[1], u[2], u[2]};
+                    for (int q = 0; q < 3; q++)
+                        if (std::min(ua[q], ub[q]) == lo && std::max(ua[q], ub[q]) == hi) {
+                            acc = (count == 0) ? pt[tri] : acc + pt[tri];                     // first: assignment (:368), then += (:372)
+                            count++;
+                        }
+                }
+                pe[3 * i + s] = unit(acc);
+                if (count == 1) local |= 1; else if (count > 2) local |= 2;                   // :422-438
+            }
+        }
+        flags.fetch_or(local);
+    });
+    out.flags = flags.load();
+
+    // ---- device records in leaf order
+    out.leaves.assign(nT, LeafRecord());
+    out.normals.assign(nT, PseudoNormals());
+    parallel_for(nT, [&](uint64_t p0, uint64_t p1) {
+        for (uint64_t pos = p0; pos < p1; pos++) {
+            const int id = out.order[pos];
+            const uint32_t* t = F + 3 * (size_t)id;
+            const P3 v0 = V[t[0]], v1 = V[t[1]], v2 = V[t[2]];
+            const P3 e0 = v1 - v0, e1 = v2 - v0;                            // TriangleMeshDistance.h:567-568
+            LeafRecord& L = out.leaves[pos];
+            L.v0[0] = v0.x; L.v0[1] = v0.y; L.v0[2] = v0.z;
+            L.e0[0] = e0.x; L.e0[1] = e0.y; L.e0[2] = e0.z;
+            L.e1[0] = e1.x; L.e1[1] = e1.y; L.e1[2] = e1.z;
+            L.a00 = dot3(e0, e0); L.a01 = dot3(e0, e1); L.a11 = dot3(e1, e1);  // :569-571
+            L.det = std::abs(L.a00 * L.a11 - L.a01 * L.a01);                   // :575
+            L.inv_det = 1 / L.det;                                            // :675
+            L.denom = L.a00 - 2 * L.a01 + L.a11;                              // :693,740,792
+            L.tri_id = id; L._pad = 0;
+            PseudoNormals& N = out.normals[pos];
+            const P3 src[7] = {pv[t[0]], pv[t[1]], pv[t[2]], pe[3 * id + 0], pe[3 * id + 1], pe[3 * id + 2], pt[id]};
+            for (int k = 0; k < 7; k++) { N.n[k][0] = src[k].x; N.n[k][1] = src[k].y; N.n[k][2] = src[k].z; }
+        }
+    });
 
     // ---- fp32 shadow of the sphere pairs (filter only), relative to the bounding-box centre
     {
@@ -183,27 +257,6 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
         std::vector<double>().swap(out.boxes);
     }
 
-    // ---- device records in leaf order
-    out.leaves.assign(nT, LeafRecord());
-    out.normals.assign(nT, PseudoNormals());
-    for (int pos = 0; pos < T; pos++) {
-        const int id = out.order[pos];
-        const uint32_t* t = F + 3 * (size_t)id;
-        const P3 v0 = V[t[0]], v1 = V[t[1]], v2 = V[t[2]];
-        const P3 e0 = v1 - v0, e1 = v2 - v0;                            // TriangleMeshDistance.h:567-568
-        LeafRecord& L = out.leaves[pos];
-        L.v0[0] = v0.x; L.v0[1] = v0.y; L.v0[2] = v0.z;
-        L.e0[0] = e0.x; L.e0[1] = e0.y; L.e0[2] = e0.z;
-        L.e1[0] = e1.x; L.e1[1] = e1.y; L.e1[2] = e1.z;
-        L.a00 = dot3(e0, e0); L.a01 = dot3(e0, e1); L.a11 = dot3(e1, e1);  // :569-571
-        L.det = std::abs(L.a00 * L.a11 - L.a01 * L.a01);                   // :575
-        L.inv_det = 1 / L.det;                                            // :675
-        L.denom = L.a00 - 2 * L.a01 + L.a11;                              // :693,740,792
-        L.tri_id = id; L._pad = 0;
-        PseudoNormals& N = out.normals[pos];
-        const P3 src[7] = {pv[t[0]], pv[t[1]], pv[t[2]], pe[3 * id + 0], pe[3 * id + 1], pe[3 * id + 2], pt[id]};
-        for (int k = 0; k < 7; k++) { N.n[k][0] = src[k].x; N.n[k][1] = src[k].y; N.n[k][2] = src[k].z; }
-    }
     return true;
 }
 
