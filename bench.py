@@ -130,6 +130,8 @@ def host_cpu_info():
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_sample_rate(mesh, mn, mx, res, seconds, steps=1, warmup=0):
     """Times the reference's CPU path on a strided sample of the node loop.  Returns (nodes/s list per step, info)."""
+    # all host threads this process may use -- set before the OpenMP runtime starts, because torchrun exports OMP_NUM_THREADS=1
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("DG_CPU_THREADS") or str(len(os.sched_getaffinity(0)))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_api import Oracle, RefMesh, have_ref
     orc = Oracle()
@@ -144,7 +146,7 @@ def cpu_sample_rate(mesh, mn, mx, res, seconds, steps=1, warmup=0):
         x = _positions(orc, gd, r, ids)
         t0 = time.perf_counter()
         if kind == "reference":
-            m.sample_points(x)
+            m.sample_points(x, nthreads=threads)
         else:
             m.distance(x)
         return time.perf_counter() - t0

@@ -122,8 +122,7 @@ struct dg_mesh {
     DevBuf<SpherePair> d_spheres;
     DevBuf<LeafRecord> d_leaves;
     DevBuf<PseudoNormals> d_normals;
-    DevBuf<SpherePairF> d_spheres_f;
-    DevBuf<BoxPairF> d_boxes_f;
+    DevBuf<float4> d_nodes_f;
     DeviceBvh dev;
     int device = 0;
     uint64_t build_us = 0, upload_us = 0;
@@ -260,15 +259,19 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     DG_CUDA_M(m->d_spheres.alloc(nT));
     DG_CUDA_M(m->d_leaves.alloc(nT));
     DG_CUDA_M(m->d_normals.alloc(nT));
-    DG_CUDA_M(m->d_spheres_f.alloc(nT));
-    DG_CUDA_M(m->d_boxes_f.alloc(nT));
+    DG_CUDA_M(m->d_nodes_f.alloc(nT * K1_NODEF_STRIDE));
     DG_CUDA_M(cudaMemcpy(m->d_spheres.p, m->host.spheres.data(), nT * sizeof(SpherePair), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_leaves.p, m->host.leaves.data(), nT * sizeof(LeafRecord), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_normals.p, m->host.normals.data(), nT * sizeof(PseudoNormals), cudaMemcpyHostToDevice));
-    DG_CUDA_M(cudaMemcpy(m->d_spheres_f.p, m->host.spheres_f.data(), nT * sizeof(SpherePairF), cudaMemcpyHostToDevice));
-    m->dev.spheres_f = m->d_spheres_f.p;
-    DG_CUDA_M(cudaMemcpy(m->d_boxes_f.p, m->host.boxes_f.data(), nT * sizeof(BoxPairF), cudaMemcpyHostToDevice));
-    m->dev.boxes_f = m->d_boxes_f.p;
+    {   // interleave the fp32 sphere pair and box pair of every internal node into one record
+        std::vector<float4> rec(nT * K1_NODEF_STRIDE, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (uint64_t i = 0; i < nT; i++) {
+            std::memcpy(&rec[i * K1_NODEF_STRIDE], &m->host.spheres_f[i], sizeof(SpherePairF));
+            std::memcpy(&rec[i * K1_NODEF_STRIDE + 2], &m->host.boxes_f[i], sizeof(BoxPairF));
+        }
+        DG_CUDA_M(cudaMemcpy(m->d_nodes_f.p, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    m->dev.nodes_f = m->d_nodes_f.p;
     for (int d = 0; d < 3; d++) m->dev.ctr[d] = m->host.center[d];
     m->dev.half_extent = (float)m->host.half_extent * 1.0000002f;   // rounded up
     m->dev.spheres = m->d_spheres.p; m->dev.leaves = m->d_leaves.p; m->dev.normals = m->d_normals.p;
@@ -300,7 +303,7 @@ int dg_mesh_info(const dg_mesh* m, uint64_t info[8])
     if (!m || !info) return fail(DG_ERR_INVALID, "dg_mesh_info: NULL argument");
     info[0] = m->host.n_vertices; info[1] = m->host.n_triangles; info[2] = (uint64_t)m->dev.stack_depth;
     info[3] = (uint64_t)m->host.flags;
-    info[4] = m->d_spheres.bytes() + m->d_leaves.bytes() + m->d_normals.bytes() + m->d_spheres_f.bytes() + m->d_boxes_f.bytes();
+    info[4] = m->d_spheres.bytes() + m->d_leaves.bytes() + m->d_normals.bytes() + m->d_nodes_f.bytes();
     info[5] = m->build_us; info[6] = m->upload_us; info[7] = 0;
     return DG_OK;
 }

@@ -206,13 +206,16 @@ __device__ __forceinline__ double sphere_dist(double px, double py, double pz, d
 // ---------------------------------------------------------------------------------------------------------------
 struct MeshDev {
     const SpherePair* spheres;
-    const SpherePairF* spheres_f;
-    const BoxPairF* boxes_f;
+    const float4* nodes_f;                 // [T][K1_NODEF_STRIDE]: sphere pair (2 float4) + box pair (3 float4)
     const LeafRecord* leaves;
     double cx, cy, cz;
     float half_extent;
     int n_tri;
 };
+
+#if K1_PREFETCH
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
 
 __device__ __forceinline__ float sqrt_approx(float x)
 {
@@ -292,7 +295,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
 #if K1_BOX_SKIP
                         {   // the best has usually shrunk since this sibling was deferred: box test against the current best
                             const bool is_left = (r >> 31) != 0u;
-                            const float* bx = reinterpret_cast<const float*>(M.boxes_f + (is_left ? re : rb)) + (is_left ? 0 : 6);
+                            const float* bx = reinterpret_cast<const float*>(M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE + 2) + (is_left ? 0 : 6);
                             const float gx = fmaxf(fmaxf(__ldg(bx) - qx, qx - __ldg(bx + 3)), 0.f), gy = fmaxf(fmaxf(__ldg(bx + 1) - qy, qy - __ldg(bx + 4)), 0.f),
                                         gz = fmaxf(fmaxf(__ldg(bx + 2) - qz, qz - __ldg(bx + 5)), 0.f);
                             if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) continue;   // visiting it could not change anything
@@ -312,8 +315,16 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                 bool decided = false;
 #if K1_FILTER
                 {
-                    const float4* f4 = reinterpret_cast<const float4*>(M.spheres_f + m);
+                    const float4* f4 = M.nodes_f + (size_t)m * K1_NODEF_STRIDE;
                     const float4 l4 = __ldg(f4), r4 = __ldg(f4 + 1);
+#if K1_PREFETCH
+                    // whichever child is entered next, its record is needed by the very next step of this lane: pull both into L1 now
+                    if (m - b == 1) prefetch_l1(M.leaves + b); else prefetch_l1(M.nodes_f + (size_t)((b + m) >> 1) * K1_NODEF_STRIDE);
+                    if (e - m == 1) prefetch_l1(M.leaves + m); else prefetch_l1(M.nodes_f + (size_t)((m + e) >> 1) * K1_NODEF_STRIDE);
+#endif
+#if K1_BOX_SKIP && K1_EARLY_BOX
+                    const float4 b0 = __ldg(f4 + 2), b1 = __ldg(f4 + 3), b2 = __ldg(f4 + 4);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
+#endif
                     const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
                     const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
                     const float dl = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) - l4.w;
@@ -330,8 +341,9 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     defer = !(d_second_f - E >= best_hi);
 #if K1_BOX_SKIP
                     if (decided && go_first) {
-                        const float4* bx = reinterpret_cast<const float4*>(M.boxes_f + m);
-                        const float4 b0 = __ldg(bx), b1 = __ldg(bx + 1), b2 = __ldg(bx + 2);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
+#if !K1_EARLY_BOX
+                        const float4 b0 = __ldg(f4 + 2), b1 = __ldg(f4 + 3), b2 = __ldg(f4 + 4);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
+#endif
                         const float lgx = fmaxf(fmaxf(b0.x - qx, qx - b0.w), 0.f), lgy = fmaxf(fmaxf(b0.y - qy, qy - b1.x), 0.f),
                                     lgz = fmaxf(fmaxf(b0.z - qz, qz - b1.y), 0.f);
                         const float rgx = fmaxf(fmaxf(b1.z - qx, qx - b2.y), 0.f), rgy = fmaxf(fmaxf(b1.w - qy, qy - b2.z), 0.f),
@@ -502,7 +514,7 @@ __global__ void fma_probe_kernel(double a, double b, double c, double* out) { ou
 }  // namespace
 
 static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)); }
-static inline MeshDev mesh_dev(const DeviceBvh& m) { return MeshDev{m.spheres, m.spheres_f, m.boxes_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri}; }
+static inline MeshDev mesh_dev(const DeviceBvh& m) { return MeshDev{m.spheres, m.nodes_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri}; }
 
 cudaError_t k1_configure(int stack_depth)
 {

@@ -33,6 +33,15 @@ constexpr int K1_THREADS = K1_THREADS_PER_BLOCK;
 #ifndef K1_FILTER
 #define K1_FILTER 1             // 1: fp32 interval filter for the sphere decisions (exact fp64 fallback); 0: all fp64
 #endif
+#ifndef K1_PREFETCH
+#define K1_PREFETCH 0            // prefetch.global.L1 of both children's records during a node step
+#endif
+#ifndef K1_NODEF_STRIDE
+#define K1_NODEF_STRIDE 5         // float4s per fp32 node record: 5 = packed 80 B, 6 = padded to 96 B
+#endif
+#ifndef K1_EARLY_BOX
+#define K1_EARLY_BOX 1           // issue the box loads together with the sphere loads (latency) instead of after the sphere decision
+#endif
 #ifndef K1_BOX_SKIP
 #define K1_BOX_SKIP 1           // skip subtrees whose box is certainly farther than the best (they cannot change the result)
 #endif
@@ -59,8 +68,7 @@ struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once b
     const SpherePair* spheres = nullptr;
     const LeafRecord* leaves = nullptr;
     const PseudoNormals* normals = nullptr;
-    const SpherePairF* spheres_f = nullptr;   // fp32 filter shadow (relative to ctr)
-    const BoxPairF* boxes_f = nullptr;         // fp32 child boxes (relative to ctr, rounded outward)
+    const float4* nodes_f = nullptr;          // fp32 record per internal node, K1_NODEF_STRIDE float4s: SpherePairF (2) + BoxPairF (3) [+ pad]
     double ctr[3] = {0, 0, 0};
     float half_extent = 0.f;
     int n_tri = 0;
