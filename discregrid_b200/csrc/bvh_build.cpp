@@ -113,7 +113,7 @@ struct Builder {
 
 }  // namespace
 
-bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err)
+bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err, bool with_leaf_shadow)
 {
     if (!Vd || !F || nT == 0 || nV == 0) { *err = "empty triangle list or vertex list"; return false; }
     if (nT >= (1ull << 25) || nV > (uint64_t)0x7fffffff) { *err = "mesh too large (< 2^25 triangles; int32 vertex indices as in the reference)"; return false; }
@@ -255,6 +255,19 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
             }
         }
         std::vector<double>().swap(out.boxes);
+        // fp32 triangle shadows in leaf order (all products formed in fp64, then rounded once)
+        if (with_leaf_shadow) out.leaves_f.assign(nT, LeafF());
+        if (with_leaf_shadow) parallel_for(nT, [&](uint64_t p0, uint64_t p1) {
+            for (uint64_t pos = p0; pos < p1; pos++) {
+                const LeafRecord& L = out.leaves[pos];
+                LeafF& f = out.leaves_f[pos];
+                double e2[3], n3[3];
+                for (int d = 0; d < 3; d++) { f.v0[d] = (float)(L.v0[d] - out.center[d]); f.e0[d] = (float)L.e0[d]; f.e1[d] = (float)L.e1[d]; e2[d] = L.e1[d] - L.e0[d]; }
+                n3[0] = L.e0[1] * L.e1[2] - L.e0[2] * L.e1[1]; n3[1] = L.e0[2] * L.e1[0] - L.e0[0] * L.e1[2]; n3[2] = L.e0[0] * L.e1[1] - L.e0[1] * L.e1[0];
+                f.d00 = (float)L.a00; f.d01 = (float)L.a01; f.d11 = (float)L.a11; f.d22 = (float)(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+                for (int d = 0; d < 3; d++) f.n[d] = (float)n3[d];
+            }
+        });
     }
 
     return true;

@@ -54,6 +54,15 @@ struct alignas(128) LeafRecord {
 };
 static_assert(sizeof(LeafRecord) == 128, "LeafRecord must be 128 bytes");
 
+// fp32 shadow of a triangle (relative to HostBvh::center), used only to REJECT leaf tests that provably cannot be accepted
+// (k1_sdf.cu, leaf filter): v0, e0, e1, |e0|^2, e0.e1, |e1|^2, |e1-e0|^2, n = e0 x e1.  Never contributes a value to the result.
+struct alignas(64) LeafF {
+    float v0[3], e0[3], e1[3];
+    float d00, d01, d11, d22;
+    float n[3];
+};
+static_assert(sizeof(LeafF) == 64, "LeafF must be 64 bytes");
+
 struct PseudoNormals { double n[7][3]; };   // V0 V1 V2 E01 E12 E02 F
 static_assert(sizeof(PseudoNormals) == 168, "PseudoNormals must be 168 bytes");
 
@@ -66,6 +75,7 @@ struct HostBvh {
     double center[3] = {0, 0, 0};           // bounding-box centre of the vertices
     double half_extent = 0;                 // max |v - center|_inf over the vertices
     std::vector<LeafRecord> leaves;         // [T]
+    std::vector<LeafF> leaves_f;            // [T]  fp32 shadow, relative to `center`
     std::vector<PseudoNormals> normals;     // [T]
     std::vector<int32_t> order;             // leaf position -> triangle id
     int max_depth = 0;                      // number of levels (root = 1)
@@ -77,7 +87,8 @@ struct HostBvh {
 };
 
 // Returns false (and leaves *err) on invalid input.
-bool build_host_bvh(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err);
+bool build_host_bvh(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err,
+                    bool with_leaf_shadow = false);
 
 // Re-expresses the implicit tree in the reference's explicit pre-order numbering (diagnostics only).
 void export_reference_tree(const HostBvh& bvh, double* spheres /*(2T-1) x 8*/, int32_t* kids /*(2T-1) x 2*/);

@@ -123,6 +123,7 @@ struct dg_mesh {
     DevBuf<LeafRecord> d_leaves;
     DevBuf<PseudoNormals> d_normals;
     DevBuf<float4> d_nodes_f;
+    DevBuf<LeafF> d_leaves_f;
     DeviceBvh dev;
     int device = 0;
     uint64_t build_us = 0, upload_us = 0;
@@ -248,7 +249,7 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     const auto t0 = std::chrono::steady_clock::now();
     const char* why = "";
     try {
-        if (!build_host_bvh(V, nV, F, nT, m->host, &why)) { delete m; return fail(DG_ERR_INVALID, "dg_mesh_create: %s", why); }
+        if (!build_host_bvh(V, nV, F, nT, m->host, &why, K1_LEAF_FILTER != 0)) { delete m; return fail(DG_ERR_INVALID, "dg_mesh_create: %s", why); }
     } catch (const std::bad_alloc&) { delete m; return fail(DG_ERR_NOMEM, "dg_mesh_create: out of host memory"); }
     const auto t1 = std::chrono::steady_clock::now();
     m->build_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
@@ -260,6 +261,11 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     DG_CUDA_M(m->d_leaves.alloc(nT));
     DG_CUDA_M(m->d_normals.alloc(nT));
     DG_CUDA_M(m->d_nodes_f.alloc(nT * K1_NODEF_STRIDE));
+#if K1_LEAF_FILTER
+    DG_CUDA_M(m->d_leaves_f.alloc(nT));
+    DG_CUDA_M(cudaMemcpy(m->d_leaves_f.p, m->host.leaves_f.data(), nT * sizeof(LeafF), cudaMemcpyHostToDevice));
+    m->dev.leaves_f = m->d_leaves_f.p;
+#endif
     DG_CUDA_M(cudaMemcpy(m->d_spheres.p, m->host.spheres.data(), nT * sizeof(SpherePair), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_leaves.p, m->host.leaves.data(), nT * sizeof(LeafRecord), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_normals.p, m->host.normals.data(), nT * sizeof(PseudoNormals), cudaMemcpyHostToDevice));
@@ -284,7 +290,8 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     // the device records are the product; the host copies of the big arrays are no longer needed
     std::vector<SpherePair>().swap(m->host.spheres);
     std::vector<SpherePairF>().swap(m->host.spheres_f);
-    std::vector<BoxPairF>().swap(m->host.boxes_f);   // keep `order`, V, F, pseudonormals for diagnostics
+    std::vector<BoxPairF>().swap(m->host.boxes_f);
+    std::vector<LeafF>().swap(m->host.leaves_f);   // keep `order`, V, F, pseudonormals for diagnostics
     std::vector<LeafRecord>().swap(m->host.leaves);
     std::vector<PseudoNormals>().swap(m->host.normals);
     *out = m;
@@ -303,7 +310,7 @@ int dg_mesh_info(const dg_mesh* m, uint64_t info[8])
     if (!m || !info) return fail(DG_ERR_INVALID, "dg_mesh_info: NULL argument");
     info[0] = m->host.n_vertices; info[1] = m->host.n_triangles; info[2] = (uint64_t)m->dev.stack_depth;
     info[3] = (uint64_t)m->host.flags;
-    info[4] = m->d_spheres.bytes() + m->d_leaves.bytes() + m->d_normals.bytes() + m->d_nodes_f.bytes();
+    info[4] = m->d_spheres.bytes() + m->d_leaves.bytes() + m->d_normals.bytes() + m->d_nodes_f.bytes() + m->d_leaves_f.bytes();
     info[5] = m->build_us; info[6] = m->upload_us; info[7] = 0;
     return DG_OK;
 }

@@ -158,24 +158,6 @@ __device__ __forceinline__ void finish_query(const LeafRecord* __restrict__ leav
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// _query (TriangleMeshDistance.h:514-562), iterative and WARP-SYNCHRONOUS.
-//
-// All 32 lanes of a warp call this together, each with its own query (`alive`).  Every lane walks the tree in the
-// reference's own order with its own stack of deferred siblings, but the warp executes ONE PHASE per iteration, chosen
-// by ballot so that each straight-line block runs converged:
-//   NODE : lanes at an internal node: two sphere tests, then descend + defer the sibling, or prune
-//   LEAF : lanes at a leaf: point-triangle test, accept if strictly closer
-//   POP  : lanes that pruned / finished a leaf: re-test deferred siblings (`d < result.distance`, :549/:557)
-// The phase holding the largest cost-weighted share of lanes runs; the other lanes idle for that iteration.  All lanes
-// start at the root together and -- being 32 adjacent grid nodes -- take mostly the same decisions, so the phases stay
-// largely aligned.  (Letting a finished lane start its next query immediately was tried and is ~1.6x SLOWER: lanes
-// then sit at unrelated depths of the tree and both phase alignment and cache sharing are lost.)
-//
-// Stack entry = 12 bytes: the sibling's sphere distance (fp64) + its leaf range packed in 32 bits.  A node at depth k
-// covers either floor(T/2^k) or that + 1 leaves (halving splits), so (begin, depth, +1 flag) identifies the range.
-// Layout [depth][lane] in shared memory: conflict-free whatever depth each lane is at.
-// ---------------------------------------------------------------------------------------------------------------
 // Stack entry = 8 bytes: the sibling's sphere distance rounded to fp32 + its leaf range packed in 32 bits.  A node at depth k
 // covers either floor(T/2^k) or that + 1 leaves (halving splits), so (begin, depth, +1 flag) identifies the range; bit 31
 // says whether the entry is its parent's LEFT child (needed to find its fp64 sphere again when the fp32 value cannot decide).
@@ -207,6 +189,7 @@ __device__ __forceinline__ double sphere_dist(double px, double py, double pz, d
 struct MeshDev {
     const SpherePair* spheres;
     const float4* nodes_f;                 // [T][K1_NODEF_STRIDE]: sphere pair (2 float4) + box pair (3 float4)
+    const LeafF* leaves_f;                 // [T] fp32 triangle shadows
     const LeafRecord* leaves;
     double cx, cy, cz;
     float half_extent;
@@ -222,6 +205,56 @@ __device__ __forceinline__ float sqrt_approx(float x)
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+
+// LEAF FILTER (K1_LEAF_FILTER): certified fp32 LOWER bound of the distance from the query to a triangle.
+//   * distance to each of the three closed edges (clamped parameter => an actual point of the edge, so each value is an upper
+//     bound of that edge's true distance up to rounding; their minimum is the true distance whenever the closest point is on the
+//     boundary, i.e. whenever the projection of the query falls outside the triangle);
+//   * distance to the supporting plane (<= the true distance always);
+//   * the projection is declared "outside" only if one edge function is negative beyond a tolerance that covers the fp32 rounding
+//     of the products and the 2^-24-relative perturbation of every coordinate (so: classified outside => truly outside).
+//   bound = outside ? min(edge distances) : min(plane distance, edge distances), minus 4E for the fp32 evaluation itself.
+// The caller rejects the leaf only if bound > best_hi + 2E (same slack accounting as the box skip).  On bunny/dragon this rejects
+// 83-90 % of the leaf tests; the rest (accepted ones, ties, near misses) take the exact fp64 test.  Prototype with 0 invalid
+// rejections in 3 M leaf tests: see DESIGN.md.
+__device__ __forceinline__ float dot3f(float ax, float ay, float az, float bx, float by, float bz) { return fmaf(az, bz, fmaf(ay, by, ax * bx)); }
+
+__device__ __forceinline__ float leaf_lower_bound(const LeafF* __restrict__ rec, float qx, float qy, float qz, float E)
+{
+    const float4* r4 = reinterpret_cast<const float4*>(rec);
+    const float4 a = __ldg(r4), b = __ldg(r4 + 1), c = __ldg(r4 + 2), d = __ldg(r4 + 3);
+    // a = v0.xyz e0.x | b = e0.yz e1.xy | c = e1.z d00 d01 d11 | d = d22 n.xyz
+    const float e0x = a.w, e0y = b.x, e0z = b.y, e1x = b.z, e1y = b.w, e1z = c.x;
+    const float d00 = c.y, d01 = c.z, d11 = c.w, d22 = d.x;
+    const float wx = qx - a.x, wy = qy - a.y, wz = qz - a.z;                       // w = q - v0
+    const float w0 = dot3f(wx, wy, wz, e0x, e0y, e0z), w1 = dot3f(wx, wy, wz, e1x, e1y, e1z);
+    // edge 01: v0 + t e0
+    float t = (d00 > 0.f) ? __fdividef(w0, d00) : 0.f; t = fminf(fmaxf(t, 0.f), 1.f);
+    float rx = wx - t * e0x, ry = wy - t * e0y, rz = wz - t * e0z;
+    float mseg = dot3f(rx, ry, rz, rx, ry, rz);
+    // edge 02: v0 + t e1
+    t = (d11 > 0.f) ? __fdividef(w1, d11) : 0.f; t = fminf(fmaxf(t, 0.f), 1.f);
+    rx = wx - t * e1x; ry = wy - t * e1y; rz = wz - t * e1z;
+    mseg = fminf(mseg, dot3f(rx, ry, rz, rx, ry, rz));
+    // edge 12: v1 + t (e1 - e0), w' = w - e0
+    const float e2x = e1x - e0x, e2y = e1y - e0y, e2z = e1z - e0z;
+    const float ux = wx - e0x, uy = wy - e0y, uz = wz - e0z;
+    const float u2 = dot3f(ux, uy, uz, e2x, e2y, e2z);
+    t = (d22 > 0.f) ? __fdividef(u2, d22) : 0.f; t = fminf(fmaxf(t, 0.f), 1.f);
+    rx = ux - t * e2x; ry = uy - t * e2y; rz = uz - t * e2z;
+    mseg = fminf(mseg, dot3f(rx, ry, rz, rx, ry, rz));
+    // plane
+    const float nn = dot3f(d.y, d.z, d.w, d.y, d.z, d.w), wn = dot3f(wx, wy, wz, d.y, d.z, d.w);
+    const float plane2 = (nn > 0.f) ? __fdividef(wn * wn, nn) : 0.f;
+    // is the projection certainly outside the triangle?
+    const float p1 = d11 * w0, p2 = d01 * w1, p3 = d00 * w1, p4 = d01 * w0, p5 = d00 * d11, p6 = d01 * d01;
+    const float numv = p1 - p2, numu = p3 - p4, den = p5 - p6;
+    const float S = d00 + d11, W = sqrt_approx(dot3f(wx, wy, wz, wx, wy, wz));
+    const float tol = 32.f * (1.2e-7f * (fabsf(p1) + fabsf(p2) + fabsf(p3) + fabsf(p4) + p5 + p6) + 0.25f * E * S * (W + sqrt_approx(S)));
+    const bool outside = (numv < -tol) || (numu < -tol) || (den - numu - numv < -tol);
+    const float lb2 = outside ? mseg : fminf(plane2, mseg);
+    return sqrt_approx(fmaxf(lb2, 0.f)) - 4.f * E;      // NaN (degenerate input) compares false in the caller: no rejection
 }
 
 // _query (TriangleMeshDistance.h:514-562), iterative and WARP-SYNCHRONOUS.
@@ -240,7 +273,7 @@ __device__ __forceinline__ float sqrt_approx(float x)
 __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool alive, double px, double py, double pz,
                                                         unsigned* stack_rng, float* stack_d, int stride)
 {
-    enum { NODE = 0, LEAF = 1, POP = 2, DONE = 3 };
+    enum { NODE = 0, LEAF = 1, POP = 2, DONE = 3, LEAFX = 4 };     // LEAF: filter pending; LEAFX: exact fp64 test needed
     const int n_tri = M.n_tri;
     QueryResult res;
     res.dist = DBL_MAX; res.s = 0; res.t = 0; res.pos = -1; res.entity = 0;
@@ -261,15 +294,19 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
     // The running best only shrinks, so a subtree found hopeless stays hopeless and its deferred re-test can be dropped too.
     const float tiny_best = 1.0e-6f * Mq;
     float skip_sq = __int_as_float(0x7f800000);              // (best_hi + 2E)^2 rounded up; +inf = never skip
+    float skip_lin = __int_as_float(0x7f800000);             // best_hi + 2E rounded up
     int b = 0, e = n_tri, depth = 0, sp = 0;
     int state = alive ? ((n_tri == 1) ? LEAF : NODE) : DONE;
     for (;;) {
-        // two ballots carry the 2-bit state of all 32 lanes
+        // three ballots carry the 3-bit state of all 32 lanes
         const unsigned bit0 = __ballot_sync(0xffffffffu, state & 1), bit1 = __ballot_sync(0xffffffffu, state & 2);
+        const unsigned bit2 = K1_LEAF_FILTER ? __ballot_sync(0xffffffffu, state & 4) : 0u;
         if ((bit0 & bit1) == 0xffffffffu) break;                               // every lane DONE
-        const int n_node = __popc(~(bit0 | bit1)), n_leaf = __popc(bit0 & ~bit1), n_pop = __popc(~bit0 & bit1);
-        const bool pop_phase = K1_POP_WEIGHT * n_pop >= K1_NODE_WEIGHT * n_node && K1_POP_WEIGHT * n_pop >= K1_LEAF_WEIGHT * n_leaf;
-        if (pop_phase) {
+        const int w_node = K1_NODE_WEIGHT * __popc(~(bit0 | bit1 | bit2)), w_pop = K1_POP_WEIGHT * __popc(~bit0 & bit1);
+        const int w_leaff = K1_LEAF_FILTER ? K1_LEAFF_WEIGHT * __popc(bit0 & ~bit1) : 0;
+        const int w_leafx = K1_LEAF_WEIGHT * __popc(K1_LEAF_FILTER ? bit2 : (bit0 & ~bit1));
+        const int w_max = max(max(w_node, w_pop), max(w_leaff, w_leafx));
+        if (w_pop == w_max) {
             if (state == POP) {
                 // deferred siblings: the reference's second `if (d < result.distance)` (:549, :557) with the updated best
 #pragma unroll 1
@@ -307,7 +344,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     }
                 }
             }
-        } else if (n_node != 0 && K1_NODE_WEIGHT * n_node >= K1_LEAF_WEIGHT * n_leaf) {
+        } else if (w_node == w_max) {
             if (state == NODE) {                                                // internal (:537-561)
                 const int m = (b + e) >> 1;
                 bool left_first, go_first, go_second = false, defer = true;
@@ -396,15 +433,21 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     state = POP;
                 }
             }
-        } else if (n_leaf != 0) {
-            if (state == LEAF) {                                                // leaf (:517-534)
+        } else if (K1_LEAF_FILTER && w_leaff == w_max) {
+            if (state == LEAF) {
+                const float lb = leaf_lower_bound(M.leaves_f + b, qx, qy, qz, E);
+                state = (lb > skip_lin) ? POP : LEAFX;      // certainly not acceptable: the reference's test would fail
+            }
+        } else {
+            if (state == (K1_LEAF_FILTER ? LEAFX : LEAF)) {                     // leaf (:517-534)
                 double s, t; int ent;
                 const double d2 = tri_dist2(M.leaves + b, px, py, pz, s, t, ent);
                 if (d2 < best_sq) {
                     best = sqrt(d2);
                     best_sq = best * best;
                     best_lo = __double2float_rd(best); best_hi = __double2float_ru(best);
-                    { const float th = __fadd_ru(best_hi, E2); skip_sq = (K1_BOX_SKIP && best_lo >= tiny_best) ? __fmul_ru(th, th) : __int_as_float(0x7f800000); }
+                    { const float th = __fadd_ru(best_hi, E2); const bool ok = best_lo >= tiny_best;
+                      skip_sq = (K1_BOX_SKIP && ok) ? __fmul_ru(th, th) : __int_as_float(0x7f800000); skip_lin = ok ? th : __int_as_float(0x7f800000); }
                     res.s = s; res.t = t; res.pos = b; res.entity = ent;
                 }
                 state = POP;
@@ -514,7 +557,7 @@ __global__ void fma_probe_kernel(double a, double b, double c, double* out) { ou
 }  // namespace
 
 static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)); }
-static inline MeshDev mesh_dev(const DeviceBvh& m) { return MeshDev{m.spheres, m.nodes_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri}; }
+static inline MeshDev mesh_dev(const DeviceBvh& m) { return MeshDev{m.spheres, m.nodes_f, m.leaves_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri}; }
 
 cudaError_t k1_configure(int stack_depth)
 {

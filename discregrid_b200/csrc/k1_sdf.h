@@ -33,6 +33,14 @@ constexpr int K1_THREADS = K1_THREADS_PER_BLOCK;
 #ifndef K1_FILTER
 #define K1_FILTER 1             // 1: fp32 interval filter for the sphere decisions (exact fp64 fallback); 0: all fp64
 #endif
+#ifndef K1_LEAF_FILTER
+#define K1_LEAF_FILTER 0         // 1: reject leaf tests whose certified fp32 lower bound exceeds the best, as a phase of its own.
+                                // Exact (all parity tests pass) and rejects 83-90 % of the leaf tests, but measured SLOWER
+                                // (67.3 vs 54.6 ms): the extra phase costs more iterations than the fp64 tests it saves.  Off.
+#endif
+#ifndef K1_LEAFF_WEIGHT
+#define K1_LEAFF_WEIGHT 2
+#endif
 #ifndef K1_PREFETCH
 #define K1_PREFETCH 0            // prefetch.global.L1 of both children's records during a node step
 #endif
@@ -68,6 +76,7 @@ struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once b
     const SpherePair* spheres = nullptr;
     const LeafRecord* leaves = nullptr;
     const PseudoNormals* normals = nullptr;
+    const LeafF* leaves_f = nullptr;            // fp32 triangle shadows (leaf filter)
     const float4* nodes_f = nullptr;          // fp32 record per internal node, K1_NODEF_STRIDE float4s: SpherePairF (2) + BoxPairF (3) [+ pad]
     double ctr[3] = {0, 0, 0};
     float half_extent = 0.f;
