@@ -194,7 +194,7 @@ def main():
     config = {"workload": f"GenerateSDF addFunction: {WORKLOAD['mesh']}; {res[0]}x{res[1]}x{res[2]} grid = {n_nodes} nodes; "
                           "GenerateSDF-padded domain; fp64 bit-exact with the reference",
               "mesh_triangles": int(mesh.nFaces()), "grid": res, "nodes": n_nodes,
-              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"node-chunks x{world}" + ("" if world == 1 else ", 8 round-robin chunks per rank on 4 streams + per-row NCCL all-gather")}
+              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"node-chunks x{world}" + ("" if world == 1 else ", 2 round-robin chunks per rank on 2 streams + one in-place NCCL all-gather per row")}
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":

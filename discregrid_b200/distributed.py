@@ -3,7 +3,8 @@
 Nodes are independent (cubic_lagrange_discrete_grid.cpp:806-817 is an embarrassingly parallel loop; OpenMP already
 splits it statically), so the node index space [0, n) is cut into `rows * world` equal chunks dealt round-robin:
 rank r owns chunks r, r + world, r + 2*world, ...  Round-robin (rather than one contiguous slab per rank) evens out
-the spatially varying cost of the nearest-triangle query (far-from-surface nodes prune worse).  Row j of the deal
+the spatially varying cost of the nearest-triangle query (far-from-surface nodes prune worse).  Two rows per rank are the
+measured optimum (every extra launch adds a ~2 ms tail of long-running warps and partially masked bricks).  Row j of the deal
 is gathered by ONE all-gather whose output is the contiguous slice [j*world*chunk, (j+1)*world*chunk) of the full
 coefficient array -- so the gathered array is already in the reference's node order and no permutation pass is
 needed.  The only exchange step on the path is this all-gather of 8-byte coefficients (NCCL over NVLink on the GPU
@@ -37,7 +38,8 @@ def make_sharding(n, world, rows=None, align=1024):
     if world == 1:
         rows = 1
     elif rows is None:
-        rows = 8 if world <= 2 else 4      # measured: more rows = better balance but more launch tails / masked brick planes
+        rows = 2                           # measured at 8 ranks, 128^3: rows 1/2/4/8 -> slowest rank 10.6/9.7/10.4/11.0 ms (ideal 6.8):
+                                           # more rows = better balance but more launch tails and masked brick planes
     per = -(-n // (rows * world))
     chunk = -(-per // align) * align
     return NodeSharding(n, world, rows, chunk)
