@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (diagnostics / profiling)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (diagnostics / profiling)")
     ap.add_argument("--no-target", action="store_true", help="skip the 256^3 / 100k-triangle target-config leg")
+    ap.add_argument("--no-real", action="store_true", help="skip the leg on the reference meshes staged under oracle/_ref/resources")
     ap.add_argument("--no-density", action="store_true", help="skip the density-map (K3) leg (diagnostics / profiling)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -345,6 +346,15 @@ def main():
         ig_ms, _ = timed(lambda: interp_step(True), 20, 3)
         iv_ms, _ = timed(lambda: interp_step(False), 20, 3)
         ig_ms, iv_ms = float(np.mean(ig_ms)), float(np.mean(iv_ms))
+        # the same points sorted by cell (z-major cell index) separate gather locality from arithmetic
+        cell = ((xh - mn) / (mx - mn) * ires[0]).astype(np.int64).clip(0, ires[0] - 1)
+        order = np.argsort((cell[:, 2] * ires[1] + cell[:, 1]) * ires[0] + cell[:, 0], kind="stable")
+        xd_sorted = torch.from_numpy(np.ascontiguousarray(xh[order])).to(dev)
+        xd_keep = xd
+        xd = xd_sorted
+        is_ms, _ = timed(lambda: interp_step(True), 20, 3)
+        is_ms = float(np.mean(is_ms))
+        xd = xd_keep
         alg = 312.0 * (q_hi - q_lo)
         gbs = alg / (ig_ms * 1e-3) / 1e9
         # e2e through the host API
@@ -356,7 +366,7 @@ def main():
             capi.check(capi.lib.dg_interpolate_batch(fh, capi.ptr(xq, capi.F64P), len(xq), capi.ptr(ph, capi.F64P), capi.ptr(gh, capi.F64P)))
         dt = max_over_ranks((time.perf_counter() - t0) / 5)
         interp = {"metric": "interpolate()+gradient Mqueries/s", "value": nq / (ig_ms * 1e-3) / 1e6, "unit": "Mqueries/s",
-                  "value_only_mqps": nq / (iv_ms * 1e-3) / 1e6, "ms_per_launch": ig_ms, "queries": nq,
+                  "value_only_mqps": nq / (iv_ms * 1e-3) / 1e6, "cell_sorted_mqps": nq / (is_ms * 1e-3) / 1e6, "ms_per_launch": ig_ms, "queries": nq,
                   "config": {"workload": f"10M splitmix64 uniform queries (seed 0x5EED) on the {ires[0]}^3 SDF of the same mesh "
                                          f"({nn} nodes; packed cell blocks {16 * ires[0] * ires[1] * ires[2] * 16 / 1e9:.2f} GB >> L2)",
                              "field_build_s": build_s},
@@ -387,6 +397,38 @@ def main():
             rates, info = cpu_sample_rate(tmesh, tmn, tmx, [256, 256, 256], args.cpu_seconds)
             target["cpu_baseline"] = dict(info, value=float(np.mean(rates)), unit="nodes/s")
         del tfull, tsampler, tmd
+
+    # ---------------------------------------------------------------- the reference's own meshes (configs 2/3/5), when staged
+    real = None
+    res_dir = os.path.join(ROOT, "oracle", "_ref", "resources")      # copied there by `make -C oracle ref`; travels with the repo
+    if not args.no_real and os.path.isdir(res_dir):
+        real = []
+        for name, r3 in (("bunny.obj", 128), ("dragon.obj", 256), ("happy_buddha.obj", 256)):
+            path = os.path.join(res_dir, name)
+            if not os.path.exists(path):
+                continue
+            rmesh = dg.TriangleMesh(path)
+            t0 = time.perf_counter(); rmd = dg.TriangleMeshDistance(rmesh); t_create = time.perf_counter() - t0
+            rmn, rmx = dg.generate_sdf_domain(rmesh.vertices)
+            rdesc = dg.grid_desc(rmn, rmx, [r3] * 3)
+            rn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(rdesc.resolution, C.byref(rn))); rn = rn.value
+            rsh = make_sharding(rn, world)
+            rfull = torch.empty(rsh.padded, dtype=torch.float64, device=dev)
+            rs = ShardedSdfSampler(rmd, rdesc, rsh, rank)
+            r_ms, _ = timed(lambda: rs.step(rfull), 2, 1)
+            r_ms = float(np.mean(r_ms))
+            entry = {"mesh": name, "triangles": int(rmesh.nFaces()), "grid": r3, "nodes": rn, "ms_per_step": r_ms, "value": rn / (r_ms * 1e-3),
+                     "unit": "nodes/s", "mesh_create_s": t_create, "watertight_flags": rmd.info()["watertight_flags"]}
+            if name == "dragon.obj" and world == 1 and not args.no_density:      # config 5: GenerateDensityMap on the dragon SDF, h = 0.1, rho0 = 1000
+                fh = C.c_void_p(); sp = C.c_void_p(stream.cuda_stream)
+                capi.check(capi.lib.dg_field_create_device(C.byref(rdesc), C.c_void_p(rfull.data_ptr()), rn, sp, C.byref(fh)))
+                dens = torch.empty(rn, dtype=torch.float64, device=dev)
+                k3_ms, _ = timed(lambda: capi.check(capi.lib.dg_density_map_device(fh, 0.1, 1000.0, 0, 0, rn, C.c_void_p(dens.data_ptr()), sp)), 1, 1)
+                entry["density_map"] = {"h": 0.1, "rho0": 1000.0, "ms": float(k3_ms[0]), "value": rn / (k3_ms[0] * 1e-3), "unit": "nodes/s",
+                                        "nodes_in_quadrature_branch": int(((dens > 0) & (dens < 1e300)).sum().item())}
+                capi.lib.dg_field_destroy(fh); del dens
+            real.append(entry)
+            del rfull, rs, rmd
 
     # ---------------------------------------------------------------- density map (config 5 kernel), N = 1 only
     density = None
@@ -435,7 +477,7 @@ def main():
         line = {"metric": "SDF grid nodes/sec (addFunction)", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "target_config": target, "density_map": density,
+                "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "target_config": target, "reference_meshes": real, "density_map": density,
                 "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms}}
         print(json.dumps(line))
     if world > 1:
