@@ -21,6 +21,7 @@
 #include "k1_sdf.h"
 
 #include <cfloat>
+#include <mutex>
 
 namespace dgb {
 
@@ -345,6 +346,12 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                 }
             }
         } else if (w_node == w_max) {
+#if K1_NODE_REPEAT
+          // consecutive node steps are the common case (about three internal levels per leaf): stay in this phase, without
+          // re-voting the full state, while the lanes still sitting at an internal node remain at least half of the lanes that ran
+          int n_run = __popc(~(bit0 | bit1 | bit2));
+          for (int rep = 0;; rep++) {
+#endif
             if (state == NODE) {                                                // internal (:537-561)
                 const int m = (b + e) >> 1;
                 bool left_first, go_first, go_second = false, defer = true;
@@ -433,6 +440,13 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     state = POP;
                 }
             }
+#if K1_NODE_REPEAT
+            if (rep + 1 >= K1_NODE_REPEAT) break;
+            const int n_still = __popc(__ballot_sync(0xffffffffu, state == NODE));
+            if (2 * n_still < n_run || n_still == 0) break;
+            n_run = n_still;
+          }
+#endif
         } else if (K1_LEAF_FILTER && w_leaff == w_max) {
             if (state == LEAF) {
                 const float lb = leaf_lower_bound(M.leaves_f + b, qx, qy, qz, E);
@@ -559,12 +573,23 @@ __global__ void fma_probe_kernel(double a, double b, double c, double* out) { ou
 static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)); }
 static inline MeshDev mesh_dev(const DeviceBvh& m) { return MeshDev{m.spheres, m.nodes_f, m.leaves_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri}; }
 
+// The opt-in limit for dynamic shared memory is a per-function attribute: keep it at the maximum any live mesh has needed
+// (per device; meshes with different tree depths can coexist).
 cudaError_t k1_configure(int stack_depth)
 {
-    const size_t bytes = k1_smem_bytes(stack_depth);
-    cudaError_t e = cudaFuncSetAttribute(sdf_sample_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    static std::mutex mu;
+    static int configured[64] = {0};              // per device: stack depth the attribute currently allows
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mesh_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && configured[dev] >= stack_depth) return cudaSuccess;
+    const size_t bytes = k1_smem_bytes(stack_depth);
+    e = cudaFuncSetAttribute(sdf_sample_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mesh_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = stack_depth;
+    return e;
 }
 
 // Splits [l_begin, l_begin+count) into the (at most four) node arrays it touches and tiles whole slow-planes of each.

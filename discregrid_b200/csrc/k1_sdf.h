@@ -41,6 +41,9 @@ constexpr int K1_THREADS = K1_THREADS_PER_BLOCK;
 #ifndef K1_LEAFF_WEIGHT
 #define K1_LEAFF_WEIGHT 2
 #endif
+#ifndef K1_NODE_REPEAT
+#define K1_NODE_REPEAT 0         // >0: up to this many consecutive node steps per phase vote (while >= half of the lanes stay at internal nodes)
+#endif
 #ifndef K1_PREFETCH
 #define K1_PREFETCH 0            // prefetch.global.L1 of both children's records during a node step
 #endif

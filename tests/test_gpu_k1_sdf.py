@@ -190,3 +190,13 @@ def test_full_size_config1_properties(dg, orc):
     xs = g.nodePositions()[ids]
     want = orc.mesh(mesh.vertices, mesh.faces).distance(xs)[0]
     assert bits_equal(full[ids], want)
+
+
+def test_meshes_of_different_depth_coexist(dg, orc, box_mesh, torus_small):
+    """two live meshes with different tree depths (the shared-memory stack size is a per-kernel attribute)"""
+    big = dg.TriangleMeshDistance(torus_small)          # deep tree first
+    small = dg.TriangleMeshDistance(box_mesh)           # then a shallow one
+    x = np.random.default_rng(3).uniform(-1.4, 1.4, (5000, 3))
+    assert bits_equal(big.signed_distance(x).distance, orc.mesh(torus_small.vertices, torus_small.faces).distance(x)[0])
+    assert bits_equal(small.signed_distance(x).distance, orc.mesh(box_mesh.vertices, box_mesh.faces).distance(x)[0])
+    assert bits_equal(big.signed_distance(x).distance, orc.mesh(torus_small.vertices, torus_small.faces).distance(x)[0])
