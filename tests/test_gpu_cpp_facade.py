@@ -86,3 +86,28 @@ def test_generate_density_map_tool(dg, orc, tmp_path):
     assert alive.any() and (~alive).any() and bits_equal(red0[alive], full0[alive])     # same coefficients, same arithmetic
     # z-sorted node order: positions' Morton keys are non-decreasing is an internal detail; coefficient multiset is preserved
     assert set(np.unique(gr.m_nodes[0])) <= set(np.unique(g.m_nodes[0]))
+
+
+def test_discrete_field_to_bitmap_tool(dg, orc, tmp_path):
+    """N4: the reference's batched-interpolate consumer on the batch API: pixel values == oracle interpolation at the same samples"""
+    exe = _need("DiscreteFieldToBitmap")
+    out = tmp_path / "box.bmp"
+    r = subprocess.run([exe, "-s", "96", "-p", "xz", "-d", "0.25", "-o", str(out), os.path.join(GOLDEN, "box.cdf")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = out.read_bytes()
+    assert raw[:2] == b"BM" and int.from_bytes(raw[18:22], "little") == 96 and int.from_bytes(raw[22:26], "little") == 96
+    g = dg.CubicLagrangeDiscreteGrid(os.path.join(GOLDEN, "box.cdf"))
+    lo, hi = g.m_domain; diag = hi - lo
+    k = np.arange(96 * 96); i, j = k % 96, k // 96
+    x = np.empty((len(k), 3))
+    x[:, 0] = lo[0] + i / 96 * diag[0] + 0.5 * diag[0] / 96
+    x[:, 2] = lo[2] + j / 96 * diag[2] + 0.5 * diag[2] / 96
+    x[:, 1] = lo[1] + 0.5 * 1.25 * diag[1]
+    gd, res = orc.grid_desc(lo, hi, g.m_resolution, g.m_cell_size, g.m_inv_cell_size)
+    v = orc.interpolate(gd, res, g.m_nodes[0], x, grad=False)[0]
+    v[v == DBL_MAX] = 0.0
+    vn = np.where(v >= 0, v / abs(v.max()), v / abs(v.min()))
+    green = np.where(vn >= 0, np.clip(255.0 * (1 - vn), 0, 255), 0).astype(np.uint8)
+    blue = np.where(vn < 0, np.clip(255.0 * (1 + vn), 0, 255), 0).astype(np.uint8)
+    px = np.frombuffer(raw, np.uint8, 96 * 96 * 3, 54).reshape(-1, 3)          # BGR, 96*3 is a multiple of 4: no padding
+    assert np.array_equal(px[:, 1], green) and np.array_equal(px[:, 0], blue) and not px[:, 2].any()
