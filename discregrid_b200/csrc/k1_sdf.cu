@@ -494,9 +494,9 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
     const unsigned tf = t % S.tiles_f; t /= S.tiles_f;
     const unsigned tm = t % S.tiles_m; const unsigned ts = t / S.tiles_m;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned f = tf * (unsigned)(K1_THREADS / 8) + warp * 4u + (lane & 3u);
-    const unsigned m = tm * 4u + ((lane >> 2) & 3u);
-    const unsigned sl = S.s0 + ts * 2u + (lane >> 4);
+    const unsigned f = tf * (unsigned)(K1_BRICK_F * (K1_THREADS / 32)) + warp * (unsigned)K1_BRICK_F + (lane % K1_BRICK_F);
+    const unsigned m = tm * (unsigned)K1_BRICK_M + ((lane / K1_BRICK_F) % K1_BRICK_M);
+    const unsigned sl = S.s0 + ts * (unsigned)K1_BRICK_S + (lane / (K1_BRICK_F * K1_BRICK_M));
     const unsigned l = S.l_base + (sl * S.Dm + m) * S.Df + f;
     const bool alive = (f < S.Df) && (m < S.Dm) && (sl < S.s1) && (l >= w.l_begin) && (l < w.l_end);
 
@@ -616,8 +616,9 @@ cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double 
         const uint64_t plane = (uint64_t)S.Dm * S.Df;
         S.s0 = (unsigned)((a - base[k]) / plane);
         S.s1 = (unsigned)((b - 1 - base[k]) / plane) + 1;
-        S.tiles_f = (S.Df + K1_THREADS / 8 - 1) / (K1_THREADS / 8); S.tiles_m = (S.Dm + 3) / 4;
-        const unsigned tiles_s = (S.s1 - S.s0 + 1) / 2;
+        const unsigned bf = K1_BRICK_F * (K1_THREADS / 32);
+        S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + K1_BRICK_M - 1) / K1_BRICK_M;
+        const unsigned tiles_s = (S.s1 - S.s0 + K1_BRICK_S - 1) / K1_BRICK_S;
         S.block_begin = blocks;
         blocks += S.tiles_f * S.tiles_m * tiles_s;
     }

@@ -41,6 +41,17 @@ constexpr int K1_THREADS = K1_THREADS_PER_BLOCK;
 #ifndef K1_LEAFF_WEIGHT
 #define K1_LEAFF_WEIGHT 2
 #endif
+// brick of nodes owned by one warp: fast x mid x slow = 32
+#ifndef K1_BRICK_F
+#define K1_BRICK_F 4
+#endif
+#ifndef K1_BRICK_M
+#define K1_BRICK_M 4
+#endif
+#ifndef K1_BRICK_S
+#define K1_BRICK_S 2
+#endif
+static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp");
 #ifndef K1_NODE_REPEAT
 #define K1_NODE_REPEAT 0         // >0: up to this many consecutive node steps per phase vote (while >= half of the lanes stay at internal nodes)
 #endif
