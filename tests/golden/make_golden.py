@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle_api import RefMesh, Oracle          # noqa: E402
+import ctypes as C                             # noqa: E402
 from discregrid_b200.mesh import bumpy_torus, uv_sphere   # noqa: E402 (pure numpy part of the package)
 
 REF_RES = "/root/reference/cmd/generate_sdf/resources"
@@ -52,4 +53,48 @@ xs = np.concatenate(pts, 0)
 d, near, ent, tri = refs.distance(xs, signed=True)
 np.savez_compressed(os.path.join(HERE, "ref_sphere_surface.npz"), x=xs, distance=d, nearest=near, entity=ent, triangle=tri,
                     sphere_args=np.array([12, 24, 0.75, 0.1, -0.2, 0.05]))
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Fixtures produced by the reference's OWN tools and grid class (unmodified sources compiled against the Eigen stand-in
+# oracle/ref_eigen; `make -C oracle ref`).  First the build is validated: its GenerateSDF must reproduce box.cdf byte for byte.
+import subprocess, tempfile
+from oracle_api import REF_BIN, RefGrid
+tmp = tempfile.mkdtemp()
+run = lambda *a: subprocess.run(list(a), check=True, capture_output=True)
+run(os.path.join(REF_BIN, "GenerateSDF"), "-r", "5 5 5", "-o", os.path.join(tmp, "box.cdf"), os.path.join(HERE, "box.obj"))
+assert open(os.path.join(tmp, "box.cdf"), "rb").read() == open(os.path.join(HERE, "box.cdf"), "rb").read(), "stand-in build does not reproduce box.cdf"
+
+sph = uv_sphere(10, 16, 0.5)
+sph.exportOBJ(os.path.join(HERE, "sphere.obj"))
+run(os.path.join(REF_BIN, "GenerateSDF"), "-r", "10 10 10", "-d", "-2 -2 -2 2 2 2", "-o", os.path.join(HERE, "ref_sphere.cdf"), os.path.join(HERE, "sphere.obj"))
+run(os.path.join(REF_BIN, "GenerateSDF"), "-i", "-r", "4 6 5", "-o", os.path.join(HERE, "ref_sphere_inverted_padded.cdf"), os.path.join(HERE, "sphere.obj"))
+run(os.path.join(REF_BIN, "GenerateDensityMap"), "-s", "0.15", "-r", "1000", "--no-reduction", "-o", os.path.join(HERE, "ref_sphere_noreduction.cdm"),
+    os.path.join(HERE, "ref_sphere.cdf"))
+run(os.path.join(REF_BIN, "GenerateDensityMap"), "-s", "0.15", "-r", "1000", "-o", os.path.join(HERE, "ref_sphere_reduced.cdm"), os.path.join(HERE, "ref_sphere.cdf"))
+run(os.path.join(REF_BIN, "DiscreteFieldToBitmap"), "-s", "64", "-p", "xz", "-d", "0.25", "-o", os.path.join(HERE, "ref_box_xz.bmp"), os.path.join(HERE, "box.cdf"))
+run(os.path.join(REF_BIN, "DiscreteFieldToBitmap"), "-s", "48", "-p", "yx", "-f", "1", "-c", "rs", "-o", os.path.join(HERE, "ref_sphere_density_yx.bmp"),
+    os.path.join(HERE, "ref_sphere_noreduction.cdm"))
+
+rng = np.random.default_rng(77)
+out = {}
+for tag, path, fields in (("box", "box.cdf", (0,)), ("red", "ref_sphere_reduced.cdm", (0, 1)), ("nr", "ref_sphere_noreduction.cdm", (1,))):
+    g = RefGrid(os.path.join(HERE, path))
+    dom = np.empty(6); res = np.empty(3, np.uint32); cell = np.empty(3); inv = np.empty(3); nc = C.c_uint64()
+    import ctypes as C2
+    g.lib.refg_info.argtypes = [C2.c_void_p, C2.POINTER(C2.c_double), C2.POINTER(C2.c_uint32), C2.POINTER(C2.c_double), C2.POINTER(C2.c_double), C2.POINTER(C2.c_uint64)]
+    nc = C2.c_uint64()
+    g.lib.refg_info(g.h, dom.ctypes.data_as(C2.POINTER(C2.c_double)), res.ctypes.data_as(C2.POINTER(C2.c_uint32)), cell.ctypes.data_as(C2.POINTER(C2.c_double)),
+                    inv.ctypes.data_as(C2.POINTER(C2.c_double)), C2.byref(nc))
+    lo, hi = dom[:3], dom[3:]
+    xq = lo - 0.03 * (hi - lo) + rng.random((6000, 3)) * 1.06 * (hi - lo)
+    xq[:4] = [lo, hi, 0.5 * (lo + hi), [hi[0], lo[1], hi[2]]]
+    out[tag + "_x"] = xq
+    for f in fields:
+        phi, grad = g.interpolate(f, xq, grad=True)
+        out[f"{tag}_f{f}_phi"], out[f"{tag}_f{f}_grad"] = phi, grad
+        out[f"{tag}_f{f}_phi_only"] = g.interpolate(f, xq, grad=False)[0]
+    if tag == "box":
+        ok, N, dN, c0, cells, phi2, grad2 = g.split(0, xq[:1500])
+        out.update(box_split_ok=ok, box_split_N=N, box_split_dN=dN, box_split_c0=c0, box_split_cell=cells, box_split_phi=phi2, box_split_grad=grad2)
+np.savez_compressed(os.path.join(HERE, "ref_grid_queries.npz"), **out)
 print("golden fixtures written to", HERE)

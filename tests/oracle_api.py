@@ -9,6 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libdgref.so")
 REF_RESOURCES = os.path.join(ROOT, "oracle", "_ref", "resources")
+REF_GRID_SO = os.path.join(ROOT, "oracle", "_ref", "libdiscregrid_ref.so")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 
 _dp = C.POINTER(C.c_double)
 _u32p = C.POINTER(C.c_uint32)
@@ -208,3 +210,42 @@ class RefMesh(_MeshBase):
         f.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_double, _dp, C.c_int]
         f(self.h, _p(x, _dp), len(x), sign, _p(out, _dp), nthreads)
         return out
+
+
+def have_ref_grid():
+    return os.path.exists(REF_GRID_SO)
+
+
+class RefGrid:
+    """The reference's own CubicLagrangeDiscreteGrid (unmodified sources compiled against the Eigen stand-in, oracle/Makefile)."""
+
+    def __init__(self, path):
+        self.lib = C.CDLL(REF_GRID_SO)
+        self.lib.refg_load.restype = C.c_void_p
+        self.lib.refg_load.argtypes = [C.c_char_p]
+        self.h = self.lib.refg_load(path.encode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.refg_destroy.argtypes = [C.c_void_p]
+            self.lib.refg_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def interpolate(self, field, x, grad=True, nthreads=0):
+        x = _f64(x).reshape(-1, 3)
+        phi = np.empty(len(x)); g = np.zeros((len(x), 3)) if grad else None
+        f = self.lib.refg_interpolate
+        f.argtypes = [C.c_void_p, C.c_uint, _dp, C.c_uint64, _dp, _dp, C.c_int]
+        f(self.h, field, _p(x, _dp), len(x), _p(phi, _dp), _p(g, _dp), nthreads)
+        return phi, g
+
+    def split(self, field, x):
+        x = _f64(x).reshape(-1, 3); n = len(x)
+        ok = np.zeros(n, np.int32); N = np.zeros((n, 32)); dN = np.zeros((n, 32, 3)); c0 = np.zeros((n, 3))
+        cell = np.zeros((n, 32), np.uint32); phi = np.zeros(n); grad = np.zeros((n, 3))
+        f = self.lib.refg_split
+        f.argtypes = [C.c_void_p, C.c_uint, _dp, C.c_uint64, _i32p, _dp, _dp, _dp, _u32p, _dp, _dp]
+        f(self.h, field, _p(x, _dp), n, _p(ok, _i32p), _p(N, _dp), _p(dN, _dp), _p(c0, _dp), _p(cell, _u32p), _p(phi, _dp), _p(grad, _dp))
+        return ok, N, dN, c0, cell, phi, grad
