@@ -376,6 +376,34 @@ def main():
                   "e2e": {"value": nq / dt / 1e6, "unit": "Mqueries/s", "h2d_bytes_per_step": 24 * nq, "d2h_bytes_per_step": 32 * nq,
                           "api": "dg_interpolate_batch(field, x_host, n, phi_host, grad_host)"}}
         capi.lib.dg_field_destroy(fh)
+        # CPU baseline of interpolate: the reference's own CubicLagrangeDiscreteGrid::interpolate (oracle/_ref/libdiscregrid_ref.so =
+        # its unmodified sources against the Eigen stand-in) in the OpenMP loop of cmd/discrete_field_to_bitmap/main.cpp:118-135
+        if rank == 0 and world == 1 and not args.no_cpu:
+            os.environ["OMP_NUM_THREADS"] = os.environ.get("DG_CPU_THREADS") or str(len(os.sched_getaffinity(0)))
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from oracle_api import Oracle, RefGrid, have_ref_grid
+            cres = [128, 128, 128]                               # a 256^3 .cdf is 3 GB on disk: the CPU arm reads the 128^3 field of the same mesh
+            cgrid = dg.CubicLagrangeDiscreteGrid(mn, mx, cres)
+            cgrid.addFunction(dg.MeshSignedDistance(md))
+            nq_cpu = 2_000_000
+            xc = np.ascontiguousarray(splitmix_points(nq_cpu, INTERP["seed"], mn, mx))
+            if have_ref_grid():
+                tmpf = "/tmp/_dg_bench_field.cdf"
+                cgrid.save(tmpf)
+                rg = RefGrid(tmpf)
+                rg.interpolate(0, xc[:100000], grad=True)
+                t0 = time.perf_counter(); pr, gr = rg.interpolate(0, xc, grad=True); t_cpu = time.perf_counter() - t0
+                kind = "reference"
+                rg.close(); os.remove(tmpf)
+            else:
+                orc = Oracle(); gd_c, r_c = orc.grid_desc(mn, mx, cres)
+                t0 = time.perf_counter(); pr, gr = orc.interpolate(gd_c, r_c, cgrid.m_nodes[0], xc, grad=True); t_cpu = time.perf_counter() - t0
+                kind = "port"
+            pg, gg = cgrid.interpolate(0, xc, gradient=True)
+            interp["cpu_baseline"] = {"value": nq_cpu / t_cpu / 1e6, "unit": "Mqueries/s", "kind": kind, "cores": int(os.environ["OMP_NUM_THREADS"]),
+                                      "sample": f"{nq_cpu} of the 10M queries on the 128^3 field of the same mesh (OpenMP parallel for, value+gradient)",
+                                      "bit_exact_vs_gpu": bool(np.array_equal(pr.view(np.uint64), pg.view(np.uint64)) and np.array_equal(gr.view(np.uint64), gg.view(np.uint64)))}
+            del cgrid
 
     # ---------------------------------------------------------------- north-star target config: 256^3 grid, 100,000-triangle mesh
     target = None

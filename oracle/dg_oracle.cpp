@@ -10,8 +10,16 @@
 //     coefficients bit-exact, 125x32 connectivity, grid constants, domain padding);
 //   * oracle/_ref/libdgref.so = the reference's own, unmodified TriangleMeshDistance.h
 //     compiled by oracle/Makefile (tree, pseudonormals and signed distances bit-exact);
+//   * the reference's own tools and grid class -- its UNMODIFIED discregrid/src/*.cpp and
+//     cmd/*/*.cpp compiled by oracle/Makefile against the Eigen stand-in oracle/ref_eigen
+//     (Eigen3 is not installed): GenerateSDF / GenerateDensityMap / DiscreteFieldToBitmap outputs
+//     and CubicLagrangeDiscreteGrid::interpolate / determineShapeFunctions results are committed
+//     as fixtures (tests/golden/make_golden.py) and reproduced bit for bit: interpolate incl.
+//     reduced fields, shape_function_ + Jacobian, the density map on every node.
+//     Caveat: the stand-in fixes Eigen's 3-term norm() order to (a0+a1)+a2 (Eigen >= 3.3); real
+//     Eigen could not be run here.  It touches only cell_diag, W(r) and the GenerateSDF padding;
 //   * mathematical identities of shape_function_ (nodal property, partition of unity,
-//     finite-difference Jacobian) -- the reference holds no stored interpolate() output.
+//     finite-difference Jacobian).
 //
 // Language note: this is C++ rather than plain C for one reason only -- the reference
 // BVH build (TriangleMeshDistance.h:494-499) orders triangles with the *unstable*
