@@ -75,6 +75,9 @@ run(os.path.join(REF_BIN, "DiscreteFieldToBitmap"), "-s", "64", "-p", "xz", "-d"
 run(os.path.join(REF_BIN, "DiscreteFieldToBitmap"), "-s", "48", "-p", "yx", "-f", "1", "-c", "rs", "-o", os.path.join(HERE, "ref_sphere_density_yx.bmp"),
     os.path.join(HERE, "ref_sphere_noreduction.cdm"))
 
+# a real mesh end to end through the reference tool (the mesh itself is not committed: GPU-side tests find it under oracle/_ref/resources)
+run(os.path.join(REF_BIN, "GenerateSDF"), "-r", "12 12 12", "-o", os.path.join(HERE, "ref_bunny_12.cdf"), os.path.join(REF_RES, "bunny.obj"))
+
 rng = np.random.default_rng(77)
 out = {}
 for tag, path, fields in (("box", "box.cdf", (0,)), ("red", "ref_sphere_reduced.cdm", (0, 1)), ("nr", "ref_sphere_noreduction.cdm", (1,))):

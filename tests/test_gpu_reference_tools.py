@@ -38,6 +38,18 @@ def test_generate_sdf_files_byte_identical(tmp_path):
     assert _same(out, os.path.join(GOLDEN, "ref_sphere_inverted_padded.cdf"))
 
 
+def test_generate_sdf_on_bunny_byte_identical(tmp_path):
+    """BASELINE config 2's mesh through the rebuilt tool vs the reference tool's own output (12^3 to keep the fixture small)"""
+    from conftest import ref_resource
+    exe = _tool("GenerateSDF")
+    obj = ref_resource("bunny.obj")
+    if obj is None:
+        pytest.skip("bunny.obj not staged (oracle/_ref/resources)")
+    out = str(tmp_path / "bunny.cdf")
+    assert subprocess.run([exe, "-r", "12 12 12", "-o", out, obj], capture_output=True).returncode == 0
+    assert _same(out, os.path.join(GOLDEN, "ref_bunny_12.cdf"))
+
+
 def test_generate_density_map_files_byte_identical(tmp_path):
     exe = _tool("GenerateDensityMap")
     src = os.path.join(GOLDEN, "ref_sphere.cdf")

@@ -99,3 +99,17 @@ def test_split_api_matches_reference_class(orc):
     cell_id = g["res"][1] * g["res"][0] * mi[:, 2] + g["res"][0] * mi[:, 1] + mi[:, 0]
     assert np.array_equal(g["cells"][0][cell_id], q["box_split_cell"][ok])
     assert bits_equal(q["box_split_phi"][ok], q["box_f0_phi"][:1500][ok]) and bits_equal(q["box_split_grad"][ok], q["box_f0_grad"][:1500][ok])
+
+
+def test_bunny_through_reference_tool(orc):
+    """the reference GenerateSDF on bunny.obj (12^3): oracle reproduces the file's coefficients (mesh from oracle/_ref/resources)"""
+    from conftest import ref_resource
+    path = ref_resource("bunny.obj")
+    if path is None:
+        pytest.skip("bunny.obj not staged")
+    g = read_cdf(os.path.join(GOLDEN, "ref_bunny_12.cdf"))
+    V, F = read_obj(path)
+    mn, mx = orc.generate_sdf_domain(V)
+    assert bits_equal(mn, g["mn"]) and bits_equal(mx, g["mx"])          # non-cubic bounding box: padding arithmetic incl. the norm order of the stand-in
+    gd, res = orc.grid_desc(mn, mx, g["res"])
+    assert bits_equal(orc.mesh(V, F).sample_sdf(gd, res), g["nodes"][0])
