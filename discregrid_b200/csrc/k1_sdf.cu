@@ -12,10 +12,16 @@
 // batched behind a ballot) and the caches: the 32 lanes of a warp are 32 adjacent grid nodes, so they fetch
 // mostly the same 64-byte sphere pairs and 128-byte triangle records.
 //
-// Data (see bvh_build.h): implicit tree over leaf ranges [b,e), sphere pair at spheres[(b+e)>>1], one
-// 128-byte record per triangle, one 7x3 pseudonormal block per triangle.  The per-lane stack of deferred
-// siblings (range + its sphere distance) lives in shared memory, laid out [depth][lane] so it is
-// bank-conflict-free whatever depth each lane is at.
+// Data (see bvh_build.h): implicit tree over leaf ranges [b,e); per internal node one 80-byte fp32 record (child spheres +
+// child boxes, relative to the mesh centre) that DECIDES, the 64-byte fp64 sphere pair at spheres[(b+e)>>1] for the rare
+// undecided case, one 128-byte fp64 record per triangle for the leaf test, one 7x3 pseudonormal block per triangle.  The
+// per-lane stack of deferred siblings (packed range + fp32 sphere distance, 8 bytes) lives in shared memory, laid out
+// [depth][lane] so it is bank-conflict-free whatever depth each lane is at.
+//
+// Structure of this file: tri_dist2 (leaf test) -> finish_query (nearest point + sign) -> [leaf_lower_bound: optional fp32
+// leaf filter, compiled out] -> nearest_triangle (the warp-synchronous traversal: NODE / LEAF / POP phases, fp32 interval
+// filter, exact-preserving shortcuts) -> the two kernels (grid nodes in 4x4x2 bricks; arbitrary points) -> launchers.
+// Tuning knobs and the measured variants are listed in k1_sdf.h / profiles/README.md.
 #include "dg_device.cuh"
 #include "bvh_build.h"
 #include "k1_sdf.h"
