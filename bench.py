@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (diagnostics / profiling)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (diagnostics / profiling)")
     ap.add_argument("--no-target", action="store_true", help="skip the 256^3 / 100k-triangle target-config leg")
+    ap.add_argument("--sharding", default="slab", choices=["slab", "chunks"], help="N>1: whole-plane slabs (one launch per rank) or round-robin node-id chunks")
     ap.add_argument("--no-real", action="store_true", help="skip the leg on the reference meshes staged under oracle/_ref/resources")
     ap.add_argument("--no-density", action="store_true", help="skip the density-map (K3) leg (diagnostics / profiling)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -184,7 +185,7 @@ def main():
 
     import discregrid_b200 as dg           # fails loudly if the CUDA library is not built
     from discregrid_b200 import _capi as capi
-    from discregrid_b200.distributed import make_sharding, allgather_rows, ShardedSdfSampler
+    from discregrid_b200.distributed import make_sharding, allgather_rows, ShardedSdfSampler, SlabSdfSampler
 
     mesh = dg.bumpy_torus(*WORKLOAD["torus"])
     mn, mx = dg.generate_sdf_domain(mesh.vertices)
@@ -195,7 +196,7 @@ def main():
     config = {"workload": f"GenerateSDF addFunction: {WORKLOAD['mesh']}; {res[0]}x{res[1]}x{res[2]} grid = {n_nodes} nodes; "
                           "GenerateSDF-padded domain; fp64 bit-exact with the reference",
               "mesh_triangles": int(mesh.nFaces()), "grid": res, "nodes": n_nodes,
-              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"node-chunks x{world}" + ("" if world == 1 else ", 2 round-robin chunks per rank on 2 streams + one in-place NCCL all-gather per row")}
+              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"x{world}" + ("" if world == 1 else (", slabs of whole plane pairs of the four node arrays: one launch per rank + one NCCL all-gather per node array" if args.sharding == "slab" else ", 2 round-robin node-id chunks per rank on 2 streams + one in-place NCCL all-gather per row"))}
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -242,7 +243,11 @@ def main():
     my_chunks = [(j, b, e) for (j, b, e) in sh.chunks_of(rank)]
     stream = torch.cuda.current_stream()
 
-    sdf_sampler = ShardedSdfSampler(md, desc, sh, rank)
+    if args.sharding == "slab":
+        sdf_sampler = SlabSdfSampler(md, desc, rank, world)
+        full = torch.empty(sdf_sampler.sh.padded, dtype=torch.float64, device=dev)
+    else:
+        sdf_sampler = ShardedSdfSampler(md, desc, sh, rank)
 
     def sdf_step():
         sdf_sampler.step(full)
@@ -278,8 +283,10 @@ def main():
         sdf_sampler.launch(full)
     k1_ms, _ = timed(k1_only, max(3, args.steps // 2), 1)
     k1_ms = float(np.mean(k1_ms))
-    my_nodes = sum(e - b for (_j, b, e) in my_chunks)
-    n_launch = sum(1 for (_j, b, e) in my_chunks if e > b)
+    if args.sharding == "slab":
+        my_nodes = sum(e - b for (b, e) in sdf_sampler.sh.ranges[rank]); n_launch = 1
+    else:
+        my_nodes = sum(e - b for (_j, b, e) in my_chunks); n_launch = sum(1 for (_j, b, e) in my_chunks if e > b)
     peaks, peak_src = measured_peaks()
     k1_alg_bytes = 8.0 * my_nodes + mesh_info["device_bytes"]          # 8 B/node written + mesh records read once
     k1_gbs = k1_alg_bytes / (k1_ms * 1e-3) / 1e9
@@ -293,12 +300,17 @@ def main():
     # ---------------------------------------------------------------- e2e: C-ABI with HOST buffers
     e2e = None
     if not args.no_e2e:
-        outs = [np.empty(max(0, e - b)) for (_j, b, e) in my_chunks]
+        if world == 1:
+            my_ranges = [(0, n_nodes)]
+        elif args.sharding == "slab":
+            my_ranges = [(b, e) for (b, e) in sdf_sampler.sh.ranges[rank] if e > b]
+        else:
+            my_ranges = [(b, e) for (_j, b, e) in my_chunks if e > b]
+        outs = [np.empty(e - b) for (b, e) in my_ranges]
 
         def e2e_step():
-            for (_j, b, e), o in zip(my_chunks, outs):
-                if e > b:
-                    capi.check(capi.lib.dg_sample_sdf(md.handle, C.byref(desc), 1.0, b, e, capi.ptr(o, capi.F64P)))
+            for (b, e), o in zip(my_ranges, outs):
+                capi.check(capi.lib.dg_sample_sdf(md.handle, C.byref(desc), 1.0, b, e, capi.ptr(o, capi.F64P)))
         for _ in range(2):
             e2e_step()
         barrier()
@@ -308,7 +320,7 @@ def main():
             e2e_step()
         torch.cuda.synchronize()
         dt = max_over_ranks((time.perf_counter() - t0) / n_e2e)
-        e2e = {"value": n_nodes / dt, "unit": "nodes/s", "h2d_bytes_per_step": C.sizeof(capi.GridDesc) * n_launch,
+        e2e = {"value": n_nodes / dt, "unit": "nodes/s", "h2d_bytes_per_step": C.sizeof(capi.GridDesc) * len(my_ranges),
                "d2h_bytes_per_step": 8 * n_nodes, "ms_per_step": dt * 1e3,
                "api": "dg_sample_sdf(mesh, grid, sign, l_begin, l_end, out_host): kernel + D2H of the coefficient array into a "
                       "pageable host buffer; the mesh/BVH was uploaded once by dg_mesh_create (as TriangleMeshDistance is built "
@@ -413,9 +425,8 @@ def main():
         tmn, tmx = dg.generate_sdf_domain(tmesh.vertices)
         tdesc = dg.grid_desc(tmn, tmx, [256, 256, 256])
         tn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(tdesc.resolution, C.byref(tn))); tn = tn.value
-        tsh = make_sharding(tn, world)
-        tfull = torch.empty(tsh.padded, dtype=torch.float64, device=dev)
-        tsampler = ShardedSdfSampler(tmd, tdesc, tsh, rank)
+        tsampler = SlabSdfSampler(tmd, tdesc, rank, world) if args.sharding == "slab" else ShardedSdfSampler(tmd, tdesc, make_sharding(tn, world), rank)
+        tfull = torch.empty(tsampler.sh.padded, dtype=torch.float64, device=dev)
         t_ms, _ = timed(lambda: tsampler.step(tfull), 3, 1)
         t_ms = float(np.mean(t_ms))
         target = {"workload": "north_star target: 256^3 grid (118,425,857 nodes), synthetic bumpy torus with exactly 100,000 triangles, "
@@ -440,9 +451,8 @@ def main():
             rmn, rmx = dg.generate_sdf_domain(rmesh.vertices)
             rdesc = dg.grid_desc(rmn, rmx, [r3] * 3)
             rn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(rdesc.resolution, C.byref(rn))); rn = rn.value
-            rsh = make_sharding(rn, world)
-            rfull = torch.empty(rsh.padded, dtype=torch.float64, device=dev)
-            rs = ShardedSdfSampler(rmd, rdesc, rsh, rank)
+            rs = SlabSdfSampler(rmd, rdesc, rank, world) if args.sharding == "slab" else ShardedSdfSampler(rmd, rdesc, make_sharding(rn, world), rank)
+            rfull = torch.empty(rs.sh.padded, dtype=torch.float64, device=dev)
             r_ms, _ = timed(lambda: rs.step(rfull), 2, 1)
             r_ms = float(np.mean(r_ms))
             entry = {"mesh": name, "triangles": int(rmesh.nFaces()), "grid": r3, "nodes": rn, "ms_per_step": r_ms, "value": rn / (r_ms * 1e-3),

@@ -59,6 +59,8 @@ SIGNATURES = {
     "dg_mesh_distance_device": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "dg_sample_sdf": (C.c_int, [_vp, _gp, C.c_double, C.c_uint64, C.c_uint64, _dp]),
     "dg_sample_sdf_device": (C.c_int, [_vp, _gp, C.c_double, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "dg_slab_ranges": (C.c_int, [_gp, C.c_uint32, C.c_uint32, _u64p]),
+    "dg_sample_sdf_slab_device": (C.c_int, [_vp, _gp, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp]),
     "dg_node_positions": (C.c_int, [_gp, C.c_uint64, C.c_uint64, _dp]),
     "dg_build_cells": (C.c_int, [_u32p, C.c_uint64, C.c_uint64, _u32p]),
     "dg_field_create": (C.c_int, [_gp, _dp, C.c_uint64, _u32p, C.c_uint64, _u32p, C.POINTER(_vp)]),

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -483,6 +484,44 @@ int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint6
             std::memcpy(out_host + off, g_pool.stage[(i - 1) & 1], cnt * sizeof(double));
         }
     }
+    return DG_OK;
+}
+
+// plane ranges of part `part` of `n_parts`: boundaries fall on even plane indices (a brick spans K1_BRICK_S = 2 planes)
+static void slab_planes(const GridDev& g, uint32_t part, uint32_t n_parts, unsigned pb[4], unsigned pe[4])
+{
+    const unsigned Ds[4] = {g.n[2] + 1, g.n[2] + 1, g.n[0] + 1, g.n[1] + 1};
+    for (int a = 0; a < 4; a++) {
+        const uint64_t groups = (Ds[a] + K1_BRICK_S - 1) / K1_BRICK_S;
+        const uint64_t q0 = groups * part / n_parts, q1 = groups * (part + 1) / n_parts;
+        pb[a] = (unsigned)std::min<uint64_t>(q0 * K1_BRICK_S, Ds[a]);
+        pe[a] = (unsigned)std::min<uint64_t>(q1 * K1_BRICK_S, Ds[a]);
+    }
+}
+
+int dg_slab_ranges(const dg_grid_desc* grid, uint32_t part, uint32_t n_parts, uint64_t ranges[8])
+{
+    GridDev g; const char* why = "";
+    if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_slab_ranges: %s", why);
+    if (!ranges || n_parts == 0 || part >= n_parts) return fail(DG_ERR_INVALID, "dg_slab_ranges: bad part / n_parts");
+    unsigned pb[4], pe[4];
+    slab_planes(g, part, n_parts, pb, pe);
+    const uint64_t base[4] = {0, g.nv, (uint64_t)g.nv + 2ull * g.ne_x, (uint64_t)g.nv + 2ull * (g.ne_x + (uint64_t)g.ne_y)};
+    const uint64_t plane[4] = {(uint64_t)(g.n[1] + 1) * (g.n[0] + 1), (uint64_t)(g.n[1] + 1) * 2 * g.n[0], (uint64_t)(g.n[2] + 1) * 2 * g.n[1],
+                               (uint64_t)(g.n[0] + 1) * 2 * g.n[2]};
+    for (int a = 0; a < 4; a++) { ranges[2 * a] = base[a] + plane[a] * pb[a]; ranges[2 * a + 1] = base[a] + plane[a] * pe[a]; }
+    return DG_OK;
+}
+
+int dg_sample_sdf_slab_device(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint32_t part, uint32_t n_parts, double* d_full, void* stream)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf_slab: mesh is NULL (not constructed)");
+    GridDev g; const char* why = "";
+    if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_sample_sdf_slab: %s", why);
+    if (n_parts == 0 || part >= n_parts || !d_full) return fail(DG_ERR_INVALID, "dg_sample_sdf_slab: bad part / n_parts / output");
+    unsigned pb[4], pe[4];
+    slab_planes(g, part, n_parts, pb, pe);
+    DG_LAUNCH(k1_launch_sample_slab(m->dev, g, sign, pb, pe, d_full, (cudaStream_t)stream));
     return DG_OK;
 }
 

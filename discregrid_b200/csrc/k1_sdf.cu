@@ -634,6 +634,33 @@ cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double 
     return cudaGetLastError();
 }
 
+cudaError_t k1_launch_sample_slab(const DeviceBvh& m, const GridDev& g, double sign, const unsigned plane_begin[4], const unsigned plane_end[4],
+                                  double* d_full, cudaStream_t stream)
+{
+    const unsigned nx = g.n[0], ny = g.n[1], nz = g.n[2];
+    const uint64_t base[4] = {0, g.nv, (uint64_t)g.nv + 2ull * g.ne_x, (uint64_t)g.nv + 2ull * (g.ne_x + (uint64_t)g.ne_y)};
+    const unsigned dims[4][3] = {{nz + 1, ny + 1, nx + 1}, {nz + 1, ny + 1, 2 * nx}, {nx + 1, nz + 1, 2 * ny}, {ny + 1, nx + 1, 2 * nz}};
+    K1Work w;
+    w.nseg = 0; w.l_begin = 0u; w.l_end = 0xffffffffu;          // whole planes: nothing to mask, out[l] is the final position
+    unsigned blocks = 0;
+    for (int k = 0; k < 4; k++) {
+        if (plane_begin[k] >= plane_end[k]) continue;
+        K1Segment& S = w.seg[w.nseg++];
+        S.kind = k; S.l_base = (unsigned)base[k];
+        S.Ds = dims[k][0]; S.Dm = dims[k][1]; S.Df = dims[k][2];
+        S.s0 = plane_begin[k]; S.s1 = plane_end[k];
+        const unsigned bf = K1_BRICK_F * (K1_THREADS / 32);
+        S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + K1_BRICK_M - 1) / K1_BRICK_M;
+        const unsigned tiles_s = (S.s1 - S.s0 + K1_BRICK_S - 1) / K1_BRICK_S;
+        S.block_begin = blocks;
+        blocks += S.tiles_f * S.tiles_m * tiles_s;
+    }
+    if (w.nseg == 0) return cudaSuccess;
+    for (int k = w.nseg; k < 4; k++) { w.seg[k] = w.seg[0]; w.seg[k].block_begin = 0xffffffffu; }
+    sdf_sample_nodes_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_full);
+    return cudaGetLastError();
+}
+
 cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t count, int is_signed, double* d_dist,
                                double* d_near, int* d_ent, int* d_tri, cudaStream_t stream)
 {

@@ -101,6 +101,9 @@ struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once b
 cudaError_t k1_configure(int stack_depth);
 cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double sign, uint64_t l_begin, uint64_t count,
                                    double* d_out, cudaStream_t stream);
+// slab form: planes [plane_begin[a], plane_end[a]) of node array a (a = 0..3), written at d_full[l]
+cudaError_t k1_launch_sample_slab(const DeviceBvh& m, const GridDev& g, double sign, const unsigned plane_begin[4], const unsigned plane_end[4],
+                                  double* d_full, cudaStream_t stream);
 cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t count, int is_signed, double* d_dist,
                                double* d_near, int* d_ent, int* d_tri, cudaStream_t stream);
 cudaError_t k1_launch_node_positions(const GridDev& g, uint64_t l_begin, uint64_t count, double* d_x, cudaStream_t stream);

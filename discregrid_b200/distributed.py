@@ -94,3 +94,82 @@ class ShardedSdfSampler:
         n = self.launch(full, sign)
         allgather_rows(full, self.sh, group)
         return n
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Slab sharding (the default of bench.py for N > 1).  Each rank samples whole slow-plane pairs of each of the four node arrays in
+# ONE launch (dg_sample_sdf_slab_device): z-slabs of the vertex and x-edge nodes, x-slabs of the y-edge nodes, y-slabs of the z-edge
+# nodes.  No partially filled bricks, one launch tail per rank, and the three slab orientations average out the spatially varying
+# cost.  A rank therefore owns four contiguous node ranges whose lengths differ slightly between ranks; each node array is
+# exchanged with ONE all-gather of equal-sized (padded) slices followed by a copy of the foreign slices to their final offsets.
+class SlabSharding:
+    def __init__(self, desc, world):
+        import ctypes as C
+        from . import _capi as capi
+        self.world = world
+        self.ranges = []                                   # ranges[rank][a] = (l_begin, l_end)
+        for r in range(world):
+            buf = (C.c_uint64 * 8)()
+            capi.check(capi.lib.dg_slab_ranges(C.byref(desc), r, world, buf))
+            self.ranges.append([(int(buf[2 * a]), int(buf[2 * a + 1])) for a in range(4)])
+        self.maxlen = [max(self.ranges[r][a][1] - self.ranges[r][a][0] for r in range(world)) for a in range(4)]
+        n = C.c_uint64()
+        capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(n)))
+        self.n = n.value
+        self.padded = self.n + max(self.maxlen)            # so that every [l_begin, l_begin + maxlen) slice stays in bounds
+
+    def covers_exactly_once(self):
+        import numpy as np
+        seen = np.zeros(self.n, np.int32)
+        for r in range(self.world):
+            for (b, e) in self.ranges[r]:
+                seen[b:e] += 1
+        return bool((seen == 1).all())
+
+
+def allgather_slabs(full, sh, group=None, scratch=None):
+    """full: 1-D tensor of sh.padded elements in which this rank has filled its own four ranges; afterwards all ranges are filled."""
+    import torch
+    import torch.distributed as dist
+    if sh.world == 1:
+        return
+    rank = dist.get_rank(group)
+    for a in range(4):
+        ml = sh.maxlen[a]
+        if ml == 0:
+            continue
+        b_me = sh.ranges[rank][a][0]
+        tmp = scratch[a] if scratch is not None else torch.empty(sh.world * ml, dtype=full.dtype, device=full.device)
+        src = full[b_me:b_me + ml]
+        dist.all_gather_into_tensor(tmp, src.clone() if full.device.type == "cpu" else src, group=group)
+        for r in range(sh.world):
+            if r == rank:
+                continue
+            b, e = sh.ranges[r][a]
+            if e > b:
+                full[b:e].copy_(tmp[r * ml:r * ml + (e - b)])
+
+
+class SlabSdfSampler:
+    """one rank of the slab-sharded node loop: launch() = this rank's single kernel, step() = launch + exchange"""
+
+    def __init__(self, md, desc, rank, world):
+        self.md, self.desc, self.rank, self.world = md, desc, rank, world
+        self.sh = SlabSharding(desc, world)
+        self.scratch = None
+
+    def launch(self, full, sign=1.0):
+        import ctypes as C
+        import torch
+        from . import _capi as capi
+        capi.check(capi.lib.dg_sample_sdf_slab_device(self.md.handle, C.byref(self.desc), sign, self.rank, self.world,
+                                                      C.c_void_p(full.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return 1
+
+    def step(self, full, sign=1.0, group=None):
+        import torch
+        if self.scratch is None and self.world > 1:
+            self.scratch = [torch.empty(self.world * ml, dtype=full.dtype, device=full.device) for ml in self.sh.maxlen]
+        self.launch(full, sign)
+        allgather_slabs(full, self.sh, group, self.scratch)
+        return 1

@@ -130,6 +130,14 @@ DG_API int dg_mesh_distance_device(const dg_mesh* mesh, const double* d_points, 
 DG_API int dg_sample_sdf(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* out_host);
 DG_API int dg_sample_sdf_device(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end,
                          double* d_out, void* stream);
+/* Slab sharding of the same loop for one-process-per-GPU jobs ("P1"): part `part` of `n_parts` samples, in ONE launch,
+ * whole slow-plane PAIRS of each of the four row-major node arrays (vertex / x-edge nodes: z-slabs; y-edge nodes: x-slabs; z-edge
+ * nodes: y-slabs), i.e. no partially filled bricks and a single launch tail per rank.  Results are written at their final positions
+ * of the full coefficient array d_full (n_nodes doubles).  ranges[8] = the four [l_begin, l_end) node ranges of this part (some may
+ * be empty); dg_slab_ranges computes them on the host (no GPU) for the exchange step. */
+DG_API int dg_slab_ranges(const dg_grid_desc* grid, uint32_t part, uint32_t n_parts, uint64_t ranges[8]);
+DG_API int dg_sample_sdf_slab_device(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint32_t part, uint32_t n_parts,
+                              double* d_full, void* stream);
 /* indexToNodePosition for l in [l_begin, l_end) -> x[(l-l_begin)*3 ..] (cubic_lagrange_discrete_grid.cpp:604-665) */
 DG_API int dg_node_positions(const dg_grid_desc* grid, uint64_t l_begin, uint64_t l_end, double* x_host);
 /* Cell connectivity table of addFunction (cubic_lagrange_discrete_grid.cpp:833-886) for cells

@@ -121,6 +121,50 @@ def test_node_sharding_partition():
         assert sh.padded >= n and sh.padded % (world * sh.rows) == 0
 
 
+def test_slab_sharding_partition(dg):
+    """dg_slab_ranges: whole plane pairs of the four node arrays, every node exactly once, for any world size (host only)"""
+    from discregrid_b200.distributed import SlabSharding
+    for res, world in (((16, 16, 16), 2), ((128, 128, 128), 8), ((7, 3, 5), 3), ((5, 9, 2), 4), ((1, 1, 1), 2), ((33, 20, 11), 1)):
+        desc = dg.grid_desc([0, 0, 0], [1, 1, 1], res)
+        sh = SlabSharding(desc, world)
+        assert sh.covers_exactly_once()
+        nx, ny, nz = res
+        nv = (nx + 1) * (ny + 1) * (nz + 1)
+        plane = [(ny + 1) * (nx + 1), (ny + 1) * 2 * nx, (nz + 1) * 2 * ny, (nx + 1) * 2 * nz]
+        base = [0, nv, nv + 2 * nx * (ny + 1) * (nz + 1), nv + 2 * nx * (ny + 1) * (nz + 1) + 2 * (nx + 1) * ny * (nz + 1)]
+        for r in range(world):
+            for a, (b, e) in enumerate(sh.ranges[r]):
+                assert (b - base[a]) % plane[a] == 0 and (e - base[a]) % plane[a] == 0          # whole planes
+                if r + 1 < world:
+                    assert ((e - base[a]) // plane[a]) % 2 == 0                                  # interior boundaries on plane pairs
+
+
+def test_allgather_slabs_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(f'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {ROOT!r})
+import discregrid_b200 as dg
+from discregrid_b200.distributed import SlabSharding, allgather_slabs
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+desc = dg.grid_desc([0, 0, 0], [1, 2, 3], (9, 5, 7))
+sh = SlabSharding(desc, world)
+full = torch.full((sh.padded,), -1.0, dtype=torch.float64)
+for (b, e) in sh.ranges[rank]:
+    full[b:e] = torch.arange(b, e, dtype=torch.float64) * 0.25 - 3.0
+allgather_slabs(full, sh)
+want = torch.arange(sh.n, dtype=torch.float64) * 0.25 - 3.0
+assert torch.equal(full[:sh.n], want), (rank, (full[:sh.n] != want).nonzero()[:5])
+dist.barrier()
+if rank == 0: print("SLAB_OK")
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29615")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29615", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "SLAB_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_allgather_rows_gloo_world2(tmp_path):
     """N > 1 host logic on CPU: two gloo ranks fill their chunks with a known function of the node id and gather."""
     script = tmp_path / "w.py"

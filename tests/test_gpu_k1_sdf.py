@@ -200,3 +200,21 @@ def test_meshes_of_different_depth_coexist(dg, orc, box_mesh, torus_small):
     assert bits_equal(big.signed_distance(x).distance, orc.mesh(torus_small.vertices, torus_small.faces).distance(x)[0])
     assert bits_equal(small.signed_distance(x).distance, orc.mesh(box_mesh.vertices, box_mesh.faces).distance(x)[0])
     assert bits_equal(big.signed_distance(x).distance, orc.mesh(torus_small.vertices, torus_small.faces).distance(x)[0])
+
+
+@pytest.mark.parametrize("res,parts", [((12, 10, 9), 3), ((16, 16, 16), 8), ((5, 4, 3), 4)])
+def test_slab_parts_cover_the_grid(dg, orc, torus_small, res, parts):
+    """dg_sample_sdf_slab_device: the parts of an n-way slab split, run one after another on one GPU, fill the full array with the
+    single-launch result (what each rank of a multi-GPU job computes; the exchange is tested in test_gpu_multi / gloo)"""
+    import ctypes as C
+    import torch
+    from discregrid_b200 import _capi as capi
+    mn, mx, gd, r = grid_for(orc, torus_small.vertices, res)
+    want = orc.mesh(torus_small.vertices, torus_small.faces).sample_sdf(gd, r)
+    md = dg.TriangleMeshDistance(torus_small)
+    desc = dg.grid_desc(mn, mx, res)
+    full = torch.full((len(want),), float("nan"), dtype=torch.float64, device="cuda")
+    for p in range(parts):
+        capi.check(capi.lib.dg_sample_sdf_slab_device(md.handle, C.byref(desc), 1.0, p, parts, C.c_void_p(full.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert bits_equal(full.cpu().numpy(), want)

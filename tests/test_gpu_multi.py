@@ -37,6 +37,14 @@ single = np.empty(n)
 capi.check(capi.lib.dg_sample_sdf(md.handle, C.byref(desc), 1.0, 0, n, capi.ptr(single, capi.F64P)))
 got = full[:n].cpu().numpy()
 assert np.array_equal(got.view(np.uint64), single.view(np.uint64)), f"rank {rank}: sharded != single-GPU"
+# slab sharding: one launch per rank, whole plane pairs, four all-gathers
+from discregrid_b200.distributed import SlabSdfSampler
+ss = SlabSdfSampler(md, desc, rank, world)
+full2 = torch.full((ss.sh.padded,), float("nan"), dtype=torch.float64, device="cuda")
+ss.step(full2)
+torch.cuda.synchronize()
+got2 = full2[:n].cpu().numpy()
+assert np.array_equal(got2.view(np.uint64), single.view(np.uint64)), f"rank {rank}: slab-sharded != single-GPU"
 dist.barrier()
 if rank == 0: print("MULTI_OK", world)
 dist.destroy_process_group()
