@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (diagnostics / profiling)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (diagnostics / profiling)")
     ap.add_argument("--no-target", action="store_true", help="skip the 256^3 / 100k-triangle target-config leg")
-    ap.add_argument("--sharding", default="slab", choices=["slab", "chunks"], help="N>1: whole-plane slabs (one launch per rank) or round-robin node-id chunks")
+    ap.add_argument("--sharding", default="chunks", choices=["slab", "chunks"], help="N>1: whole-plane slabs (one launch per rank) or round-robin node-id chunks")
     ap.add_argument("--no-real", action="store_true", help="skip the leg on the reference meshes staged under oracle/_ref/resources")
     ap.add_argument("--no-density", action="store_true", help="skip the density-map (K3) leg (diagnostics / profiling)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")

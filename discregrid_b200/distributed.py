@@ -97,7 +97,7 @@ class ShardedSdfSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
-# Slab sharding (the default of bench.py for N > 1).  Each rank samples whole slow-plane pairs of each of the four node arrays in
+# Slab sharding (bench.py --sharding slab; the node-id chunks above are the default: measured 10.5 vs 10.1 ms per step at 8 GPUs).  Each rank samples whole slow-plane pairs of each of the four node arrays in
 # ONE launch (dg_sample_sdf_slab_device): z-slabs of the vertex and x-edge nodes, x-slabs of the y-edge nodes, y-slabs of the z-edge
 # nodes.  No partially filled bricks, one launch tail per rank, and the three slab orientations average out the spatially varying
 # cost.  A rank therefore owns four contiguous node ranges whose lengths differ slightly between ranks; each node array is
