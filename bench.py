@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (diagnostics / profiling)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (diagnostics / profiling)")
     ap.add_argument("--no-target", action="store_true", help="skip the 256^3 / 100k-triangle target-config leg")
-    ap.add_argument("--sharding", default="chunks", choices=["slab", "chunks"], help="N>1: whole-plane slabs (one launch per rank) or round-robin node-id chunks")
+    ap.add_argument("--sharding", default="chunks", choices=["slab", "chunks", "interleaved"], help="N>1: whole-plane slabs (one launch per rank) or round-robin node-id chunks")
     ap.add_argument("--no-real", action="store_true", help="skip the leg on the reference meshes staged under oracle/_ref/resources")
     ap.add_argument("--no-density", action="store_true", help="skip the density-map (K3) leg (diagnostics / profiling)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -185,7 +185,7 @@ def main():
 
     import discregrid_b200 as dg           # fails loudly if the CUDA library is not built
     from discregrid_b200 import _capi as capi
-    from discregrid_b200.distributed import make_sharding, allgather_rows, ShardedSdfSampler, SlabSdfSampler
+    from discregrid_b200.distributed import make_sharding, allgather_rows, ShardedSdfSampler, SlabSdfSampler, InterleavedSdfSampler
 
     mesh = dg.bumpy_torus(*WORKLOAD["torus"])
     mn, mx = dg.generate_sdf_domain(mesh.vertices)
@@ -196,7 +196,7 @@ def main():
     config = {"workload": f"GenerateSDF addFunction: {WORKLOAD['mesh']}; {res[0]}x{res[1]}x{res[2]} grid = {n_nodes} nodes; "
                           "GenerateSDF-padded domain; fp64 bit-exact with the reference",
               "mesh_triangles": int(mesh.nFaces()), "grid": res, "nodes": n_nodes,
-              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"x{world}" + ("" if world == 1 else (", slabs of whole plane pairs of the four node arrays: one launch per rank + one NCCL all-gather per node array" if args.sharding == "slab" else ", 2 round-robin node-id chunks per rank on 2 streams + one in-place NCCL all-gather per row"))}
+              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"x{world}" + ("" if world == 1 else (", slabs of whole plane pairs of the four node arrays: one launch per rank + one NCCL all-gather per node array" if args.sharding == "slab" else ", plane pairs dealt round-robin: one launch per rank + ONE NCCL all-gather + unpack kernel" if args.sharding == "interleaved" else ", 2 round-robin node-id chunks per rank on 2 streams + one in-place NCCL all-gather per row"))}
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -243,14 +243,31 @@ def main():
     my_chunks = [(j, b, e) for (j, b, e) in sh.chunks_of(rank)]
     stream = torch.cuda.current_stream()
 
-    if args.sharding == "slab":
-        sdf_sampler = SlabSdfSampler(md, desc, rank, world)
+    def make_sampler(md_, desc_, n_):
+        if args.sharding == "slab":
+            return SlabSdfSampler(md_, desc_, rank, world)
+        if args.sharding == "interleaved":
+            return InterleavedSdfSampler(md_, desc_, rank, world)
+        return ShardedSdfSampler(md_, desc_, make_sharding(n_, world), rank)
+
+    if args.sharding != "chunks":
+        sdf_sampler = make_sampler(md, desc, n_nodes)
         full = torch.empty(sdf_sampler.sh.padded, dtype=torch.float64, device=dev)
     else:
         sdf_sampler = ShardedSdfSampler(md, desc, sh, rank)
 
     def sdf_step():
         sdf_sampler.step(full)
+
+    def same_as_single_launch(md_, desc_, n_, sharded):
+        """every rank: the assembled array of the sharded step vs ONE dg_sample_sdf_device launch over all nodes on this GPU (bit-for-bit)"""
+        if world == 1:
+            return None
+        single = torch.empty(n_, dtype=torch.float64, device=dev)
+        capi.check(capi.lib.dg_sample_sdf_device(md_.handle, C.byref(desc_), 1.0, 0, n_, C.c_void_p(single.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        ok = bool(torch.equal(single.view(torch.int64), sharded[:n_].view(torch.int64)))
+        del single
+        return bool(max_over_ranks(0.0 if ok else 1.0) == 0.0)
 
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
@@ -274,6 +291,7 @@ def main():
     launches0 = dg.kernel_launch_count()
     sdf_ms, sdf_wall = timed(sdf_step, args.steps, args.warmup)
     launches = (dg.kernel_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    sharded_ok = same_as_single_launch(md, desc, n_nodes, full)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = float(np.mean(sdf_ms))
     value = n_nodes / (ms_step * 1e-3)
@@ -285,6 +303,8 @@ def main():
     k1_ms = float(np.mean(k1_ms))
     if args.sharding == "slab":
         my_nodes = sum(e - b for (b, e) in sdf_sampler.sh.ranges[rank]); n_launch = 1
+    elif args.sharding == "interleaved":
+        my_nodes = n_nodes // world; n_launch = 1
     else:
         my_nodes = sum(e - b for (_j, b, e) in my_chunks); n_launch = sum(1 for (_j, b, e) in my_chunks if e > b)
     peaks, peak_src = measured_peaks()
@@ -304,6 +324,8 @@ def main():
             my_ranges = [(0, n_nodes)]
         elif args.sharding == "slab":
             my_ranges = [(b, e) for (b, e) in sdf_sampler.sh.ranges[rank] if e > b]
+        elif args.sharding == "interleaved":
+            my_ranges = [((n_nodes * rank) // world, (n_nodes * (rank + 1)) // world)]     # host API has no interleaved form: equal contiguous share
         else:
             my_ranges = [(b, e) for (_j, b, e) in my_chunks if e > b]
         outs = [np.empty(e - b) for (b, e) in my_ranges]
@@ -425,13 +447,13 @@ def main():
         tmn, tmx = dg.generate_sdf_domain(tmesh.vertices)
         tdesc = dg.grid_desc(tmn, tmx, [256, 256, 256])
         tn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(tdesc.resolution, C.byref(tn))); tn = tn.value
-        tsampler = SlabSdfSampler(tmd, tdesc, rank, world) if args.sharding == "slab" else ShardedSdfSampler(tmd, tdesc, make_sharding(tn, world), rank)
+        tsampler = make_sampler(tmd, tdesc, tn)
         tfull = torch.empty(tsampler.sh.padded, dtype=torch.float64, device=dev)
         t_ms, _ = timed(lambda: tsampler.step(tfull), 3, 1)
         t_ms = float(np.mean(t_ms))
         target = {"workload": "north_star target: 256^3 grid (118,425,857 nodes), synthetic bumpy torus with exactly 100,000 triangles, "
                               "strong scaling over node chunks + all-gather", "ms_per_step": t_ms, "value": tn / (t_ms * 1e-3), "unit": "nodes/s",
-                  "n_gpus": world}
+                  "n_gpus": world, "sharded_equals_single_launch": same_as_single_launch(tmd, tdesc, tn, tfull)}
         if rank == 0 and world == 1 and not args.no_cpu:
             rates, info = cpu_sample_rate(tmesh, tmn, tmx, [256, 256, 256], args.cpu_seconds)
             target["cpu_baseline"] = dict(info, value=float(np.mean(rates)), unit="nodes/s")
@@ -451,7 +473,7 @@ def main():
             rmn, rmx = dg.generate_sdf_domain(rmesh.vertices)
             rdesc = dg.grid_desc(rmn, rmx, [r3] * 3)
             rn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(rdesc.resolution, C.byref(rn))); rn = rn.value
-            rs = SlabSdfSampler(rmd, rdesc, rank, world) if args.sharding == "slab" else ShardedSdfSampler(rmd, rdesc, make_sharding(rn, world), rank)
+            rs = make_sampler(rmd, rdesc, rn)
             rfull = torch.empty(rs.sh.padded, dtype=torch.float64, device=dev)
             r_ms, _ = timed(lambda: rs.step(rfull), 2, 1)
             r_ms = float(np.mean(r_ms))
@@ -516,7 +538,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "target_config": target, "reference_meshes": real, "density_map": density,
-                "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms}}
+                "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms},
+                "sharded_equals_single_launch": sharded_ok}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

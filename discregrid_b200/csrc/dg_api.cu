@@ -525,6 +525,38 @@ int dg_sample_sdf_slab_device(const dg_mesh* m, const dg_grid_desc* grid, double
     return DG_OK;
 }
 
+int dg_interleaved_slot_elems(const dg_grid_desc* grid, uint32_t n_parts, uint64_t* slot_elems)
+{
+    GridDev g; const char* why = "";
+    if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_interleaved_slot_elems: %s", why);
+    InterleavedLayout L;
+    if (!slot_elems || !k1_interleaved_layout(g, n_parts, L)) return fail(DG_ERR_INVALID, "dg_interleaved_slot_elems: n_parts must be 1..16");
+    *slot_elems = L.slot_elems;
+    return DG_OK;
+}
+
+int dg_sample_sdf_interleaved_device(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint32_t part, uint32_t n_parts, double* d_slot, void* stream)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf_interleaved: mesh is NULL (not constructed)");
+    GridDev g; const char* why = "";
+    if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_sample_sdf_interleaved: %s", why);
+    InterleavedLayout L;
+    if (!k1_interleaved_layout(g, n_parts, L) || part >= n_parts || !d_slot) return fail(DG_ERR_INVALID, "dg_sample_sdf_interleaved: bad part / n_parts (1..16) / output");
+    DG_LAUNCH(k1_launch_sample_interleaved(m->dev, g, sign, L, part, d_slot, (cudaStream_t)stream));
+    return DG_OK;
+}
+
+int dg_interleaved_unpack_device(const dg_grid_desc* grid, uint32_t n_parts, const double* d_slots, double* d_nodes, void* stream)
+{
+    if (int rc = require_device()) return rc;
+    GridDev g; const char* why = "";
+    if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_interleaved_unpack: %s", why);
+    InterleavedLayout L;
+    if (!k1_interleaved_layout(g, n_parts, L) || !d_slots || !d_nodes) return fail(DG_ERR_INVALID, "dg_interleaved_unpack: bad n_parts (1..16) / NULL buffer");
+    DG_LAUNCH(k1_launch_unpack_interleaved(g, L, d_slots, d_nodes, (cudaStream_t)stream));
+    return DG_OK;
+}
+
 int dg_node_positions(const dg_grid_desc* grid, uint64_t l_begin, uint64_t l_end, double* x_host)
 {
     if (int rc = require_device()) return rc;

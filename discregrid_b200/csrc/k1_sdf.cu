@@ -502,7 +502,8 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned f = tf * (unsigned)(K1_BRICK_F * (K1_THREADS / 32)) + warp * (unsigned)K1_BRICK_F + (lane % K1_BRICK_F);
     const unsigned m = tm * (unsigned)K1_BRICK_M + ((lane / K1_BRICK_F) % K1_BRICK_M);
-    const unsigned sl = S.s0 + ts * (unsigned)K1_BRICK_S + (lane / (K1_BRICK_F * K1_BRICK_M));
+    const unsigned lane_s = lane / (K1_BRICK_F * K1_BRICK_M);
+    const unsigned sl = S.s0 + ts * S.pl_stride * (unsigned)K1_BRICK_S + lane_s;
     const unsigned l = S.l_base + (sl * S.Dm + m) * S.Df + f;
     const bool alive = (f < S.Df) && (m < S.Dm) && (sl < S.s1) && (l >= w.l_begin) && (l < w.l_end);
 
@@ -525,7 +526,8 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
     if (!alive) return;
     double dist, qx, qy, qz; int tri;
     finish_query(mesh.leaves, normals, r, px, py, pz, true, dist, qx, qy, qz, tri);
-    out[l - w.l_begin] = (sign == 1.0) ? dist : sign * dist;     // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
+    const unsigned out_idx = w.compact ? S.out_base + ((ts * (unsigned)K1_BRICK_S + lane_s) * S.Dm + m) * S.Df + f : l - w.l_begin;
+    out[out_idx] = (sign == 1.0) ? dist : sign * dist;           // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
 }
 
 // batched TriangleMeshDistance::{signed,unsigned}_distance on arbitrary points (a warp = 32 consecutive points)
@@ -610,7 +612,7 @@ cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double 
                               (uint64_t)g.nv + 2ull * ((uint64_t)g.ne_x + g.ne_y + g.ne_z)};
     const unsigned dims[4][3] = {{nz + 1, ny + 1, nx + 1}, {nz + 1, ny + 1, 2 * nx}, {nx + 1, nz + 1, 2 * ny}, {ny + 1, nx + 1, 2 * nz}};
     K1Work w;
-    w.nseg = 0; w.l_begin = (unsigned)l_begin; w.l_end = (unsigned)l_end;
+    w.nseg = 0; w.l_begin = (unsigned)l_begin; w.l_end = (unsigned)l_end; w.compact = 0;
     unsigned blocks = 0;
     for (int k = 0; k < 4; k++) {
         const uint64_t a = l_begin > base[k] ? l_begin : base[k];
@@ -620,6 +622,7 @@ cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double 
         S.kind = k; S.l_base = (unsigned)base[k];
         S.Ds = dims[k][0]; S.Dm = dims[k][1]; S.Df = dims[k][2];
         const uint64_t plane = (uint64_t)S.Dm * S.Df;
+        S.pl_stride = 1u; S.out_base = 0u;
         S.s0 = (unsigned)((a - base[k]) / plane);
         S.s1 = (unsigned)((b - 1 - base[k]) / plane) + 1;
         const unsigned bf = K1_BRICK_F * (K1_THREADS / 32);
@@ -641,14 +644,14 @@ cudaError_t k1_launch_sample_slab(const DeviceBvh& m, const GridDev& g, double s
     const uint64_t base[4] = {0, g.nv, (uint64_t)g.nv + 2ull * g.ne_x, (uint64_t)g.nv + 2ull * (g.ne_x + (uint64_t)g.ne_y)};
     const unsigned dims[4][3] = {{nz + 1, ny + 1, nx + 1}, {nz + 1, ny + 1, 2 * nx}, {nx + 1, nz + 1, 2 * ny}, {ny + 1, nx + 1, 2 * nz}};
     K1Work w;
-    w.nseg = 0; w.l_begin = 0u; w.l_end = 0xffffffffu;          // whole planes: nothing to mask, out[l] is the final position
+    w.nseg = 0; w.l_begin = 0u; w.l_end = 0xffffffffu; w.compact = 0;   // whole planes: nothing to mask, out[l] is the final position
     unsigned blocks = 0;
     for (int k = 0; k < 4; k++) {
         if (plane_begin[k] >= plane_end[k]) continue;
         K1Segment& S = w.seg[w.nseg++];
         S.kind = k; S.l_base = (unsigned)base[k];
         S.Ds = dims[k][0]; S.Dm = dims[k][1]; S.Df = dims[k][2];
-        S.s0 = plane_begin[k]; S.s1 = plane_end[k];
+        S.s0 = plane_begin[k]; S.s1 = plane_end[k]; S.pl_stride = 1u; S.out_base = 0u;
         const unsigned bf = K1_BRICK_F * (K1_THREADS / 32);
         S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + K1_BRICK_M - 1) / K1_BRICK_M;
         const unsigned tiles_s = (S.s1 - S.s0 + K1_BRICK_S - 1) / K1_BRICK_S;
@@ -658,6 +661,85 @@ cudaError_t k1_launch_sample_slab(const DeviceBvh& m, const GridDev& g, double s
     if (w.nseg == 0) return cudaSuccess;
     for (int k = w.nseg; k < 4; k++) { w.seg[k] = w.seg[0]; w.seg[k].block_begin = 0xffffffffu; }
     sdf_sample_nodes_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_full);
+    return cudaGetLastError();
+}
+
+static void node_arrays(const GridDev& g, uint64_t base[4], unsigned dims[4][3])
+{
+    const unsigned nx = g.n[0], ny = g.n[1], nz = g.n[2];
+    base[0] = 0; base[1] = g.nv; base[2] = (uint64_t)g.nv + 2ull * g.ne_x; base[3] = (uint64_t)g.nv + 2ull * (g.ne_x + (uint64_t)g.ne_y);
+    const unsigned d[4][3] = {{nz + 1, ny + 1, nx + 1}, {nz + 1, ny + 1, 2 * nx}, {nx + 1, nz + 1, 2 * ny}, {ny + 1, nx + 1, 2 * nz}};
+    for (int a = 0; a < 4; a++) for (int k = 0; k < 3; k++) dims[a][k] = d[a][k];
+}
+
+bool k1_interleaved_layout(const GridDev& g, unsigned n_parts, InterleavedLayout& L)
+{
+    if (n_parts == 0 || n_parts > 16) return false;
+    uint64_t base[4]; unsigned dims[4][3];
+    node_arrays(g, base, dims);
+    L.n_parts = n_parts; L.slot_elems = 0;
+    for (int a = 0; a < 4; a++) { L.pairs[a] = (dims[a][0] + K1_BRICK_S - 1) / K1_BRICK_S; L.plane[a] = dims[a][1] * dims[a][2]; }
+    for (unsigned r = 0; r < n_parts; r++) {
+        uint64_t off = 0;
+        for (int a = 0; a < 4; a++) {
+            L.off[a][r] = (unsigned)off;
+            const uint64_t mine = (L.pairs[a] > r) ? (L.pairs[a] - r + n_parts - 1) / n_parts : 0;      // pairs r, r + n_parts, ...
+            off += mine * K1_BRICK_S * (uint64_t)L.plane[a];
+        }
+        if (off > 0xffffffffull) return false;
+        if (off > L.slot_elems) L.slot_elems = off;
+    }
+    for (unsigned r = n_parts; r < 16; r++) for (int a = 0; a < 4; a++) L.off[a][r] = 0;
+    return true;
+}
+
+cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, double sign, const InterleavedLayout& L, unsigned part,
+                                         double* d_slot, cudaStream_t stream)
+{
+    uint64_t base[4]; unsigned dims[4][3];
+    node_arrays(g, base, dims);
+    K1Work w;
+    w.nseg = 0; w.l_begin = 0u; w.l_end = 0xffffffffu; w.compact = 1;
+    unsigned blocks = 0;
+    for (int k = 0; k < 4; k++) {
+        const unsigned mine = (L.pairs[k] > part) ? (L.pairs[k] - part + L.n_parts - 1) / L.n_parts : 0;
+        if (mine == 0) continue;
+        K1Segment& S = w.seg[w.nseg++];
+        S.kind = k; S.l_base = (unsigned)base[k];
+        S.Ds = dims[k][0]; S.Dm = dims[k][1]; S.Df = dims[k][2];
+        S.s0 = part * K1_BRICK_S; S.s1 = S.Ds; S.pl_stride = L.n_parts; S.out_base = L.off[k][part];
+        const unsigned bf = K1_BRICK_F * (K1_THREADS / 32);
+        S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + K1_BRICK_M - 1) / K1_BRICK_M;
+        S.block_begin = blocks;
+        blocks += S.tiles_f * S.tiles_m * mine;
+    }
+    if (w.nseg == 0) return cudaSuccess;
+    for (int k = w.nseg; k < 4; k++) { w.seg[k] = w.seg[0]; w.seg[k].block_begin = 0xffffffffu; }
+    sdf_sample_nodes_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_slot);
+    return cudaGetLastError();
+}
+
+namespace {
+// gathered slots [n_parts][slot_elems] -> coefficient array in the reference's node order
+__global__ void unpack_interleaved_kernel(GridDev g, InterleavedLayout L, unsigned long long n_nodes, const double* __restrict__ slots,
+                                          double* __restrict__ nodes)
+{
+    const unsigned long long l = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_nodes) return;
+    const unsigned long long b1 = g.nv, b2 = b1 + 2ull * g.ne_x, b3 = b2 + 2ull * g.ne_y;
+    const int a = (l < b1) ? 0 : ((l < b2) ? 1 : ((l < b3) ? 2 : 3));
+    const unsigned long long rel = l - ((a == 0) ? 0ull : ((a == 1) ? b1 : ((a == 2) ? b2 : b3)));
+    const unsigned plane = L.plane[a];
+    const unsigned s = (unsigned)(rel / plane), inplane = (unsigned)(rel - (unsigned long long)s * plane);
+    const unsigned pair = s / K1_BRICK_S, r = pair % L.n_parts, j = pair / L.n_parts;
+    nodes[l] = slots[(size_t)r * L.slot_elems + L.off[a][r] + (size_t)(j * K1_BRICK_S + (s % K1_BRICK_S)) * plane + inplane];
+}
+}  // namespace
+
+cudaError_t k1_launch_unpack_interleaved(const GridDev& g, const InterleavedLayout& L, const double* d_slots, double* d_nodes, cudaStream_t stream)
+{
+    const unsigned long long n = (unsigned long long)g.nv + 2ull * ((unsigned long long)g.ne_x + g.ne_y + g.ne_z);
+    unpack_interleaved_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(g, L, n, d_slots, d_nodes);
     return cudaGetLastError();
 }
 

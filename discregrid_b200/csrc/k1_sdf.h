@@ -78,12 +78,15 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 // slow-planes [s0, s1) that a node range touches.  l = l_base + (s*Dm + m)*Df + f.
 struct K1Segment {
     unsigned l_base, Ds, Dm, Df, s0, s1, tiles_f, tiles_m, block_begin;
+    unsigned pl_stride;            // plane groups between consecutive brick layers (1 = contiguous slab, n_parts = interleaved deal)
+    unsigned out_base;             // interleaved mode: element offset of this array inside the part's exchange slot
     int kind;                      // 0 vertex (s,m,f)=(k,j,i); 1 x-edge (k,j,2i+b); 2 y-edge (i,k,2j+b); 3 z-edge (j,i,2k+b)
 };
 struct K1Work {
     K1Segment seg[4];
     int nseg;
     unsigned l_begin, l_end;
+    int compact;                   // 0: out[l - l_begin]; 1: interleaved exchange slot (see k1_launch_sample_interleaved)
 };
 
 struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once by dg_mesh_create
@@ -104,6 +107,19 @@ cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double 
 // slab form: planes [plane_begin[a], plane_end[a]) of node array a (a = 0..3), written at d_full[l]
 cudaError_t k1_launch_sample_slab(const DeviceBvh& m, const GridDev& g, double sign, const unsigned plane_begin[4], const unsigned plane_end[4],
                                   double* d_full, cudaStream_t stream);
+// interleaved deal of plane pairs: part `part` owns pairs part, part + n_parts, ... of every node array and writes
+// them compactly into its exchange slot; k1_launch_unpack_interleaved scatters the gathered slots into node order.
+struct InterleavedLayout {
+    unsigned n_parts = 1;
+    unsigned off[4][16];           // off[a][part]: element offset of array a in part's slot
+    unsigned pairs[4];             // plane pairs of array a
+    unsigned plane[4];             // elements per plane of array a
+    uint64_t slot_elems = 0;       // elements per slot (max over parts)
+};
+bool k1_interleaved_layout(const GridDev& g, unsigned n_parts, InterleavedLayout& L);
+cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, double sign, const InterleavedLayout& L, unsigned part,
+                                         double* d_slot, cudaStream_t stream);
+cudaError_t k1_launch_unpack_interleaved(const GridDev& g, const InterleavedLayout& L, const double* d_slots, double* d_nodes, cudaStream_t stream);
 cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t count, int is_signed, double* d_dist,
                                double* d_near, int* d_ent, int* d_tri, cudaStream_t stream);
 cudaError_t k1_launch_node_positions(const GridDev& g, uint64_t l_begin, uint64_t count, double* d_x, cudaStream_t stream);

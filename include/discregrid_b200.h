@@ -138,6 +138,15 @@ DG_API int dg_sample_sdf_device(const dg_mesh* mesh, const dg_grid_desc* grid, d
 DG_API int dg_slab_ranges(const dg_grid_desc* grid, uint32_t part, uint32_t n_parts, uint64_t ranges[8]);
 DG_API int dg_sample_sdf_slab_device(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint32_t part, uint32_t n_parts,
                               double* d_full, void* stream);
+/* Interleaved slab sharding: the slow-plane pairs of every node array are dealt round-robin -- pair p belongs to
+ * part p % n_parts -- which balances the spatially varying cost almost perfectly and still needs ONE launch per rank and no masked
+ * bricks.  A part writes its pairs compactly into its slot of an exchange buffer of n_parts x slot_elems doubles
+ * (dg_interleaved_slot_elems); after ONE all-gather of the slots, dg_interleaved_unpack_device scatters them into the
+ * reference's node order.  n_parts <= 16. */
+DG_API int dg_interleaved_slot_elems(const dg_grid_desc* grid, uint32_t n_parts, uint64_t* slot_elems);
+DG_API int dg_sample_sdf_interleaved_device(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint32_t part, uint32_t n_parts,
+                                     double* d_slot, void* stream);
+DG_API int dg_interleaved_unpack_device(const dg_grid_desc* grid, uint32_t n_parts, const double* d_slots, double* d_nodes, void* stream);
 /* indexToNodePosition for l in [l_begin, l_end) -> x[(l-l_begin)*3 ..] (cubic_lagrange_discrete_grid.cpp:604-665) */
 DG_API int dg_node_positions(const dg_grid_desc* grid, uint64_t l_begin, uint64_t l_end, double* x_host);
 /* Cell connectivity table of addFunction (cubic_lagrange_discrete_grid.cpp:833-886) for cells

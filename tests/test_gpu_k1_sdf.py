@@ -218,3 +218,25 @@ def test_slab_parts_cover_the_grid(dg, orc, torus_small, res, parts):
         capi.check(capi.lib.dg_sample_sdf_slab_device(md.handle, C.byref(desc), 1.0, p, parts, C.c_void_p(full.data_ptr()), None))
     torch.cuda.synchronize()
     assert bits_equal(full.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("res,parts", [((12, 10, 9), 3), ((16, 16, 16), 8), ((5, 4, 3), 4), ((7, 3, 5), 16), ((9, 9, 9), 1)])
+def test_interleaved_parts_cover_the_grid(dg, orc, torus_small, res, parts):
+    """dg_sample_sdf_interleaved_device + dg_interleaved_unpack_device: plane pairs dealt round-robin over `parts`, every part run on
+    this one GPU into its slot, unpacked == the single-launch result"""
+    import ctypes as C
+    import torch
+    from discregrid_b200 import _capi as capi
+    mn, mx, gd, r = grid_for(orc, torus_small.vertices, res)
+    want = orc.mesh(torus_small.vertices, torus_small.faces).sample_sdf(gd, r)
+    md = dg.TriangleMeshDistance(torus_small)
+    desc = dg.grid_desc(mn, mx, res)
+    se = C.c_uint64(); capi.check(capi.lib.dg_interleaved_slot_elems(C.byref(desc), parts, C.byref(se)))
+    slots = torch.full((parts * se.value,), float("nan"), dtype=torch.float64, device="cuda")
+    for p in range(parts):
+        capi.check(capi.lib.dg_sample_sdf_interleaved_device(md.handle, C.byref(desc), 1.0, p, parts, C.c_void_p(slots.data_ptr() + 8 * p * se.value), None))
+    full = torch.full((len(want),), float("nan"), dtype=torch.float64, device="cuda")
+    capi.check(capi.lib.dg_interleaved_unpack_device(C.byref(desc), parts, C.c_void_p(slots.data_ptr()), C.c_void_p(full.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert bits_equal(full.cpu().numpy(), want)
+    assert capi.lib.dg_interleaved_slot_elems(C.byref(desc), 17, C.byref(se)) == capi.DG_ERR_INVALID

@@ -45,6 +45,14 @@ ss.step(full2)
 torch.cuda.synchronize()
 got2 = full2[:n].cpu().numpy()
 assert np.array_equal(got2.view(np.uint64), single.view(np.uint64)), f"rank {rank}: slab-sharded != single-GPU"
+# interleaved slab sharding: plane pairs dealt round-robin, one all-gather, unpack
+from discregrid_b200.distributed import InterleavedSdfSampler
+it = InterleavedSdfSampler(md, desc, rank, world)
+full3 = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+it.step(full3)
+torch.cuda.synchronize()
+got3 = full3.cpu().numpy()
+assert np.array_equal(got3.view(np.uint64), single.view(np.uint64)), f"rank {rank}: interleaved != single-GPU"
 dist.barrier()
 if rank == 0: print("MULTI_OK", world)
 dist.destroy_process_group()
