@@ -64,6 +64,7 @@ SIGNATURES = {
     "dg_interleaved_slot_elems": (C.c_int, [_gp, C.c_uint32, _u64p]),
     "dg_sample_sdf_interleaved_device": (C.c_int, [_vp, _gp, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp]),
     "dg_interleaved_unpack_device": (C.c_int, [_gp, C.c_uint32, _vp, _vp, _vp]),
+    "dg_interleaved_node_slots": (C.c_int, [_gp, C.c_uint32, C.c_uint64, C.c_uint64, _u32p, _u64p]),
     "dg_node_positions": (C.c_int, [_gp, C.c_uint64, C.c_uint64, _dp]),
     "dg_build_cells": (C.c_int, [_u32p, C.c_uint64, C.c_uint64, _u32p]),
     "dg_field_create": (C.c_int, [_gp, _dp, C.c_uint64, _u32p, C.c_uint64, _u32p, C.POINTER(_vp)]),

@@ -535,6 +535,18 @@ int dg_interleaved_slot_elems(const dg_grid_desc* grid, uint32_t n_parts, uint64
     return DG_OK;
 }
 
+int dg_interleaved_node_slots(const dg_grid_desc* grid, uint32_t n_parts, uint64_t l_begin, uint64_t l_end, uint32_t* part_out, uint64_t* pos_out)
+{
+    GridDev g; const char* why = "";
+    if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_interleaved_node_slots: %s", why);
+    InterleavedLayout L;
+    if (!k1_interleaved_layout(g, n_parts, L)) return fail(DG_ERR_INVALID, "dg_interleaved_node_slots: n_parts must be 1..16");
+    const uint64_t n = (uint64_t)g.nv + 2ull * ((uint64_t)g.ne_x + g.ne_y + g.ne_z);
+    if (l_begin > l_end || l_end > n) return fail(DG_ERR_INVALID, "dg_interleaved_node_slots: node range outside [0, %llu]", (unsigned long long)n);
+    k1_interleaved_node_slots(g, L, l_begin, l_end - l_begin, part_out, pos_out);
+    return DG_OK;
+}
+
 int dg_sample_sdf_interleaved_device(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint32_t part, uint32_t n_parts, double* d_slot, void* stream)
 {
     if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf_interleaved: mesh is NULL (not constructed)");

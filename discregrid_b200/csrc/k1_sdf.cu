@@ -719,6 +719,19 @@ cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, d
     return cudaGetLastError();
 }
 
+// node id -> (part, position inside that part's slot): the one statement of the exchange layout, shared by the unpack kernel and the host
+__host__ __device__ inline unsigned long long interleaved_slot_of(const GridDev& g, const InterleavedLayout& L, unsigned long long l, unsigned& part)
+{
+    const unsigned long long b1 = g.nv, b2 = b1 + 2ull * g.ne_x, b3 = b2 + 2ull * g.ne_y;
+    const int a = (l < b1) ? 0 : ((l < b2) ? 1 : ((l < b3) ? 2 : 3));
+    const unsigned long long rel = l - ((a == 0) ? 0ull : ((a == 1) ? b1 : ((a == 2) ? b2 : b3)));
+    const unsigned plane = L.plane[a];
+    const unsigned s = (unsigned)(rel / plane), inplane = (unsigned)(rel - (unsigned long long)s * plane);
+    const unsigned pair = s / K1_BRICK_S, j = pair / L.n_parts;
+    part = pair % L.n_parts;
+    return (unsigned long long)L.off[a][part] + (unsigned long long)(j * K1_BRICK_S + (s % K1_BRICK_S)) * plane + inplane;
+}
+
 namespace {
 // gathered slots [n_parts][slot_elems] -> coefficient array in the reference's node order
 __global__ void unpack_interleaved_kernel(GridDev g, InterleavedLayout L, unsigned long long n_nodes, const double* __restrict__ slots,
@@ -726,15 +739,21 @@ __global__ void unpack_interleaved_kernel(GridDev g, InterleavedLayout L, unsign
 {
     const unsigned long long l = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_nodes) return;
-    const unsigned long long b1 = g.nv, b2 = b1 + 2ull * g.ne_x, b3 = b2 + 2ull * g.ne_y;
-    const int a = (l < b1) ? 0 : ((l < b2) ? 1 : ((l < b3) ? 2 : 3));
-    const unsigned long long rel = l - ((a == 0) ? 0ull : ((a == 1) ? b1 : ((a == 2) ? b2 : b3)));
-    const unsigned plane = L.plane[a];
-    const unsigned s = (unsigned)(rel / plane), inplane = (unsigned)(rel - (unsigned long long)s * plane);
-    const unsigned pair = s / K1_BRICK_S, r = pair % L.n_parts, j = pair / L.n_parts;
-    nodes[l] = slots[(size_t)r * L.slot_elems + L.off[a][r] + (size_t)(j * K1_BRICK_S + (s % K1_BRICK_S)) * plane + inplane];
+    unsigned r;
+    const unsigned long long pos = interleaved_slot_of(g, L, l, r);
+    nodes[l] = slots[(size_t)r * L.slot_elems + pos];
 }
 }  // namespace
+
+void k1_interleaved_node_slots(const GridDev& g, const InterleavedLayout& L, uint64_t l_begin, uint64_t count, uint32_t* part_out, uint64_t* pos_out)
+{
+    for (uint64_t i = 0; i < count; i++) {
+        unsigned r;
+        const unsigned long long pos = interleaved_slot_of(g, L, l_begin + i, r);
+        if (part_out) part_out[i] = r;
+        if (pos_out) pos_out[i] = pos;
+    }
+}
 
 cudaError_t k1_launch_unpack_interleaved(const GridDev& g, const InterleavedLayout& L, const double* d_slots, double* d_nodes, cudaStream_t stream)
 {

@@ -119,6 +119,7 @@ struct InterleavedLayout {
 bool k1_interleaved_layout(const GridDev& g, unsigned n_parts, InterleavedLayout& L);
 cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, double sign, const InterleavedLayout& L, unsigned part,
                                          double* d_slot, cudaStream_t stream);
+void k1_interleaved_node_slots(const GridDev& g, const InterleavedLayout& L, uint64_t l_begin, uint64_t count, uint32_t* part_out, uint64_t* pos_out);
 cudaError_t k1_launch_unpack_interleaved(const GridDev& g, const InterleavedLayout& L, const double* d_slots, double* d_nodes, cudaStream_t stream);
 cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t count, int is_signed, double* d_dist,
                                double* d_near, int* d_ent, int* d_tri, cudaStream_t stream);

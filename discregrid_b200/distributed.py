@@ -178,6 +178,23 @@ class SlabSdfSampler:
 # ---------------------------------------------------------------------------------------------------------------------------
 # Interleaved slab sharding: plane pairs dealt round-robin (pair p -> rank p % world).  One launch per rank, no masked
 # bricks, near-perfect balance; ONE in-place all-gather of equal slots; one unpack kernel into the reference's node order.
+def allgather_slots(slots, slot_elems, rank, world, group=None):
+    """the exchange step: ONE in-place all-gather of the equal-sized slots (rank r's slot = slots[r*slot_elems : (r+1)*slot_elems])"""
+    import torch.distributed as dist
+    if world > 1:
+        dist.all_gather_into_tensor(slots, slots[rank * slot_elems:(rank + 1) * slot_elems], group=group)
+
+
+def interleaved_node_slots(desc, world, l_begin, l_end):
+    """host statement of the layout (dg_interleaved_node_slots): (part, position-in-slot) of nodes [l_begin, l_end) as numpy arrays"""
+    import ctypes as C
+    import numpy as np
+    from . import _capi as capi
+    part = np.empty(l_end - l_begin, np.uint32); pos = np.empty(l_end - l_begin, np.uint64)
+    capi.check(capi.lib.dg_interleaved_node_slots(C.byref(desc), world, l_begin, l_end, capi.ptr(part, capi.U32P), capi.ptr(pos, capi.U64P)))
+    return part, pos
+
+
 class InterleavedSdfSampler:
     def __init__(self, md, desc, rank, world):
         import ctypes as C
@@ -214,12 +231,9 @@ class InterleavedSdfSampler:
     def step(self, full, sign=1.0, group=None):
         import ctypes as C
         import torch
-        import torch.distributed as dist
         from . import _capi as capi
         self.launch(full, sign)
-        if self.world > 1:
-            mine = self.slots[self.rank * self.slot:(self.rank + 1) * self.slot]
-            dist.all_gather_into_tensor(self.slots, mine, group=group)
+        allgather_slots(self.slots, self.slot, self.rank, self.world, group)
         sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         capi.check(capi.lib.dg_interleaved_unpack_device(C.byref(self.desc), self.world, C.c_void_p(self.slots.data_ptr()),
                                                          C.c_void_p(full.data_ptr()), sp))

@@ -147,6 +147,10 @@ DG_API int dg_interleaved_slot_elems(const dg_grid_desc* grid, uint32_t n_parts,
 DG_API int dg_sample_sdf_interleaved_device(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint32_t part, uint32_t n_parts,
                                      double* d_slot, void* stream);
 DG_API int dg_interleaved_unpack_device(const dg_grid_desc* grid, uint32_t n_parts, const double* d_slots, double* d_nodes, void* stream);
+/* the same layout on the host (no GPU): for node ids l in [l_begin, l_end), the part that samples node l and its position inside
+ * that part's slot (either output may be NULL) -- for hosts that consume or exchange slots themselves */
+DG_API int dg_interleaved_node_slots(const dg_grid_desc* grid, uint32_t n_parts, uint64_t l_begin, uint64_t l_end, uint32_t* part_out,
+                              uint64_t* pos_out);
 /* indexToNodePosition for l in [l_begin, l_end) -> x[(l-l_begin)*3 ..] (cubic_lagrange_discrete_grid.cpp:604-665) */
 DG_API int dg_node_positions(const dg_grid_desc* grid, uint64_t l_begin, uint64_t l_end, double* x_host);
 /* Cell connectivity table of addFunction (cubic_lagrange_discrete_grid.cpp:833-886) for cells

@@ -239,4 +239,8 @@ def test_interleaved_parts_cover_the_grid(dg, orc, torus_small, res, parts):
     capi.check(capi.lib.dg_interleaved_unpack_device(C.byref(desc), parts, C.c_void_p(slots.data_ptr()), C.c_void_p(full.data_ptr()), None))
     torch.cuda.synchronize()
     assert bits_equal(full.cpu().numpy(), want)
+    # ... and the slots hold exactly what the host statement of the layout (dg_interleaved_node_slots) says
+    from discregrid_b200.distributed import interleaved_node_slots
+    part, pos = interleaved_node_slots(desc, parts, 0, len(want))
+    assert bits_equal(slots.cpu().numpy()[part.astype(np.int64) * se.value + pos.astype(np.int64)], want)
     assert capi.lib.dg_interleaved_slot_elems(C.byref(desc), 17, C.byref(se)) == capi.DG_ERR_INVALID
