@@ -24,13 +24,19 @@ CPPBIN   := build/bin
 CPPFLAGS := -std=c++11 -O2 -ffp-contract=off -I$(EIGEN3_INCLUDE_DIR) -Icpp/include -Iinclude
 CPPLINK  := -Ldiscregrid_b200/lib -ldiscregrid_b200 -Wl,-rpath,'$$ORIGIN/../../discregrid_b200/lib'
 CPPHDRS  := $(wildcard cpp/include/Discregrid/* cpp/include/Discregrid/*/*) include/discregrid_b200.h
-cpp: $(CPPBIN)/GenerateSDF $(CPPBIN)/GenerateDensityMap $(CPPBIN)/DiscreteFieldToBitmap $(CPPBIN)/facade_check $(CPPBIN)/bvh_host_check
+cpp: $(CPPBIN)/GenerateSDF $(CPPBIN)/GenerateDensityMap $(CPPBIN)/DiscreteFieldToBitmap $(CPPBIN)/facade_check $(CPPBIN)/bvh_host_check $(CPPBIN)/reduce_facade_check
 $(CPPBIN)/DiscreteFieldToBitmap: cpp/cmd/discrete_field_to_bitmap.cpp $(CPPHDRS) $(LIB)
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK)
 $(CPPBIN)/bvh_host_check: tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/bvh_build.h
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp -o $@ -lpthread
+# test binary: the facade's reduceField with dg_node_positions interposed by the oracle (runs without a GPU)
+$(CPPBIN)/reduce_facade_check: tests/cpp/reduce_facade_check.cpp $(CPPHDRS) $(LIB) oracle/liboracle.so
+	@mkdir -p $(CPPBIN)
+	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK) -Loracle -loracle -Wl,-rpath,'$$ORIGIN/../../oracle'
+oracle/liboracle.so:
+	$(MAKE) -C oracle oracle
 $(CPPBIN)/GenerateSDF: cpp/cmd/generate_sdf.cpp $(CPPHDRS) $(LIB)
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK)
@@ -44,11 +50,11 @@ $(CPPBIN)/facade_check: cpp/cmd/facade_check.cpp $(CPPHDRS) $(LIB)
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
-$(OBJ)/bvh_build.o: $(SRC)/bvh_build.cpp $(HDRS)
+$(OBJ)/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p $(OBJ)
 	$(HOSTCXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/bvh_build.o
+$(LIB): $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/bvh_build.o $(OBJ)/reduce_field.o
 	@mkdir -p $(dir $(LIB))
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $^ -Xlinker --exclude-libs=ALL
 

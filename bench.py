@@ -59,6 +59,55 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ helpers
+def reduce_field_leg(capi, desc, values, cells, lo, hi, with_reference, tmp_dir="/tmp"):
+    """reduceField(field, lo <= v <= hi) (cmd/generate_density_map/main.cpp:141-144) on a sampled field -- host code on
+    both sides: dg_reduce_field (index passes, multithreaded) vs the reference class's own reduceField (oracle/_ref, when built)."""
+    keep = np.ascontiguousarray((lo <= values) & (values <= hi) & (values != np.finfo(np.float64).max), np.uint8)
+    n_grid_cells = int(desc.resolution[0]) * int(desc.resolution[1]) * int(desc.resolution[2])
+    best, out = None, None
+    for _ in range(3):
+        nodes, cc = values.copy(), cells.copy()
+        cmap = np.empty(n_grid_cells, np.uint32); n1, n2 = C.c_uint64(), C.c_uint64(); tm = np.zeros(5)
+        t0 = time.perf_counter()
+        capi.check(capi.lib.dg_reduce_field(C.byref(desc), capi.ptr(nodes, capi.F64P), len(nodes), keep.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                            capi.ptr(cc, capi.U32P), len(cc), capi.ptr(cmap, capi.U32P), 0, C.byref(n1), C.byref(n2), capi.ptr(tm, capi.F64P)))
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, out = dt, (nodes[:n1.value], cc[:n2.value], cmap, tm.copy())
+    leg = {"what": "reduceField of the density field with the tool's predicate 0 <= v <= 3 rho0: host index passes of dg_reduce_field",
+           "nodes_in": int(len(values)), "nodes_out": int(len(out[0])), "cells_in": int(len(cells)), "cells_out": int(len(out[1])),
+           "ms": best * 1e3, "ms_cells_nodes_sort_write": [float(t) for t in out[3][:4]], "reference_sort_replayed": bool(out[3][4])}
+    if with_reference:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_api import REF_GRID_SO, RefGrid
+        if os.path.exists(REF_GRID_SO):
+            import struct
+            src, dst = os.path.join(tmp_dir, f"dg_reduce_in_{os.getpid()}.cdf"), os.path.join(tmp_dir, f"dg_reduce_out_{os.getpid()}.cdf")
+            try:
+                with open(src, "wb") as f:                              # the reference's one-field file layout (:678-719)
+                    f.write(struct.pack("<3d", *desc.domain_min)); f.write(struct.pack("<3d", *desc.domain_max)); f.write(struct.pack("<3I", *desc.resolution))
+                    f.write(struct.pack("<3d", *desc.cell_size)); f.write(struct.pack("<3d", *desc.inv_cell_size)); f.write(struct.pack("<QQ", n_grid_cells, 1))
+                    for arr in (values, cells, np.arange(len(cells), dtype=np.uint32)):
+                        f.write(struct.pack("<QQ", 1, len(arr))); f.write(np.ascontiguousarray(arr).tobytes())
+                ref = RefGrid(src); t_ref = ref.reduce_window(0, lo, hi); ref.save(dst); ref.close()
+                raw = np.fromfile(dst, np.uint8)
+                off = 24 * 4 + 12 + 16                                   # header: 4 x 3 doubles, 3 uint32, n_cells, n_fields
+                def nested(dtype, width):
+                    nonlocal off
+                    n = int(raw[off + 8:off + 16].view(np.uint64)[0]); off += 16
+                    a = raw[off:off + n * width * np.dtype(dtype).itemsize].view(dtype); off += a.nbytes
+                    return a.reshape(n, width) if width > 1 else a
+                rn, rc, rm = nested(np.float64, 1), nested(np.uint32, 32), nested(np.uint32, 1)
+                same = bool(np.array_equal(rn.view(np.uint64), out[0].view(np.uint64)) and np.array_equal(rc, out[1]) and np.array_equal(rm, out[2]))
+                leg["reference"] = {"ms": t_ref * 1e3, "kind": "reference", "impl": "CubicLagrangeDiscreteGrid::reduceField of oracle/_ref (serial, one std::set per node)",
+                                    "identical_nodes_cells_cell_map": same, "speedup": t_ref / best}
+            finally:
+                for p_ in (src, dst):
+                    if os.path.exists(p_):
+                        os.remove(p_)
+    return leg
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -527,6 +576,13 @@ def main():
             density["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "nodes/s", "kind": "port", "cores": orc.max_threads(),
                                        "sample": f"{n_cpu} nodes in 8 windows, oracle/dg_oracle.cpp (the reference tool needs Eigen)",
                                        "bit_exact_vs_gpu": bool(ok)}
+        try:                                                    # N3: the step after the density map in GenerateDensityMap (host code)
+            cells_h = np.empty((int(np.prod(np.array(res, np.uint64))), 32), np.uint32)
+            capi.check(capi.lib.dg_build_cells(desc.resolution, 0, len(cells_h), capi.ptr(cells_h, capi.U32P)))
+            density["reduce_field"] = reduce_field_leg(capi, desc, dens_h, cells_h, 0.0, 3000.0, with_reference=not args.no_cpu)
+            del cells_h
+        except Exception as ex:                                 # an auxiliary leg must not take the bench line down
+            density["reduce_field"] = {"error": repr(ex)}
         capi.lib.dg_field_destroy(fh)
         del dens
 

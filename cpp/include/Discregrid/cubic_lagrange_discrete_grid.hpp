@@ -22,7 +22,6 @@
 #include <limits>
 #include <map>
 #include <numeric>
-#include <set>
 #include <stdexcept>
 #include "discrete_grid.hpp"
 #include "geometry/TriangleMeshDistance.h"
@@ -190,8 +189,8 @@ public:
         return phi;
     }
 
-    // ---- reduceField (:1065-1174): host bookkeeping, same resulting members (kept cells in order, surviving nodes
-    // compacted by swap-with-last from the back, then sorted by the Morton value of their position)
+    // ---- reduceField (:1065-1174): the predicate is evaluated here; cells / nodes / cell map are rewritten by dg_reduce_field
+    // and end up exactly as the reference leaves them (kept cells in order, surviving nodes in its Z-curve order)
     void reduceField(unsigned int field_id, Predicate pred) override;
 
     void forEachCell(unsigned int, std::function<void(unsigned int, Eigen::AlignedBox3d const&, unsigned int)> const& cb) const
@@ -239,15 +238,6 @@ private:
         for (int d = 0; d < 3; d++) { mi[d] = static_cast<unsigned int>((x[d] - m_domain.min()[d]) * m_inv_cell_size[d]); if (mi[d] >= m_resolution[d]) mi[d] = m_resolution[d] - 1; }
         return m_cell_map[field_id][multiToSingleIndex({{mi[0], mi[1], mi[2]}})] != std::numeric_limits<unsigned int>::max();
     }
-    // Z-order key of reduceField.  The reference's morton_lut (src/data/z_sort_table.hpp:119-134) shifts its first stage by
-    // 48 and then by 24 bits, so the top byte of each coordinate falls off the 64-bit word: the key interleaves only the
-    // LOW 16 BITS of x, y, z (x at bit 0).  Reproduced as is -- the node order in a reduced .cdm depends on it.
-    static std::uint64_t morton3(std::uint32_t x, std::uint32_t y, std::uint32_t z)
-    {
-        auto spread = [](std::uint64_t v) { v &= 0xffff; v = (v | v << 16) & 0x0000ff0000ffull; v = (v | v << 8) & 0x00f00f00f00full;
-                                            v = (v | v << 4) & 0x0c30c30c30c3ull; v = (v | v << 2) & 0x249249249249ull; return v; };
-        return spread(x) | (spread(y) << 1) | (spread(z) << 2);
-    }
 };
 
 inline void CubicLagrangeDiscreteGrid::reduceField(unsigned int field_id, Predicate pred)
@@ -259,53 +249,18 @@ inline void CubicLagrangeDiscreteGrid::reduceField(unsigned int field_id, Predic
     std::vector<double> pos(3 * coeffs.size());
     check(dg_node_positions(&d, 0, coeffs.size(), pos.data()));              // indexToNodePosition for every node (:604-665)
     const double dbl_max = std::numeric_limits<double>::max();
-    std::vector<char> keep(coeffs.size());
+    std::vector<std::uint8_t> keep(coeffs.size());                            // the predicate is the caller's: evaluated here, serially (:1069-1074)
     for (std::size_t l = 0; l < coeffs.size(); ++l)
-        keep[l] = pred(Eigen::Vector3d(pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]), coeffs[l]) && coeffs[l] != dbl_max;
+        keep[l] = (pred(Eigen::Vector3d(pos[3 * l], pos[3 * l + 1], pos[3 * l + 2]), coeffs[l]) && coeffs[l] != dbl_max) ? 1 : 0;
+    std::vector<double>().swap(pos);
     auto& cell_map = m_cell_map[field_id];
-    cell_map.assign(m_n_cells, 0u);
-    std::vector<std::array<unsigned int, 32>> kept;
-    for (std::size_t i = 0; i < cells.size(); ++i) {                          // a cell survives if any of its nodes does
-        bool any = false;
-        for (auto v : cells[i]) any = any || keep[v];
-        if (any) { kept.push_back(cells[i]); cell_map[i] = static_cast<unsigned int>(kept.size() - 1); }
-        else cell_map[i] = std::numeric_limits<unsigned int>::max();
-    }
-    cells.swap(kept);
-    // Morton key of every node position: zValue(x, 4 * min(inv_cell)) (:583-601, :1114)
-    const double inv = 4.0 * std::min(std::min(m_inv_cell_size[0], m_inv_cell_size[1]), m_inv_cell_size[2]);
-    std::vector<std::uint64_t> zval(coeffs.size());
-    for (std::size_t l = 0; l < coeffs.size(); ++l) {
-        std::uint32_t p[3];
-        for (int k = 0; k < 3; k++) {
-            const double xk = pos[3 * l + k];
-            const int key = (xk >= 0.0) ? static_cast<int>(inv * xk) : static_cast<int>(inv * xk) - 1;
-            p[k] = static_cast<std::uint32_t>(static_cast<std::int64_t>(key) - (std::numeric_limits<int>::lowest() + 1));
-        }
-        zval[l] = morton3(p[0], p[1], p[2]);
-    }
-    // nodes referenced by surviving cells, with back-references (cell, slot)
-    std::fill(keep.begin(), keep.end(), 0);
-    std::vector<std::set<std::pair<unsigned int, unsigned int>>> users(coeffs.size());
-    for (unsigned c = 0; c < cells.size(); ++c)
-        for (unsigned j = 0; j < 32; ++j) { keep[cells[c][j]] = 1; users[cells[c][j]].insert({c, j}); }
-    unsigned last = static_cast<unsigned>(coeffs.size() - 1);
-    for (int i = static_cast<int>(coeffs.size()) - 1; i >= 0; --i) {          // compaction by swap-with-last, from the back
-        if (keep[i]) continue;
-        std::swap(coeffs[i], coeffs[last]); std::swap(zval[i], zval[last]); std::swap(users[i], users[last]);
-        for (auto const& u : users[i]) cells[u.first][u.second] = static_cast<unsigned>(i);
-        for (auto const& u : users[last]) cells[u.first][u.second] = last;
-        last--;
-    }
-    coeffs.resize(last + 1); zval.resize(coeffs.size());
-    std::vector<unsigned int> order(coeffs.size());
-    std::iota(order.begin(), order.end(), 0u);
-    std::sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return zval[a] < zval[b]; });
-    for (unsigned i = 0; i < order.size(); ++i)
-        for (auto const& u : users[order[i]]) cells[u.first][u.second] = i;
-    std::vector<double> sorted(coeffs.size());
-    for (unsigned i = 0; i < order.size(); ++i) sorted[i] = coeffs[order[i]];
-    coeffs.swap(sorted);
+    cell_map.resize(m_n_cells);
+    // surviving cells, surviving nodes in Z-curve order, renumbered connectivity, cell map (:1076-1173) -- the library's index passes
+    std::uint64_t n_nodes = 0, n_cells = 0;
+    check(dg_reduce_field(&d, coeffs.data(), coeffs.size(), keep.data(), reinterpret_cast<std::uint32_t*>(cells.data()), cells.size(),
+                          cell_map.data(), 0u, &n_nodes, &n_cells, nullptr));
+    coeffs.resize(n_nodes);
+    cells.resize(n_cells);
 }
 
 }  // namespace Discregrid

@@ -22,6 +22,7 @@
 #include "k1_sdf.h"
 #include "k2_interp.h"
 #include "k3_density.h"
+#include "reduce_field.h"
 
 using namespace dgb;
 
@@ -789,6 +790,26 @@ int dg_density_map(const dg_field* f, double h, double rho0, int no_reduction, u
     DG_CUDA(d_out.alloc(n));
     if (int rc = dg_density_map_device(f, h, rho0, no_reduction, l_begin, l_end, d_out.p, nullptr)) return rc;
     if (n) DG_CUDA(cudaMemcpy(out_host, d_out.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return DG_OK;
+}
+
+int dg_reduce_field(const dg_grid_desc* grid, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
+                    uint32_t* cell_map, uint32_t flags, uint64_t* n_nodes_out, uint64_t* n_cells_out, double* timings_ms)
+{
+    GridDev g; const char* why = "";
+    if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_reduce_field: %s", why);
+    const uint64_t n_grid_nodes = (uint64_t)g.nv + 2ull * ((uint64_t)g.ne_x + g.ne_y + g.ne_z);
+    const uint64_t n_grid_cells = (uint64_t)g.n[0] * g.n[1] * g.n[2];
+    if (!nodes || !keep_node || !cell_map || (n_cells_in && !cells) || !n_nodes_out || !n_cells_out)
+        return fail(DG_ERR_INVALID, "dg_reduce_field: NULL argument");
+    if (n_nodes != n_grid_nodes)          // node ids must be the grid's own numbering: their positions feed the Z-curve key (:1113)
+        return fail(DG_ERR_INVALID, "dg_reduce_field: the field has %llu nodes, the grid %llu (already reduced?)", (unsigned long long)n_nodes,
+                    (unsigned long long)n_grid_nodes);
+    ReduceStats st; const char* err = "";
+    if (!reduce_field_host(g, nodes, n_nodes, keep_node, cells, n_cells_in, cell_map, n_grid_cells, (flags & DG_REDUCE_REFERENCE_SORT) != 0, st, &err))
+        return fail(DG_ERR_INVALID, "dg_reduce_field: %s", err);
+    *n_nodes_out = st.nodes_out; *n_cells_out = st.cells_out;
+    if (timings_ms) { timings_ms[0] = st.ms_cells; timings_ms[1] = st.ms_nodes; timings_ms[2] = st.ms_sort; timings_ms[3] = st.ms_write; timings_ms[4] = (double)st.tie_path; }
     return DG_OK;
 }
 

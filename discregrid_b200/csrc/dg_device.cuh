@@ -6,7 +6,12 @@
 // probes for contraction at run time and refuses to run if it is on.
 #pragma once
 #include <cstdint>
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#define DG_HD __host__ __device__ __forceinline__
+#else                              // host-only translation units (reduce_field.cpp) share the index algebra; built with -ffp-contract=off
+#define DG_HD inline
+#endif
 
 namespace dgb {
 
@@ -20,7 +25,7 @@ struct GridDev {                 // dg_grid_desc, device copy (passed by value a
 
 // indexToNodePosition, cubic_lagrange_discrete_grid.cpp:604-665.  Unsigned 32-bit index algebra exactly as
 // the reference; position = min + cell*ijk, then the 1/3 or 2/3 offset ((1.0 + b) / 3.0) * cell[d].
-__device__ __forceinline__ void node_position(const GridDev& g, unsigned l, double& x, double& y, double& z)
+DG_HD void node_position(const GridDev& g, unsigned l, double& x, double& y, double& z)
 {
     const unsigned nx = g.n[0], ny = g.n[1], nz = g.n[2];
     unsigned i, j, k;
@@ -56,7 +61,7 @@ __device__ __forceinline__ void node_position(const GridDev& g, unsigned l, doub
 }
 
 // closed-form connectivity of cell (i,j,k): node id of local node jn (cubic_lagrange_discrete_grid.cpp:848-885)
-__device__ __forceinline__ unsigned cell_node_id(const GridDev& g, unsigned i, unsigned j, unsigned k, unsigned jn)
+DG_HD unsigned cell_node_id(const GridDev& g, unsigned i, unsigned j, unsigned k, unsigned jn)
 {
     const unsigned nx = g.n[0], ny = g.n[1], nz = g.n[2];
     if (jn < 8) {

@@ -151,6 +151,21 @@ class CubicLagrangeDiscreteGrid:
         self.m_n_fields += 1
         return self.m_n_fields - 1
 
+    # ------------------------------------------------------------------ reduceField (cubic_lagrange_discrete_grid.cpp:1065-1174)
+    def reduceField(self, field_id, pred):
+        """Sparsifies a field.  pred(x[n,3], values[n]) -> bool[n] is the reference's Predicate, vectorised; nodes, cells and the
+        cell map end up exactly as the reference leaves them (dg_reduce_field)."""
+        nodes = np.ascontiguousarray(self.m_nodes[field_id], np.float64).copy()
+        keep = np.asarray(pred(self.nodePositions(0, len(nodes)), nodes), bool) & (nodes != np.finfo(np.float64).max)   # :1073
+        keep = np.ascontiguousarray(keep, np.uint8)
+        cells = np.ascontiguousarray(self.m_cells[field_id], np.uint32).copy()
+        cmap = np.empty(self.m_n_cells, np.uint32)
+        n_nodes, n_cells = C.c_uint64(), C.c_uint64()
+        capi.check(capi.lib.dg_reduce_field(C.byref(self._desc), capi.ptr(nodes, capi.F64P), len(nodes), keep.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                            capi.ptr(cells, capi.U32P), len(cells), capi.ptr(cmap, capi.U32P), 0, C.byref(n_nodes), C.byref(n_cells), None))
+        self._invalidate()
+        self.m_nodes[field_id], self.m_cells[field_id], self.m_cell_map[field_id] = nodes[:n_nodes.value].copy(), cells[:n_cells.value].copy(), cmap
+
     # ------------------------------------------------------------------ device field cache
     def _device_field(self, field_id):
         if field_id not in self._fields:

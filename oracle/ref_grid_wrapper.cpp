@@ -4,6 +4,7 @@
 // oracle's interpolate / shape functions to the reference's code, to generate golden vectors, and as the "reference" CPU
 // baseline of interpolate (the OpenMP pixel-loop pattern of cmd/discrete_field_to_bitmap/main.cpp:118-135).
 #include <Discregrid/All>
+#include <chrono>
 #include <cstdint>
 #include <limits>
 #ifdef _OPENMP
@@ -61,4 +62,14 @@ void refg_split(void* h, unsigned field, const double* x, uint64_t n, int32_t* o
         for (int d = 0; d < 3; d++) grad2[3 * q + d] = gq[d];
     }
 }
+// reduceField (:1065-1174) with the value-window predicate of cmd/generate_density_map/main.cpp:141-144 (lo <= v <= hi), timed;
+// the result is read back through save() (the members have no accessors).
+double refg_reduce_window(void* h, unsigned field, double lo, double hi)
+{
+    auto* g = (CubicLagrangeDiscreteGrid*)h;
+    const auto t0 = std::chrono::steady_clock::now();
+    g->reduceField(field, [lo, hi](Vector3d const&, double v) { return lo <= v && v <= hi; });
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+void refg_save(void* h, const char* path) { ((CubicLagrangeDiscreteGrid*)h)->save(std::string(path)); }
 }

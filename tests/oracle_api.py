@@ -241,6 +241,16 @@ class RefGrid:
         f(self.h, field, _p(x, _dp), len(x), _p(phi, _dp), _p(g, _dp), nthreads)
         return phi, g
 
+    def reduce_window(self, field, lo, hi):
+        """reduceField(field, lo <= v <= hi); returns the seconds the reference's call took"""
+        f = self.lib.refg_reduce_window
+        f.argtypes = [C.c_void_p, C.c_uint, C.c_double, C.c_double]; f.restype = C.c_double
+        return f(self.h, field, lo, hi)
+
+    def save(self, path):
+        self.lib.refg_save.argtypes = [C.c_void_p, C.c_char_p]
+        self.lib.refg_save(self.h, path.encode())
+
     def split(self, field, x):
         x = _f64(x).reshape(-1, 3); n = len(x)
         ok = np.zeros(n, np.int32); N = np.zeros((n, 32)); dN = np.zeros((n, 32, 3)); c0 = np.zeros((n, 3))

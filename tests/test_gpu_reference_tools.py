@@ -102,3 +102,24 @@ def test_shape_function_kernel_matches_reference_class(dg):
     N = np.empty((len(xi), 32)); dN = np.empty((len(xi), 32, 3))
     capi.check(capi.lib.dg_shape_functions(capi.ptr(xi, capi.F64P), len(xi), capi.ptr(N, capi.F64P), capi.ptr(dN, capi.F64P)))
     assert bits_equal(N, q["box_split_N"][ok]) and bits_equal(dN, q["box_split_dN"][ok])
+
+
+def test_python_reduce_field_then_interpolate(dg):
+    """Python mirror of reduceField (node positions from the GPU, dg_reduce_field on the host): ref_sphere.cdf reduced with the tool's
+    SDF predicate must equal field 0 of the reference tool's reduced file, and the sparsified field must interpolate like it"""
+    h = 0.15
+    g = dg.CubicLagrangeDiscreteGrid(os.path.join(GOLDEN, "ref_sphere.cdf"))
+    red = read_cdf(os.path.join(GOLDEN, "ref_sphere_reduced.cdm"))
+    cs = g.cellSize()
+    cell_diag = np.sqrt((cs[0] ** 2 + cs[1] ** 2) + cs[2] ** 2)
+    seen = {}
+
+    def pred(x, v):
+        seen["x"] = x
+        return (-6.0 * h < v + cell_diag) & (v - cell_diag < 2.0 * h)
+    g.reduceField(0, pred)
+    assert seen["x"].shape == (len(read_cdf(os.path.join(GOLDEN, "ref_sphere.cdf"))["nodes"][0]), 3)
+    assert bits_equal(g.m_nodes[0], red["nodes"][0]) and np.array_equal(g.m_cells[0], red["cells"][0]) and np.array_equal(g.m_cell_map[0], red["cmap"][0])
+    q = np.load(os.path.join(GOLDEN, "ref_grid_queries.npz"))
+    phi, grad = g.interpolate(0, q["red_x"], gradient=True)
+    assert bits_equal(phi, q["red_f0_phi"]) and bits_equal(grad, q["red_f0_grad"])
