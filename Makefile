@@ -54,7 +54,7 @@ $(OBJ)/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p $(OBJ)
 	$(HOSTCXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/bvh_build.o $(OBJ)/reduce_field.o
+$(LIB): $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/bvh_build.o $(OBJ)/reduce_field.o $(OBJ)/obj_reader.o
 	@mkdir -p $(dir $(LIB))
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $^ -Xlinker --exclude-libs=ALL
 

@@ -366,6 +366,8 @@ def main():
     k1_gbs = k1_alg_bytes / (k1_ms * 1e-3) / 1e9
     roofline = {"kernel": "sdf_sample_nodes_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": k1_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "traffic_ncu_other_config": {"bytes_per_launch": 27.4e6, "capture": "profiles/r1d_ncu_summary.csv: ncu --set full at 64^3 (the bench runs 128^3): dram read "
+                                                                                    "27.0 MB = the mesh records once, 0.4 MB written back inside the launch"},
                 "algorithmic_bytes_per_launch": k1_alg_bytes / max(1, n_launch), "launches_per_step": n_launch,
                 "avg_launch_ms": k1_ms / max(1, n_launch),
                 "note": "K1 is NOT HBM-bound: BVH + triangle records are L2-resident and compulsory HBM traffic is 8 B/node "
@@ -458,7 +460,10 @@ def main():
                              "field_build_s": build_s},
                   "roofline": {"kernel": "interpolate_kernel<true> (K2)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                               "algorithmic_bytes_per_query": 312},
+                               "algorithmic_bytes_per_query": 312,
+                               "traffic_ncu_other_config": {"bytes_per_launch": 2.78e9, "algorithmic_bytes_per_launch": 3.12e9,
+                                                            "capture": "profiles/r1e_k2k3_ncu_summary.csv: ncu --set full on the 128^3 field (the bench runs 256^3), "
+                                                                       "dram read 2.46 GB + write 0.314 GB"}},
                   "e2e": {"value": nq / dt / 1e6, "unit": "Mqueries/s", "h2d_bytes_per_step": 24 * nq, "d2h_bytes_per_step": 32 * nq,
                           "api": "dg_interpolate_batch(field, x_host, n, phi_host, grad_host)"}}
         capi.lib.dg_field_destroy(fh)

@@ -4,12 +4,14 @@
 // The half-edge adjacency of the reference class is not needed by TriangleMeshDistance (TriangleMeshDistance.h:227-230).
 #pragma once
 #include <array>
+#include <cstdint>
 #include <fstream>
 #include <iostream>
-#include <sstream>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #include <Eigen/Dense>
+#include "discregrid_b200.h"
 
 namespace Discregrid {
 class TriangleMesh {
@@ -23,27 +25,18 @@ public:
         for (std::size_t i = 0; i < nv; i++) m_vertices[i] = Eigen::Vector3d(vertices[3 * i], vertices[3 * i + 1], vertices[3 * i + 2]);
         for (std::size_t i = 0; i < nf; i++) m_faces[i] = {{faces[3 * i], faces[3 * i + 1], faces[3 * i + 2]}};
     }
+    // OBJ file: the library's reader (dg_obj_read) -- same records, same values as the reference's stream parser (triangle_mesh.cpp:90-124)
     explicit TriangleMesh(std::string const& path)
     {
-        std::ifstream in(path, std::ios::in);
-        if (!in) { std::cerr << "Cannot open " << path << std::endl; return; }
-        std::string line;
-        while (std::getline(in, line)) {
-            if (line.substr(0, 2) == "v ") {
-                std::istringstream s(line.substr(2));
-                Eigen::Vector3d v; s >> v.x(); s >> v.y(); s >> v.z();
-                m_vertices.push_back(v);
-            } else if (line.substr(0, 2) == "f ") {
-                std::istringstream s(line.substr(2));
-                Face f;
-                for (unsigned int j = 0; j < 3; ++j) {
-                    std::string buf; s >> buf;
-                    buf = buf.substr(0, buf.find_first_of('/'));
-                    f[j] = static_cast<unsigned int>(std::stoi(buf) - 1);
-                }
-                m_faces.push_back(f);
-            }
-        }
+        double* v = nullptr; std::uint32_t* f = nullptr;
+        std::uint64_t nv = 0, nf = 0;
+        const int rc = dg_obj_read(path.c_str(), &v, &nv, &f, &nf);
+        if (rc == DG_ERR_IO) { std::cerr << "Cannot open " << path << std::endl; return; }              // :93-97: message, object left empty
+        if (rc != DG_OK) throw std::invalid_argument(std::string("stoi: ") + dg_last_error());            // what std::stoi does at :113
+        m_vertices.resize(nv); m_faces.resize(nf);
+        for (std::size_t i = 0; i < nv; i++) m_vertices[i] = Eigen::Vector3d(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        for (std::size_t i = 0; i < nf; i++) m_faces[i] = {{f[3 * i], f[3 * i + 1], f[3 * i + 2]}};
+        dg_obj_free(v, f);
     }
     void exportOBJ(std::string const& filename) const
     {

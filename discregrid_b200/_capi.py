@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DISCREGRID_B200_LIB: tuning builds of the same library (tools/build_variants.py); never a different implementation
 LIB_PATH = os.environ.get("DISCREGRID_B200_LIB") or os.path.join(_HERE, "lib", "libdiscregrid_b200.so")
 
-DG_OK, DG_ERR_INVALID, DG_ERR_NO_DEVICE, DG_ERR_CUDA, DG_ERR_NOMEM, DG_ERR_SELFTEST = 0, -1, -2, -3, -4, -5
+DG_OK, DG_ERR_INVALID, DG_ERR_NO_DEVICE, DG_ERR_CUDA, DG_ERR_NOMEM, DG_ERR_SELFTEST, DG_ERR_IO = 0, -1, -2, -3, -4, -5, -6
 DBL_MAX = 1.7976931348623157e308
 UINT32_MAX = 0xFFFFFFFF
 
@@ -50,6 +50,8 @@ SIGNATURES = {
     "dg_grid_init": (C.c_int, [_dp, _dp, _u32p, _gp]),
     "dg_grid_num_nodes": (C.c_int, [_u32p, _u64p]),
     "dg_generate_sdf_domain": (C.c_int, [_dp, C.c_uint64, _dp, _dp]),
+    "dg_obj_read": (C.c_int, [C.c_char_p, C.POINTER(_dp), _u64p, C.POINTER(_u32p), _u64p]),
+    "dg_obj_free": (None, [_dp, _u32p]),
     "dg_mesh_create": (C.c_int, [_dp, C.c_uint64, _u32p, C.c_uint64, C.POINTER(_vp)]),
     "dg_mesh_destroy": (C.c_int, [_vp]),
     "dg_mesh_info": (C.c_int, [_vp, _u64p]),

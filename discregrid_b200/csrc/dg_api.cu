@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -23,6 +24,7 @@
 #include "k2_interp.h"
 #include "k3_density.h"
 #include "reduce_field.h"
+#include "obj_reader.h"
 
 using namespace dgb;
 
@@ -811,6 +813,26 @@ int dg_reduce_field(const dg_grid_desc* grid, double* nodes, uint64_t n_nodes, c
     *n_nodes_out = st.nodes_out; *n_cells_out = st.cells_out;
     if (timings_ms) { timings_ms[0] = st.ms_cells; timings_ms[1] = st.ms_nodes; timings_ms[2] = st.ms_sort; timings_ms[3] = st.ms_write; timings_ms[4] = (double)st.tie_path; }
     return DG_OK;
+}
+
+int dg_obj_read(const char* path, double** vertices, uint64_t* n_vertices, uint32_t** triangles, uint64_t* n_triangles)
+{
+    if (!path || !vertices || !n_vertices || !triangles || !n_triangles) return fail(DG_ERR_INVALID, "dg_obj_read: NULL argument");
+    *vertices = nullptr; *triangles = nullptr; *n_vertices = 0; *n_triangles = 0;
+    ObjData d; std::string err;
+    if (!read_obj(path, d, err)) return fail(err.rfind("Cannot open", 0) == 0 || err.rfind("short read", 0) == 0 ? DG_ERR_IO : DG_ERR_INVALID, "dg_obj_read: %s", err.c_str());
+    double* v = static_cast<double*>(std::malloc(std::max<size_t>(1, d.vertices.size() * sizeof(double))));
+    uint32_t* f = static_cast<uint32_t*>(std::malloc(std::max<size_t>(1, d.faces.size() * sizeof(uint32_t))));
+    if (!v || !f) { std::free(v); std::free(f); return fail(DG_ERR_NOMEM, "dg_obj_read: out of host memory"); }
+    if (!d.vertices.empty()) std::memcpy(v, d.vertices.data(), d.vertices.size() * sizeof(double));
+    if (!d.faces.empty()) std::memcpy(f, d.faces.data(), d.faces.size() * sizeof(uint32_t));
+    *vertices = v; *triangles = f; *n_vertices = d.vertices.size() / 3; *n_triangles = d.faces.size() / 3;
+    return DG_OK;
+}
+
+void dg_obj_free(double* vertices, uint32_t* triangles)
+{
+    std::free(vertices); std::free(triangles);
 }
 
 }  // extern "C"

@@ -42,18 +42,23 @@ class TriangleMesh:
 
 
 def _read_obj(path):
-    verts, faces = [], []
-    with open(path, "r") as fh:
-        for line in fh:
-            if line.startswith("v "):
-                p = line[2:].split()
-                verts.append((float(p[0]), float(p[1]), float(p[2])))
-            elif line.startswith("f "):
-                p = line[2:].split()
-                faces.append(tuple(int(tok.split("/")[0]) - 1 for tok in p[:3]))
-    if not verts and not faces:
+    """the library's OBJ reader (dg_obj_read: the records Discregrid::TriangleMesh(path) accepts, triangle_mesh.cpp:90-124)"""
+    import ctypes as C
+    from . import _capi as capi
+    v, f = capi.F64P(), capi.U32P()
+    nv, nf = C.c_uint64(), C.c_uint64()
+    rc = capi.lib.dg_obj_read(str(path).encode(), C.byref(v), C.byref(nv), C.byref(f), C.byref(nf))
+    if rc == capi.DG_ERR_IO:
+        raise FileNotFoundError((capi.lib.dg_last_error() or b"").decode("utf-8", "replace"))
+    capi.check(rc)
+    try:
+        verts = np.ctypeslib.as_array(v, shape=(nv.value, 3)).copy() if nv.value else np.zeros((0, 3))
+        faces = np.ctypeslib.as_array(f, shape=(nf.value, 3)).copy() if nf.value else np.zeros((0, 3), np.uint32)
+    finally:
+        capi.lib.dg_obj_free(v, f)
+    if not len(verts) and not len(faces):
         raise ValueError(f"no 'v'/'f' records in {path}")
-    return np.array(verts, np.float64).reshape(-1, 3), np.array(faces, np.int64).reshape(-1, 3).astype(np.uint32)
+    return verts, faces
 
 
 def bumpy_torus(nu=250, nv=200, R=1.0, r0=0.4, amp=0.05, ku=7, kv=5):

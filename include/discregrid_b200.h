@@ -48,7 +48,8 @@ typedef enum dg_status {
     DG_ERR_NO_DEVICE = -2,   /* no usable CUDA device: there is no CPU fallback */
     DG_ERR_CUDA = -3,        /* a CUDA runtime call failed; dg_last_error() has the cudaError string */
     DG_ERR_NOMEM = -4,       /* host or device allocation failed */
-    DG_ERR_SELFTEST = -5     /* device self-test failed (e.g. library built with FMA contraction on) */
+    DG_ERR_SELFTEST = -5,    /* device self-test failed (e.g. library built with FMA contraction on) */
+    DG_ERR_IO = -6           /* a file could not be opened or read */
 } dg_status;
 
 /* TriangleMeshDistance.h:75 -- same numbering */
@@ -88,6 +89,14 @@ DG_API void        dg_kernel_launch_count_reset(void);
 DG_API int dg_grid_init(const double domain_min[3], const double domain_max[3], const uint32_t resolution[3], dg_grid_desc* out);
 DG_API int dg_grid_num_nodes(const uint32_t resolution[3], uint64_t* n_nodes);
 DG_API int dg_generate_sdf_domain(const double* vertices, uint64_t n_vertices, double domain_min[3], double domain_max[3]);
+
+/* ---- OBJ reader (host, no GPU) ---------------------------------------------------------
+ * replaces the parser of Discregrid::TriangleMesh(path) (src/mesh/triangle_mesh.cpp:90-124): "v x y z" and "f a[/..] b[/..] c[/..]"
+ * lines, everything else ignored; same doubles as the stream extraction (correctly rounded), indices made 0-based.  The arrays
+ * are allocated by the library and released with dg_obj_free.  DG_ERR_IO when the file cannot be read, DG_ERR_INVALID for a face
+ * index the reference's std::stoi would throw on. */
+DG_API int dg_obj_read(const char* path, double** vertices, uint64_t* n_vertices, uint32_t** triangles, uint64_t* n_triangles);
+DG_API void dg_obj_free(double* vertices, uint32_t* triangles);
 
 /* ---- mesh / distance ------------------------------------------------------------------------------
  * dg_mesh_create replaces TriangleMeshDistance::construct / _construct / _build_tree

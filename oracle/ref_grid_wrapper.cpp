@@ -72,4 +72,20 @@ double refg_reduce_window(void* h, unsigned field, double lo, double hi)
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 void refg_save(void* h, const char* path) { ((CubicLagrangeDiscreteGrid*)h)->save(std::string(path)); }
+// the reference's OBJ loader, Discregrid::TriangleMesh(path) (src/mesh/triangle_mesh.cpp:90-124), timed
+void* refm_open(const char* path, double* seconds)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    auto* m = new Discregrid::TriangleMesh(std::string(path));
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return m;
+}
+void refm_sizes(void* h, uint64_t* nv, uint64_t* nf) { auto* m = (Discregrid::TriangleMesh*)h; *nv = m->nVertices(); *nf = m->nFaces(); }
+void refm_copy(void* h, double* V, uint32_t* F)
+{
+    auto* m = (Discregrid::TriangleMesh*)h;
+    for (std::size_t i = 0; i < m->nVertices(); i++) for (int d = 0; d < 3; d++) V[3 * i + d] = m->vertex_data()[i][d];
+    for (std::size_t i = 0; i < m->nFaces(); i++) for (int d = 0; d < 3; d++) F[3 * i + d] = m->face_data()[i][d];
+}
+void refm_close(void* h) { delete (Discregrid::TriangleMesh*)h; }
 }

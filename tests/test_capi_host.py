@@ -106,6 +106,67 @@ def test_obj_reader(dg, tmp_path):
     assert len(np.unique(key)) == len(key) and np.array_equal(np.sort(key), np.sort(e[:, 1] * t.nVertices() + e[:, 0]))
 
 
+def test_obj_reader_records_and_errors(dg, tmp_path):
+    """dg_obj_read accepts exactly what the reference's stream parser does (src/mesh/triangle_mesh.cpp:90-124)"""
+    from discregrid_b200 import _capi as capi
+    p = tmp_path / "odd.obj"
+    p.write_bytes(b"# comment\r\n"
+                  b"v 1 2 3\r\n"                       # CRLF
+                  b"v   +0.5\t-2.5e-1   1e2 0.75\n"    # blanks, tab, explicit +, a 4th value (ignored)
+                  b"v\t9 9 9\n"                        # "v<TAB>" is not "v ": ignored
+                  b"vn 0 0 1\nvt 0 1\ng grp\n"
+                  b"v 0.1 0.2\n"                        # short record: the missing value stays 0 here (uninitialised in the reference)
+                  b"v .5 -.25 1.\n"
+                  b"f 1/7/9 2//3 3 4\n"                 # only the first three corners, index before the first '/'
+                  b"f  4   1   2")                      # no trailing newline
+    m = dg.TriangleMesh(str(p))
+    assert np.array_equal(m.vertices, [[1, 2, 3], [0.5, -0.25, 100.0], [0.1, 0.2, 0.0], [0.5, -0.25, 1.0]])
+    assert np.array_equal(m.faces, [[0, 1, 2], [3, 0, 1]])
+    # correctly rounded like operator>>: 17-digit round trip of awkward values
+    vals = np.array([0.1, 1 / 3, 2 ** -1074, 1.7976931348623157e308, 123456789.12345678, 5e-324, 0.30000000000000004], np.float64)
+    q = tmp_path / "round.obj"
+    q.write_text("".join(f"v {a!r} {-a!r} {a!r}\n" for a in vals.tolist()))
+    got = dg.TriangleMesh(str(q)).vertices
+    assert bits_equal(got[:, 0], vals) and bits_equal(got[:, 1], -vals)
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2\n")            # std::stoi("") throws in the reference
+    with pytest.raises(dg.DiscregridError) as ei:
+        dg.TriangleMesh(str(bad))
+    assert ei.value.code == capi.DG_ERR_INVALID and "bad.obj:4" in str(ei.value)
+    with pytest.raises(FileNotFoundError):
+        dg.TriangleMesh(str(tmp_path / "missing.obj"))
+
+
+def test_obj_reader_parallel_chunks_and_reference_loader(dg, tmp_path):
+    """a file large enough to be parsed by several threads (chunks cut at line starts) gives the same arrays as a line-by-line
+    reader; the staged reference meshes equal the reference's own loader bit for bit where that was compiled (oracle/_ref)"""
+    import ctypes as C
+    from test_oracle_golden import read_obj
+    t = dg.bumpy_torus(300, 301, 1.0, 0.4, 0.05, 7, 5)
+    p = str(tmp_path / "big.obj")
+    t.exportOBJ(p)
+    assert os.path.getsize(p) > (1 << 21)
+    m = dg.TriangleMesh(p)
+    V, F = read_obj(p)
+    assert bits_equal(m.vertices, V) and np.array_equal(m.faces, F) and bits_equal(m.vertices, t.vertices) and np.array_equal(m.faces, t.faces)
+    from oracle_api import REF_GRID_SO
+    from conftest import ref_resource
+    if not os.path.exists(REF_GRID_SO) or ref_resource("bunny.obj") is None:
+        return
+    lib = C.CDLL(REF_GRID_SO)
+    lib.refm_open.restype = C.c_void_p; lib.refm_open.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
+    lib.refm_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.refm_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]; lib.refm_close.argtypes = [C.c_void_p]
+    for name in ("bunny.obj", "dragon.obj"):
+        path = ref_resource(name)
+        sec = C.c_double(); h = lib.refm_open(path.encode(), C.byref(sec))
+        nv, nf = C.c_uint64(), C.c_uint64(); lib.refm_sizes(h, C.byref(nv), C.byref(nf))
+        Vr = np.empty((nv.value, 3)); Fr = np.empty((nf.value, 3), np.uint32)
+        lib.refm_copy(h, Vr.ctypes.data, Fr.ctypes.data); lib.refm_close(h)
+        mine = dg.TriangleMesh(path)
+        assert bits_equal(mine.vertices, Vr) and np.array_equal(mine.faces, Fr)
+
+
 def test_node_sharding_partition():
     from discregrid_b200.distributed import make_sharding
     for n, world in ((14926977, 8), (32657, 2), (1296, 4), (118425857, 8), (77, 1)):
