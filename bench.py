@@ -76,7 +76,7 @@ def reduce_field_leg(capi, desc, values, cells, lo, hi, with_reference, tmp_dir=
             best, out = dt, (nodes[:n1.value], cc[:n2.value], cmap, tm.copy())
     leg = {"what": "reduceField of the density field with the tool's predicate 0 <= v <= 3 rho0: host index passes of dg_reduce_field",
            "nodes_in": int(len(values)), "nodes_out": int(len(out[0])), "cells_in": int(len(cells)), "cells_out": int(len(out[1])),
-           "ms": best * 1e3, "ms_cells_nodes_sort_write": [float(t) for t in out[3][:4]], "reference_sort_replayed": bool(out[3][4])}
+           "ms": best * 1e3, "ms_cells_nodes_sort_write": [float(t) for t in out[3][:4]], "morton_keys_tied": bool(out[3][4])}
     if with_reference:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from oracle_api import REF_GRID_SO, RefGrid

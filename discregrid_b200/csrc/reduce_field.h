@@ -6,9 +6,10 @@
 //   2. nodes: those referenced by a surviving cell survive.  The reference compacts them by "swap the dead node with the last
 //      live slot, walking from the back" (:1136-1156) -- replayed on a permutation array, O(n), no sets;
 //   3. the survivors are ordered by the Morton key of their position (zValue, :583-601, with the LUT's 16-bit truncation,
-//      z_sort_table.hpp:119-134).  std::sort is not stable, so when two survivors share a key the reference's order is whatever
-//      libstdc++'s introsort leaves: in that case the very same std::sort call is made (same input sequence, same comparisons =>
-//      same result); when all keys are distinct -- the normal case -- the order is unique and a multithreaded sample sort is used.
+//      z_sort_table.hpp:119-134).  std::sort is not stable, so when two survivors share a key -- the normal case on the anisotropic
+//      cells of a bounding-box-fitted domain -- the reference's order is whatever libstdc++'s introsort leaves.  That sort is
+//      replayed on all host threads (replay_std_sort below: same comparisons, same swaps, same result); should the process run on
+//      a standard library that sorts differently, the plain std::sort call is made instead (any sort while keys are distinct).
 // Host code: the reference's reduceField is host bookkeeping around the sampled fields; nothing here is a kernel's fallback.
 #pragma once
 #include <cstdint>
@@ -18,7 +19,7 @@ namespace dgb {
 
 struct ReduceStats {
     uint64_t nodes_out = 0, cells_out = 0;
-    int tie_path = 0;              // 1 = duplicate Morton keys among the survivors: the reference's std::sort was replayed
+    int tie_path = 0;              // 1 = duplicate Morton keys among the survivors: their order is std::sort's, not the keys'
     double ms_cells = 0, ms_nodes = 0, ms_sort = 0, ms_write = 0;
 };
 
@@ -27,6 +28,17 @@ struct ReduceStats {
 // force_std_sort: always take the reference's own sort (tests).
 bool reduce_field_host(const GridDev& g, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
                        uint32_t* cell_map, uint64_t n_cells_grid, bool force_std_sort, ReduceStats& st, const char** err);
+
+// The tie path.  std::sort on n (key, position) records ordered by key only is libstdc++'s introsort: median-of-3 quicksort down to
+// 16-element blocks with a 2*floor(log2 n) depth budget (heapsort beyond it), then one insertion-sort pass.  Every quicksort split
+// leaves two independent ranges, and the insertion pass never moves a record across a split (left part <= pivot <= right part), so
+// the same sequence of comparisons and swaps can run on many threads and ends in the same arrangement, ties included.
+// replay_std_sort does that; replay_std_sort_matches() checks it against std::sort itself on tie-heavy inputs once per process
+// (a different standard library may sort differently: then the library's own std::sort call is used, single-threaded).
+struct KeyPos { uint64_t key; uint32_t pos; };
+void replay_std_sort(KeyPos* a, uint64_t n, unsigned n_threads);
+bool replay_std_sort_matches();
+uint64_t replay_std_sort_heap_fallbacks();      // number of depth-exhausted ranges so far (tests)
 
 // zValue(indexToNodePosition(l), 4 * min(inv_cell_size)) for one node (exposed for tests)
 uint64_t reduce_field_morton_key(const GridDev& g, uint32_t l);

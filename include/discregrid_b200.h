@@ -205,8 +205,9 @@ DG_API int dg_density_map_device(const dg_field* sdf, double h, double rho0, int
  * reference leaves its members: cells (n_cells_in x 32; first *n_cells_out rows = surviving cells, renumbered), nodes (first
  * *n_nodes_out coefficients = surviving nodes in the reference's Z-curve order) and cell_map (resolution product entries; 0xffffffff
  * for removed cells).  Host bookkeeping like the reference's (multithreaded, no per-node std::set); needs no GPU.
- * flags: DG_REDUCE_REFERENCE_SORT forces the reference's own std::sort (it is used anyway when two surviving nodes share a key).
- * timings_ms: NULL or 5 doubles (ms spent on cells, node compaction, sort, write-back; 1.0 if the reference's std::sort was used). */
+ * flags: DG_REDUCE_REFERENCE_SORT makes the plain single-threaded std::sort call instead of its multithreaded replay (same result).
+ * timings_ms: NULL or 5 doubles (ms spent on cells, node compaction, sort, write-back; 1.0 if surviving nodes shared Morton keys,
+ * i.e. the node order depended on how std::sort leaves equal keys). */
 #define DG_REDUCE_REFERENCE_SORT 1u
 DG_API int dg_reduce_field(const dg_grid_desc* grid, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells,
                     uint64_t n_cells_in, uint32_t* cell_map, uint32_t flags, uint64_t* n_nodes_out, uint64_t* n_cells_out,

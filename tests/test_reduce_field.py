@@ -127,3 +127,15 @@ def test_against_the_reference_library(dg, orc, tmp_path, mn, mx, res, lo, hi):
     g = dict(mn=np.array(mn, float), mx=np.array(mx, float), res=np.array(res, np.uint32), cell=gd[6:9], inv=gd[9:12])
     nodes, c2, cmap = reduce_field(dg, g, v, (lo <= v) & (v <= hi) & (v != DBL_MAX), cells)
     assert bits_equal(nodes, want["nodes"][0]) and np.array_equal(c2, want["cells"][0]) and np.array_equal(cmap, want["cmap"][0])
+
+
+def test_threaded_sort_replay_equals_std_sort():
+    """tests/cpp/sort_replay_check.cpp: the tie path's multithreaded replay of libstdc++'s introsort leaves records with equal keys
+    exactly where std::sort leaves them (random ties, few keys, presorted, adversarial input that exhausts the depth budget)"""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "build", "bin", "sort_replay_check")
+    if not os.path.exists(exe):
+        pytest.skip("build/bin/sort_replay_check not built (make cpp)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
