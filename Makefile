@@ -28,13 +28,13 @@ cpp: $(CPPBIN)/GenerateSDF $(CPPBIN)/GenerateDensityMap $(CPPBIN)/DiscreteFieldT
 $(CPPBIN)/DiscreteFieldToBitmap: cpp/cmd/discrete_field_to_bitmap.cpp $(CPPHDRS) $(LIB)
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK)
-$(CPPBIN)/bvh_host_check: tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/bvh_build.h
+$(CPPBIN)/bvh_host_check: tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp $(SRC)/sort_replay.h $(SRC)/bvh_build.h
 	@mkdir -p $(CPPBIN)
-	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp -o $@ -lpthread
+	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp -o $@ -lpthread
 # test binary: the threaded std::sort replay of reduce_field.cpp against std::sort (ties, depth exhaustion)
-$(CPPBIN)/sort_replay_check: tests/cpp/sort_replay_check.cpp $(SRC)/reduce_field.cpp $(SRC)/reduce_field.h $(SRC)/dg_device.cuh
+$(CPPBIN)/sort_replay_check: tests/cpp/sort_replay_check.cpp $(SRC)/reduce_field.cpp $(SRC)/sort_replay.cpp $(SRC)/sort_replay.h $(SRC)/reduce_field.h $(SRC)/dg_device.cuh
 	@mkdir -p $(CPPBIN)
-	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default -I$(SRC) tests/cpp/sort_replay_check.cpp $(SRC)/reduce_field.cpp -o $@ -lpthread
+	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default -I$(SRC) tests/cpp/sort_replay_check.cpp $(SRC)/reduce_field.cpp $(SRC)/sort_replay.cpp -o $@ -lpthread
 # test binary: the facade's reduceField with dg_node_positions interposed by the oracle (runs without a GPU)
 $(CPPBIN)/reduce_facade_check: tests/cpp/reduce_facade_check.cpp $(CPPHDRS) $(LIB) oracle/liboracle.so
 	@mkdir -p $(CPPBIN)
@@ -58,7 +58,7 @@ $(OBJ)/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p $(OBJ)
 	$(HOSTCXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/bvh_build.o $(OBJ)/reduce_field.o $(OBJ)/obj_reader.o
+$(LIB): $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/bvh_build.o $(OBJ)/reduce_field.o $(OBJ)/obj_reader.o $(OBJ)/sort_replay.o
 	@mkdir -p $(dir $(LIB))
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $^ -Xlinker --exclude-libs=ALL
 

@@ -1,6 +1,7 @@
 // See bvh_build.h.  Compiled with -ffp-contract=off: every expression below must round exactly like the
 // reference's x86-64 build (no FMA), because these values feed bit-exact device comparisons.
 #include "bvh_build.h"
+#include "sort_replay.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -50,6 +51,8 @@ struct Builder {
     std::vector<Key> keys;                 // scratch for the sort (same comparisons => same permutation as the reference)
     std::atomic<int> max_depth{0};
     int par_levels = 0;                    // subtrees of the first `par_levels` levels are built by separate threads
+    unsigned hw_threads = 1;               // host threads the whole build may use
+    bool replay_ok = false;                // sort_replay_matches_std_sort()
 
     inline P3 vert(int32_t tri, int k) const { return V[F[3 * (size_t)tri + k]]; }
 
@@ -92,7 +95,14 @@ struct Builder {
 
         // unstable std::sort on the first vertex's coordinate (TriangleMeshDistance.h:494-499)
         for (int i = b; i < e; i++) keys[i] = {at(vert(order[i], 0), split), order[i]};
-        std::sort(keys.begin() + b, keys.begin() + e, [](const Key& x, const Key& y) { return x.k < y.k; });
+        {
+            auto by_key = [](const Key& x, const Key& y) { return x.k < y.k; };
+            // near the root one sort is most of the critical path: same comparisons and swaps as std::sort, on the threads this
+            // subtree may use (sort_replay.h); the arrangement -- ties included -- is the one std::sort leaves
+            const unsigned share = hw_threads >> (depth - 1 < 16 ? depth - 1 : 16);
+            if (n >= 32768 && share >= 2 && replay_ok) replay_sort(keys.data() + b, (uint64_t)n, by_key, share);
+            else std::sort(keys.begin() + b, keys.begin() + e, by_key);
+        }
         for (int i = b; i < e; i++) order[i] = keys[i].id;
 
         const int m = (b + e) >> 1;
@@ -124,15 +134,19 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
     out.n_vertices = nV; out.n_triangles = nT;
     out.V.assign(Vd, Vd + 3 * nV);
     out.F.assign(F, F + 3 * nT);
-    out.spheres.assign(nT, SpherePair());
+    out.spheres.resize(nT);
+    std::memset(&out.spheres[0], 0, sizeof(SpherePair));               // index 0 is no node's split position
     out.order.resize(nT);
     for (int i = 0; i < T; i++) out.order[i] = i;
 
     Builder bld{V, F, out, out.order};
     bld.keys.resize(nT);
-    { unsigned hw = std::thread::hardware_concurrency(); int lv = 0; while ((1u << (lv + 1)) <= hw && lv < 6) lv++; bld.par_levels = lv; }
+    { unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 1; if (hw > 64) hw = 64;
+      int lv = 0; while ((1u << (lv + 1)) <= hw && lv < 6) lv++; bld.par_levels = lv; bld.hw_threads = hw;
+      bld.replay_ok = nT >= 32768 && sort_replay_matches_std_sort(); }
     double root_c[3], root_r, root_box[6];
-    out.boxes.assign(12 * nT, 0.0);
+    out.boxes.resize(12 * nT);
+    std::memset(out.boxes.data(), 0, 12 * sizeof(double));
     bld.build(0, T, root_c, root_r, root_box, 1);
     out.max_depth = bld.max_depth.load();      // root sphere is computed and unused, as in the reference (:125,357)
 
@@ -140,7 +154,7 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
     // The reference accumulates into per-vertex / per-edge sums while looping over the triangles in index order (an
     // unordered_map keyed by the vertex pair for the edges).  The same sums, term by term in the same order, are produced
     // here from a vertex -> (triangle, slot) incidence list, which makes every stage a parallel loop.
-    out.pn_tri.assign(3 * nT, 0.0); out.pn_edge.assign(9 * nT, 0.0); out.pn_vert.assign(3 * nV, 0.0);
+    out.pn_tri.resize(3 * nT); out.pn_edge.resize(9 * nT); out.pn_vert.resize(3 * nV);          // every entry is written below
     P3* pt = reinterpret_cast<P3*>(out.pn_tri.data());
     P3* pe = reinterpret_cast<P3*>(out.pn_edge.data());
     P3* pv = reinterpret_cast<P3*>(out.pn_vert.data());
@@ -206,8 +220,8 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
     out.flags = flags.load();
 
     // ---- device records in leaf order
-    out.leaves.assign(nT, LeafRecord());
-    out.normals.assign(nT, PseudoNormals());
+    out.leaves.resize(nT);
+    out.normals.resize(nT);
     parallel_for(nT, [&](uint64_t p0, uint64_t p1) {
         for (uint64_t pos = p0; pos < p1; pos++) {
             const int id = out.order[pos];
@@ -235,28 +249,29 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
         for (uint64_t i = 0; i < nV; i++) for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], Vd[3 * i + d]); hi[d] = std::max(hi[d], Vd[3 * i + d]); }
         out.half_extent = 0;
         for (int d = 0; d < 3; d++) { out.center[d] = 0.5 * (lo[d] + hi[d]); out.half_extent = std::max(out.half_extent, std::max(hi[d] - out.center[d], out.center[d] - lo[d])); }
-        out.spheres_f.assign(nT, SpherePairF());
-        for (uint64_t m = 0; m < nT; m++) {
-            const SpherePair& sp = out.spheres[m];
-            SpherePairF& f = out.spheres_f[m];
-            for (int d = 0; d < 3; d++) { f.lc[d] = (float)(sp.lc[d] - out.center[d]); f.rc[d] = (float)(sp.rc[d] - out.center[d]); }
-            f.lr = (float)sp.lr; f.rr = (float)sp.rr;
-        }
-        // child boxes, rounded outward so that the fp32 box contains the fp64 one
-        out.boxes_f.assign(nT, BoxPairF());
+        out.spheres_f.resize(nT);
+        out.boxes_f.resize(nT);
+        // child boxes are rounded outward so that the fp32 box contains the fp64 one
         auto down = [](double v) { float f = (float)v; return ((double)f > v) ? std::nextafterf(f, -INFINITY) : f; };
         auto up = [](double v) { float f = (float)v; return ((double)f < v) ? std::nextafterf(f, INFINITY) : f; };
-        for (uint64_t m = 1; m < nT; m++) {
-            const double* bx = &out.boxes[12 * m];
-            BoxPairF& q = out.boxes_f[m];
-            for (int d = 0; d < 3; d++) {
-                q.l_lo[d] = down(bx[d] - out.center[d]); q.l_hi[d] = up(bx[3 + d] - out.center[d]);
-                q.r_lo[d] = down(bx[6 + d] - out.center[d]); q.r_hi[d] = up(bx[9 + d] - out.center[d]);
+        parallel_for(nT, [&](uint64_t m0, uint64_t m1) {
+            for (uint64_t m = m0; m < m1; m++) {
+                const SpherePair& sp = out.spheres[m];
+                SpherePairF& f = out.spheres_f[m];
+                for (int d = 0; d < 3; d++) { f.lc[d] = (float)(sp.lc[d] - out.center[d]); f.rc[d] = (float)(sp.rc[d] - out.center[d]); }
+                f.lr = (float)sp.lr; f.rr = (float)sp.rr;
+                BoxPairF& q = out.boxes_f[m];
+                if (m == 0) { std::memset(&q, 0, sizeof q); continue; }
+                const double* bx = &out.boxes[12 * m];
+                for (int d = 0; d < 3; d++) {
+                    q.l_lo[d] = down(bx[d] - out.center[d]); q.l_hi[d] = up(bx[3 + d] - out.center[d]);
+                    q.r_lo[d] = down(bx[6 + d] - out.center[d]); q.r_hi[d] = up(bx[9 + d] - out.center[d]);
+                }
             }
-        }
-        std::vector<double>().swap(out.boxes);
+        });
+        RawVec<double>().swap(out.boxes);
         // fp32 triangle shadows in leaf order (all products formed in fp64, then rounded once)
-        if (with_leaf_shadow) out.leaves_f.assign(nT, LeafF());
+        if (with_leaf_shadow) out.leaves_f.resize(nT);
         if (with_leaf_shadow) parallel_for(nT, [&](uint64_t p0, uint64_t p1) {
             for (uint64_t pos = p0; pos < p1; pos++) {
                 const LeafRecord& L = out.leaves[pos];

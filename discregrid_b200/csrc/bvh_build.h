@@ -17,9 +17,23 @@
 //     (V0,V1,V2,E01,E12,E02,F), so the sign needs a single 24-byte gather.
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace dgb {
+
+// std::vector whose resize() leaves trivially-constructible elements uninitialised: the big record arrays are written exactly once,
+// by parallel loops, and zero-filling them first (serially, touching every page) cost as much as filling them
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using RawVec = std::vector<T, DefaultInitAllocator<T>>;
 
 struct alignas(64) SpherePair {   // children of the internal node whose split position is the array index
     double lc[3], lr;             // left child sphere  (TriangleMeshDistance.h:105)
@@ -68,22 +82,22 @@ static_assert(sizeof(PseudoNormals) == 168, "PseudoNormals must be 168 bytes");
 
 struct HostBvh {
     uint64_t n_vertices = 0, n_triangles = 0;
-    std::vector<SpherePair> spheres;        // [T]  (index 0 unused)
-    std::vector<SpherePairF> spheres_f;     // [T]  fp32 shadow, relative to `center`
-    std::vector<BoxPairF> boxes_f;          // [T]  fp32 child boxes, relative to `center`, rounded outward
-    std::vector<double> boxes;              // [T][12] fp64 child boxes (build scratch)
+    RawVec<SpherePair> spheres;             // [T]  (index 0 unused, zeroed)
+    RawVec<SpherePairF> spheres_f;          // [T]  fp32 shadow, relative to `center`
+    RawVec<BoxPairF> boxes_f;               // [T]  fp32 child boxes, relative to `center`, rounded outward
+    RawVec<double> boxes;                   // [T][12] fp64 child boxes (build scratch)
     double center[3] = {0, 0, 0};           // bounding-box centre of the vertices
     double half_extent = 0;                 // max |v - center|_inf over the vertices
-    std::vector<LeafRecord> leaves;         // [T]
-    std::vector<LeafF> leaves_f;            // [T]  fp32 shadow, relative to `center`
-    std::vector<PseudoNormals> normals;     // [T]
+    RawVec<LeafRecord> leaves;              // [T]
+    RawVec<LeafF> leaves_f;                 // [T]  fp32 shadow, relative to `center`
+    RawVec<PseudoNormals> normals;          // [T]
     std::vector<int32_t> order;             // leaf position -> triangle id
     int max_depth = 0;                      // number of levels (root = 1)
     int flags = 0;                          // bit0: edge with a single triangle; bit1: edge with > 2 triangles
     // reference-numbered copies for dg_mesh_tree / dg_mesh_pseudonormals (diagnostics, built on demand)
     std::vector<double> V;                  // nV x 3
     std::vector<uint32_t> F;                // nT x 3
-    std::vector<double> pn_tri, pn_edge, pn_vert;
+    RawVec<double> pn_tri, pn_edge, pn_vert;
 };
 
 // Returns false (and leaves *err) on invalid input.

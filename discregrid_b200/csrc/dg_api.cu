@@ -292,12 +292,12 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     const auto t2 = std::chrono::steady_clock::now();
     m->upload_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
     // the device records are the product; the host copies of the big arrays are no longer needed
-    std::vector<SpherePair>().swap(m->host.spheres);
-    std::vector<SpherePairF>().swap(m->host.spheres_f);
-    std::vector<BoxPairF>().swap(m->host.boxes_f);
-    std::vector<LeafF>().swap(m->host.leaves_f);   // keep `order`, V, F, pseudonormals for diagnostics
-    std::vector<LeafRecord>().swap(m->host.leaves);
-    std::vector<PseudoNormals>().swap(m->host.normals);
+    RawVec<SpherePair>().swap(m->host.spheres);
+    RawVec<SpherePairF>().swap(m->host.spheres_f);
+    RawVec<BoxPairF>().swap(m->host.boxes_f);
+    RawVec<LeafF>().swap(m->host.leaves_f);        // keep `order`, V, F, pseudonormals for diagnostics
+    RawVec<LeafRecord>().swap(m->host.leaves);
+    RawVec<PseudoNormals>().swap(m->host.normals);
     *out = m;
     return DG_OK;
 }

@@ -1,5 +1,6 @@
 // See reduce_field.h.  Host C++ (threads), compiled with -ffp-contract=off like every translation unit of the library.
 #include "reduce_field.h"
+#include "sort_replay.h"
 
 #include <algorithm>
 #include <atomic>
@@ -97,138 +98,6 @@ void sample_sort(std::vector<KeyPos>& a, unsigned nt)
     a.swap(out);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------------
-// introsort as libstdc++ runs it, restated with an explicit range / depth so that the two sides of every split can go to
-// different threads.  `lt` is the only comparison (strict, on the key).
-inline bool lt(const KeyPos& x, const KeyPos& y) { return x.key < y.key; }
-
-// sift `v` down from `hole` in the max-heap a[0, len), then up again (the usual "move the hole to a leaf, then push" form)
-void heap_adjust(KeyPos* a, int64_t hole, int64_t len, KeyPos v)
-{
-    const int64_t top = hole;
-    int64_t child = hole;
-    while (child < (len - 1) / 2) {
-        child = 2 * (child + 1);
-        if (lt(a[child], a[child - 1])) child--;
-        a[hole] = a[child];
-        hole = child;
-    }
-    if ((len & 1) == 0 && child == (len - 2) / 2) {
-        child = 2 * (child + 1);
-        a[hole] = a[child - 1];
-        hole = child - 1;
-    }
-    int64_t parent = (hole - 1) / 2;
-    while (hole > top && lt(a[parent], v)) {
-        a[hole] = a[parent];
-        hole = parent;
-        parent = (hole - 1) / 2;
-    }
-    a[hole] = v;
-}
-
-std::atomic<uint64_t> g_heap_sorts{0};                      // how often the depth budget ran out (tests)
-
-void heap_sort(KeyPos* a, int64_t len)                       // make_heap + sort_heap: the depth-exhausted branch
-{
-    g_heap_sorts.fetch_add(1, std::memory_order_relaxed);
-    if (len < 2) return;
-    for (int64_t parent = (len - 2) / 2;; parent--) {
-        heap_adjust(a, parent, len, a[parent]);
-        if (parent == 0) break;
-    }
-    for (int64_t last = len - 1; last >= 1; last--) {
-        const KeyPos v = a[last];
-        a[last] = a[0];
-        heap_adjust(a, 0, last, v);
-    }
-}
-
-// median of a[1], a[mid], a[len-1] to a[0]; Hoare partition of a[1, len) around it; returns the cut
-int64_t split(KeyPos* a, int64_t len)
-{
-    KeyPos *x = a + 1, *y = a + len / 2, *z = a + len - 1, *m;
-    if (lt(*x, *y)) m = lt(*y, *z) ? y : (lt(*x, *z) ? z : x);
-    else m = lt(*x, *z) ? x : (lt(*y, *z) ? z : y);
-    std::swap(*a, *m);
-    KeyPos* lo = a + 1;
-    KeyPos* hi = a + len;
-    for (;;) {
-        while (lt(*lo, *a)) ++lo;
-        --hi;
-        while (lt(*a, *hi)) --hi;
-        if (!(lo < hi)) return lo - a;
-        std::swap(*lo, *hi);
-        ++lo;
-    }
-}
-
-void insertion_block(KeyPos* a, int64_t len)                 // what the final insertion pass does to one finished block
-{
-    for (int64_t i = 1; i < len; i++) {
-        const KeyPos v = a[i];
-        int64_t j = i;
-        while (j > 0 && lt(v, a[j - 1])) { a[j] = a[j - 1]; j--; }
-        a[j] = v;
-    }
-}
-
-struct SortJob { KeyPos* a; int64_t len; int depth; };
-
-class SortPool {
-public:
-    SortPool(unsigned nt, int64_t grain) : grain_(grain) { nt_ = nt < 1 ? 1 : nt; }
-    void run(KeyPos* a, int64_t n, int depth)
-    {
-        push({a, n, depth});
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < nt_; t++) th.emplace_back([this]() { work(); });
-        work();
-        for (auto& t : th) t.join();
-    }
-private:
-    void push(SortJob j)
-    {
-        { std::lock_guard<std::mutex> g(mu_); jobs_.push_back(j); pending_++; }
-        cv_.notify_one();
-    }
-    void work()
-    {
-        for (;;) {
-            SortJob j;
-            {
-                std::unique_lock<std::mutex> g(mu_);
-                cv_.wait(g, [this]() { return !jobs_.empty() || pending_ == 0; });
-                if (jobs_.empty()) return;
-                j = jobs_.back(); jobs_.pop_back();
-            }
-            loop(j.a, j.len, j.depth);
-            bool done;
-            { std::lock_guard<std::mutex> g(mu_); done = (--pending_ == 0); }
-            if (done) cv_.notify_all();
-        }
-    }
-    // the introsort loop on a[0, len): the right side of each split is handed on (or recursed into when small), the left side continues
-    void loop(KeyPos* a, int64_t len, int depth)
-    {
-        while (len > 16) {
-            if (depth == 0) { heap_sort(a, len); return; }
-            --depth;
-            const int64_t cut = split(a, len);
-            if (len - cut >= grain_ && nt_ > 1) push({a + cut, len - cut, depth});
-            else loop(a + cut, len - cut, depth);
-            len = cut;
-        }
-        insertion_block(a, len);
-    }
-    unsigned nt_;
-    int64_t grain_;
-    std::mutex mu_;
-    std::condition_variable cv_;
-    std::vector<SortJob> jobs_;
-    int64_t pending_ = 0;
-};
-
 }  // namespace
 
 uint64_t reduce_field_morton_key(const GridDev& g, uint32_t l)
@@ -246,46 +115,11 @@ uint64_t reduce_field_morton_key(const GridDev& g, uint32_t l)
 
 void replay_std_sort(KeyPos* a, uint64_t n, unsigned nt)
 {
-    if (n < 2) return;
-    int lg = 0;
-    for (uint64_t v = n; v > 1; v >>= 1) lg++;                    // floor(log2 n)
-    SortPool pool(n < (1u << 16) ? 1u : nt, 1 << 14);
-    pool.run(a, (int64_t)n, 2 * lg);
+    replay_sort(a, n, [](const KeyPos& x, const KeyPos& y) { return x.key < y.key; }, nt);
 }
 
-uint64_t replay_std_sort_heap_fallbacks() { return g_heap_sorts.load(); }
-
-bool replay_std_sort_matches()
-{
-    static const bool ok = []() {
-        // tie-heavy, ordered, organ-pipe and few-distinct inputs, sizes around the block threshold and large enough to use the threads
-        const uint64_t sizes[] = {0, 1, 2, 3, 15, 16, 17, 33, 100, 1000, 4097, 70000, 300000};
-        uint64_t rng = 0x9E3779B97F4A7C15ull;
-        auto next = [&rng]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
-        for (uint64_t n : sizes)
-            for (int kind = 0; kind < 6; kind++) {
-                std::vector<KeyPos> a(n);
-                for (uint64_t i = 0; i < n; i++) {
-                    uint64_t k;
-                    switch (kind) {
-                        case 0: k = next() % (n / 3 + 1); break;              // about three records per key
-                        case 1: k = next() & 7; break;                       // eight distinct keys
-                        case 2: k = i / 2; break;                            // sorted, pairs
-                        case 3: k = (n - i) / 2; break;                      // reversed, pairs
-                        case 4: k = i < n / 2 ? i : n - i; break;            // organ pipe
-                        default: k = next(); break;                          // distinct
-                    }
-                    a[i] = {k, (uint32_t)i};
-                }
-                std::vector<KeyPos> b(a);
-                std::sort(b.begin(), b.end(), [](const KeyPos& x, const KeyPos& y) { return x.key < y.key; });
-                replay_std_sort(a.data(), n, 4);
-                for (uint64_t i = 0; i < n; i++) if (a[i].pos != b[i].pos) return false;
-            }
-        return true;
-    }();
-    return ok;
-}
+bool replay_std_sort_matches() { return sort_replay_matches_std_sort(); }
+uint64_t replay_std_sort_heap_fallbacks() { return g_replay_heap_sorts.load(); }
 
 bool reduce_field_host(const GridDev& g, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
                        uint32_t* cell_map, uint64_t n_cells_grid, bool force_std_sort, ReduceStats& st, const char** err)

@@ -29,12 +29,7 @@ struct ReduceStats {
 bool reduce_field_host(const GridDev& g, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
                        uint32_t* cell_map, uint64_t n_cells_grid, bool force_std_sort, ReduceStats& st, const char** err);
 
-// The tie path.  std::sort on n (key, position) records ordered by key only is libstdc++'s introsort: median-of-3 quicksort down to
-// 16-element blocks with a 2*floor(log2 n) depth budget (heapsort beyond it), then one insertion-sort pass.  Every quicksort split
-// leaves two independent ranges, and the insertion pass never moves a record across a split (left part <= pivot <= right part), so
-// the same sequence of comparisons and swaps can run on many threads and ends in the same arrangement, ties included.
-// replay_std_sort does that; replay_std_sort_matches() checks it against std::sort itself on tie-heavy inputs once per process
-// (a different standard library may sort differently: then the library's own std::sort call is used, single-threaded).
+// The tie path: std::sort on (key, position) records ordered by key only, replayed on all threads (sort_replay.h).
 struct KeyPos { uint64_t key; uint32_t pos; };
 void replay_std_sort(KeyPos* a, uint64_t n, unsigned n_threads);
 bool replay_std_sort_matches();
