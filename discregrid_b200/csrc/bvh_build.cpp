@@ -24,24 +24,6 @@ inline P3 unit(P3 a) { const double l = len(a); return {a.x / l, a.y / l, a.z / 
 inline P3 crs(P3 a, P3 b) { return {a.y * b.z - a.z * b.y, -a.x * b.z + a.z * b.x, a.x * b.y - a.y * b.x}; }
 inline double at(const P3& p, int d) { return d == 0 ? p.x : (d == 1 ? p.y : p.z); }
 
-// static partition of [0, n) over the hardware threads; fn(begin, end)
-template <class Fn>
-void parallel_for(uint64_t n, Fn fn)
-{
-    unsigned nt = std::thread::hardware_concurrency();
-    if (nt == 0) nt = 1;
-    if (nt > 32) nt = 32;
-    if (n < 4096 || nt == 1) { fn(0, n); return; }
-    std::vector<std::thread> th;
-    const uint64_t per = (n + nt - 1) / nt;
-    for (unsigned k = 0; k < nt; k++) {
-        const uint64_t b = k * per, e = std::min(n, b + per);
-        if (b >= e) break;
-        th.emplace_back([=, &fn]() { fn(b, e); });
-    }
-    for (auto& t : th) t.join();
-}
-
 struct Builder {
     const P3* V;
     const uint32_t* F;

@@ -17,7 +17,9 @@
 //     (V0,V1,V2,E01,E12,E02,F), so the sign needs a single 24-byte gather.
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <memory>
+#include <thread>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -34,6 +36,25 @@ struct DefaultInitAllocator : std::allocator<T> {
     template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
 };
 template <class T> using RawVec = std::vector<T, DefaultInitAllocator<T>>;
+
+// static partition of [0, n) over the hardware threads; fn(begin, end)
+template <class Fn>
+void parallel_for(uint64_t n, Fn fn)
+{
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > 32) nt = 32;
+    if (n < 4096 || nt == 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    const uint64_t per = (n + nt - 1) / nt;
+    for (unsigned k = 0; k < nt; k++) {
+        const uint64_t b = k * per, e = std::min(n, b + per);
+        if (b >= e) break;
+        th.emplace_back([=, &fn]() { fn(b, e); });
+    }
+    for (auto& t : th) t.join();
+}
+
 
 struct alignas(64) SpherePair {   // children of the internal node whose split position is the array index
     double lc[3], lr;             // left child sphere  (TriangleMeshDistance.h:105)

@@ -274,11 +274,15 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     DG_CUDA_M(cudaMemcpy(m->d_leaves.p, m->host.leaves.data(), nT * sizeof(LeafRecord), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_normals.p, m->host.normals.data(), nT * sizeof(PseudoNormals), cudaMemcpyHostToDevice));
     {   // interleave the fp32 sphere pair and box pair of every internal node into one record
-        std::vector<float4> rec(nT * K1_NODEF_STRIDE, make_float4(0.f, 0.f, 0.f, 0.f));
-        for (uint64_t i = 0; i < nT; i++) {
-            std::memcpy(&rec[i * K1_NODEF_STRIDE], &m->host.spheres_f[i], sizeof(SpherePairF));
-            std::memcpy(&rec[i * K1_NODEF_STRIDE + 2], &m->host.boxes_f[i], sizeof(BoxPairF));
-        }
+        static_assert(K1_NODEF_STRIDE * sizeof(float4) >= sizeof(SpherePairF) + sizeof(BoxPairF), "node record too small");
+        RawVec<float4> rec(nT * K1_NODEF_STRIDE);
+        parallel_for(nT, [&](uint64_t i0, uint64_t i1) {
+            for (uint64_t i = i0; i < i1; i++) {
+                std::memset(&rec[i * K1_NODEF_STRIDE], 0, K1_NODEF_STRIDE * sizeof(float4));
+                std::memcpy(&rec[i * K1_NODEF_STRIDE], &m->host.spheres_f[i], sizeof(SpherePairF));
+                std::memcpy(&rec[i * K1_NODEF_STRIDE + 2], &m->host.boxes_f[i], sizeof(BoxPairF));
+            }
+        });
         DG_CUDA_M(cudaMemcpy(m->d_nodes_f.p, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice));
     }
     m->dev.nodes_f = m->d_nodes_f.p;

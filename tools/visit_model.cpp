@@ -4,7 +4,7 @@
 //   B  the kernel's rule: spheres + "hopeless" box skip against the running best (k1_sdf.cu)
 //   C  B + an external pruning bound U = d(brick centre) + |x - centre| (one extra query per 4x4x2 brick)
 //   D  B + the ideal bound U = d(x) (1 + 1e-6): the least work this tree allows
-// build: g++ -O2 -fopenmp -I discregrid_b200/csrc tools/visit_model.cpp discregrid_b200/csrc/bvh_build.cpp -o /tmp/vm/visit_model
+// build: g++ -O2 -fopenmp -ffp-contract=off -I discregrid_b200/csrc tools/visit_model.cpp discregrid_b200/csrc/bvh_build.cpp discregrid_b200/csrc/sort_replay.cpp -o visit_model -lpthread
 // usage: visit_model mesh.V mesh.F resolution [brick_stride]
 #include <algorithm>
 #include <cfloat>
