@@ -196,14 +196,22 @@ def interleaved_node_slots(desc, world, l_begin, l_end):
 
 
 class InterleavedSdfSampler:
-    def __init__(self, md, desc, rank, world):
+    """splits > 1 (experimental, default 1): the deal is made over world * splits parts and rank r takes parts r*splits .. r*splits +
+    splits - 1, one launch each on its own stream -- the launches' ~2 ms tails overlap as they do for the node-id chunks, and the
+    rank's slots stay contiguous, so the exchange is still ONE all-gather.  world * splits <= 16."""
+
+    def __init__(self, md, desc, rank, world, splits=1):
         import ctypes as C
         from . import _capi as capi
-        self.md, self.desc, self.rank, self.world = md, desc, rank, world
+        if splits < 1 or world * splits > 16:
+            raise ValueError("world * splits must be in 1..16")
+        self.md, self.desc, self.rank, self.world, self.splits = md, desc, rank, world, splits
+        self.parts = world * splits
         n = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(n)))
-        se = C.c_uint64(); capi.check(capi.lib.dg_interleaved_slot_elems(C.byref(desc), world, C.byref(se)))
-        self.n, self.slot = n.value, se.value
+        se = C.c_uint64(); capi.check(capi.lib.dg_interleaved_slot_elems(C.byref(desc), self.parts, C.byref(se)))
+        self.n, self.slot = n.value, se.value              # slot = one PART's slot; a rank owns `splits` consecutive ones
         self.slots = None
+        self.streams = None
 
     class _Sh:                                             # the attribute bench.py reads from every sampler
         def __init__(self, padded):
@@ -216,25 +224,33 @@ class InterleavedSdfSampler:
     def _buffers(self, full):
         import torch
         if self.slots is None:
-            self.slots = torch.empty(self.world * self.slot, dtype=full.dtype, device=full.device)
+            self.slots = torch.empty(self.parts * self.slot, dtype=full.dtype, device=full.device)
+            self.streams = [torch.cuda.Stream() for _ in range(self.splits)] if self.splits > 1 else []
 
     def launch(self, full, sign=1.0):
         import ctypes as C
         import torch
         from . import _capi as capi
         self._buffers(full)
-        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        capi.check(capi.lib.dg_sample_sdf_interleaved_device(self.md.handle, C.byref(self.desc), sign, self.rank, self.world,
-                                                             C.c_void_p(self.slots.data_ptr() + 8 * self.rank * self.slot), sp))
-        return 1
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(cur)
+        for k in range(self.splits):
+            part = self.rank * self.splits + k
+            st = self.streams[k] if self.streams else cur
+            capi.check(capi.lib.dg_sample_sdf_interleaved_device(self.md.handle, C.byref(self.desc), sign, part, self.parts,
+                                                                 C.c_void_p(self.slots.data_ptr() + 8 * part * self.slot), C.c_void_p(st.cuda_stream)))
+        for st in self.streams:
+            cur.wait_stream(st)
+        return self.splits
 
     def step(self, full, sign=1.0, group=None):
         import ctypes as C
         import torch
         from . import _capi as capi
         self.launch(full, sign)
-        allgather_slots(self.slots, self.slot, self.rank, self.world, group)
+        allgather_slots(self.slots, self.slot * self.splits, self.rank, self.world, group)
         sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        capi.check(capi.lib.dg_interleaved_unpack_device(C.byref(self.desc), self.world, C.c_void_p(self.slots.data_ptr()),
+        capi.check(capi.lib.dg_interleaved_unpack_device(C.byref(self.desc), self.parts, C.c_void_p(self.slots.data_ptr()),
                                                          C.c_void_p(full.data_ptr()), sp))
-        return 2
+        return self.splits + 1

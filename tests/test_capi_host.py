@@ -278,9 +278,11 @@ def test_interleaved_layout_is_a_bijection_into_the_slots(dg, res, world):
     assert capi.lib.dg_interleaved_node_slots(C.byref(desc), 17, 0, n, None, None) == capi.DG_ERR_INVALID
 
 
-def test_allgather_slots_gloo_world2(tmp_path):
-    """N > 1 host logic of the interleaved sharding on CPU: two gloo ranks fill their slots with f(node id) at the positions the host
-    layout names, exchange them with the sampler's own collective call, and unpack through the same layout."""
+@pytest.mark.parametrize("splits", [1, 2])
+def test_allgather_slots_gloo_world2(tmp_path, splits):
+    """N > 1 host logic of the interleaved sharding on CPU: two gloo ranks fill the slots of their parts (splits consecutive parts per
+    rank) with f(node id) at the positions the host layout names, exchange them with the sampler's own collective call, and unpack
+    through the same layout."""
     script = tmp_path / "w.py"
     script.write_text(f'''
 import os, sys, ctypes as C, numpy as np, torch, torch.distributed as dist
@@ -290,21 +292,24 @@ from discregrid_b200 import _capi as capi
 from discregrid_b200.distributed import allgather_slots, interleaved_node_slots
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
+splits = {splits}
+parts = world * splits
 desc = dg.grid_desc([0, 0, 0], [1, 2, 3], (9, 5, 7))
 n = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(n))); n = n.value
-se = C.c_uint64(); capi.check(capi.lib.dg_interleaved_slot_elems(C.byref(desc), world, C.byref(se))); se = se.value
-part, pos = interleaved_node_slots(desc, world, 0, n)
+se = C.c_uint64(); capi.check(capi.lib.dg_interleaved_slot_elems(C.byref(desc), parts, C.byref(se))); se = se.value
+part, pos = interleaved_node_slots(desc, parts, 0, n)
 f = np.arange(n, dtype=np.float64) * 0.25 - 3.0
-slots = torch.full((world * se,), -1.0, dtype=torch.float64)
-mine = part == rank
-slots[rank * se + torch.from_numpy(pos[mine].astype(np.int64))] = torch.from_numpy(f[mine])
-allgather_slots(slots, se, rank, world)
+slots = torch.full((parts * se,), -1.0, dtype=torch.float64)
+mine = (part // splits) == rank                          # rank r owns parts r*splits .. r*splits + splits - 1
+slots[torch.from_numpy(part[mine].astype(np.int64) * se + pos[mine].astype(np.int64))] = torch.from_numpy(f[mine])
+allgather_slots(slots, se * splits, rank, world)
 got = slots[torch.from_numpy(part.astype(np.int64) * se + pos.astype(np.int64))].numpy()
 assert np.array_equal(got, f), (rank, np.nonzero(got != f)[0][:5])
 dist.barrier()
 if rank == 0: print("SLOTS_OK")
 ''')
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617")
+    port = str(29617 + splits)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=300)
+                        "--master-port", port, str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "SLOTS_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

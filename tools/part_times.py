@@ -62,5 +62,21 @@ def inter_of(r):
     return lambda: capi.check(capi.lib.dg_sample_sdf_interleaved_device(md.handle, C.byref(desc), 1.0, r, world, C.c_void_p(slots.data_ptr() + 8 * r * se), sp))
 ti = [timed(inter_of(r)) for r in range(world)]
 print("interleaved ", " ".join(f"{t:6.2f}" for t in ti), f"| max {max(ti):.2f} mean {np.mean(ti):.2f}")
+# interleaved over 2 * world parts, two launches per rank on two streams (InterleavedSdfSampler(splits=2))
+if 2 * world <= 16:
+    se2 = C.c_uint64(); capi.check(capi.lib.dg_interleaved_slot_elems(C.byref(desc), 2 * world, C.byref(se2))); se2 = se2.value
+    slots2 = torch.empty(2 * world * se2, dtype=torch.float64, device="cuda")
+    def inter2_of(r):
+        def f():
+            cur = torch.cuda.current_stream()
+            for st in streams: st.wait_stream(cur)
+            for k in range(2):
+                part = 2 * r + k
+                capi.check(capi.lib.dg_sample_sdf_interleaved_device(md.handle, C.byref(desc), 1.0, part, 2 * world, C.c_void_p(slots2.data_ptr() + 8 * part * se2),
+                                                                     C.c_void_p(streams[k].cuda_stream)))
+            for st in streams: cur.wait_stream(st)
+        return f
+    t2 = [timed(inter2_of(r)) for r in range(world)]
+    print("interleaved2", " ".join(f"{t:6.2f}" for t in t2), f"| max {max(t2):.2f} mean {np.mean(t2):.2f}")
 tu = timed(lambda: capi.check(capi.lib.dg_interleaved_unpack_device(C.byref(desc), world, C.c_void_p(slots.data_ptr()), C.c_void_p(full.data_ptr()), sp)))
 print(f"unpack {tu:.3f} ms; slot {se} elems ({8 * se * world / 1e6:.1f} MB gathered vs {8 * n / 1e6:.1f} MB of nodes)")
