@@ -96,6 +96,32 @@ class ShardedSdfSampler:
         return n
 
 
+class ShardedDensityMap:
+    """GenerateDensityMap's node loop (K3, dg_density_map_device) for one rank of a one-process-per-GPU job: the SDF field is
+    replicated (every rank holds the gathered coefficients anyway), the nodes are dealt in `rows` round-robin node-id chunks per rank
+    -- many small chunks, because only the nodes in the surface band take the 4096-point branch -- and the density coefficients are
+    exchanged exactly like the SDF's: one in-place all-gather per row ("density map = same all-gather as K1")."""
+
+    def __init__(self, field_handle, n_nodes, rank, world, rows=8):
+        self.fh, self.rank, self.world = field_handle, rank, world
+        self.sh = make_sharding(n_nodes, world, rows)
+        self.chunks = [(j, b, e) for (j, b, e) in self.sh.chunks_of(rank) if e > b]
+
+    def launch(self, out, h, rho0, no_reduction=False):
+        import ctypes as C
+        import torch
+        from . import _capi as capi
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for (_j, b, e) in self.chunks:
+            capi.check(capi.lib.dg_density_map_device(self.fh, h, rho0, int(no_reduction), b, e, C.c_void_p(out.data_ptr() + 8 * b), sp))
+        return len(self.chunks)
+
+    def step(self, out, h, rho0, no_reduction=False, group=None):
+        n = self.launch(out, h, rho0, no_reduction)
+        allgather_rows(out, self.sh, group)
+        return n
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 # Slab sharding (bench.py --sharding slab; the node-id chunks above are the default: measured 10.5 vs 10.1 ms per step at 8 GPUs).  Each rank samples whole slow-plane pairs of each of the four node arrays in
 # ONE launch (dg_sample_sdf_slab_device): z-slabs of the vertex and x-edge nodes, x-slabs of the y-edge nodes, y-slabs of the z-edge

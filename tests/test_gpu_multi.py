@@ -53,6 +53,19 @@ it.step(full3)
 torch.cuda.synchronize()
 got3 = full3.cpu().numpy()
 assert np.array_equal(got3.view(np.uint64), single.view(np.uint64)), f"rank {rank}: interleaved != single-GPU"
+# density map (K3) over node-id chunks of the replicated SDF field + the same all-gather
+from discregrid_b200.distributed import ShardedDensityMap
+fh = C.c_void_p()
+capi.check(capi.lib.dg_field_create_device(C.byref(desc), C.c_void_p(full3.data_ptr()), n, sp, C.byref(fh)))
+dm = ShardedDensityMap(fh, n, rank, world, rows=3)
+dens = torch.full((dm.sh.padded,), float("nan"), dtype=torch.float64, device="cuda")
+dm.step(dens, 0.08, 1000.0)
+one = torch.empty(n, dtype=torch.float64, device="cuda")
+capi.check(capi.lib.dg_density_map_device(fh, 0.08, 1000.0, 0, 0, n, C.c_void_p(one.data_ptr()), sp))
+torch.cuda.synchronize()
+assert torch.equal(dens[:n].view(torch.int64), one.view(torch.int64)), f"rank {rank}: sharded density map != single launch"
+assert bool(((one > 0) & (one < 1e300)).any()) and bool((one == 0).any())
+capi.lib.dg_field_destroy(fh)
 dist.barrier()
 if rank == 0: print("MULTI_OK", world)
 dist.destroy_process_group()
