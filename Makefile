@@ -24,13 +24,17 @@ CPPBIN   := build/bin
 CPPFLAGS := -std=c++11 -O2 -ffp-contract=off -I$(EIGEN3_INCLUDE_DIR) -Icpp/include -Iinclude
 CPPLINK  := -Ldiscregrid_b200/lib -ldiscregrid_b200 -Wl,-rpath,'$$ORIGIN/../../discregrid_b200/lib'
 CPPHDRS  := $(wildcard cpp/include/Discregrid/* cpp/include/Discregrid/*/*) include/discregrid_b200.h
-cpp: $(CPPBIN)/GenerateSDF $(CPPBIN)/GenerateDensityMap $(CPPBIN)/DiscreteFieldToBitmap $(CPPBIN)/facade_check $(CPPBIN)/bvh_host_check $(CPPBIN)/reduce_facade_check $(CPPBIN)/sort_replay_check
+cpp: $(CPPBIN)/GenerateSDF $(CPPBIN)/GenerateDensityMap $(CPPBIN)/DiscreteFieldToBitmap $(CPPBIN)/facade_check $(CPPBIN)/bvh_host_check $(CPPBIN)/reduce_facade_check $(CPPBIN)/sort_replay_check $(CPPBIN)/fast_div_check
 $(CPPBIN)/DiscreteFieldToBitmap: cpp/cmd/discrete_field_to_bitmap.cpp $(CPPHDRS) $(LIB)
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK)
 $(CPPBIN)/bvh_host_check: tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp $(SRC)/sort_replay.h $(SRC)/bvh_build.h
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp -o $@ -lpthread
+# test binary: the reciprocal-based exact division of fast_div.h against '/' (brute force)
+$(CPPBIN)/fast_div_check: tests/cpp/fast_div_check.cpp $(SRC)/fast_div.h $(SRC)/dg_device.cuh
+	@mkdir -p $(CPPBIN)
+	$(HOSTCXX) $(CXXFLAGS) -I$(SRC) tests/cpp/fast_div_check.cpp -o $@
 # test binary: the threaded std::sort replay of reduce_field.cpp against std::sort (ties, depth exhaustion)
 $(CPPBIN)/sort_replay_check: tests/cpp/sort_replay_check.cpp $(SRC)/reduce_field.cpp $(SRC)/sort_replay.cpp $(SRC)/sort_replay.h $(SRC)/reduce_field.h $(SRC)/dg_device.cuh
 	@mkdir -p $(CPPBIN)

@@ -2,6 +2,7 @@
 // reference's x86-64 build (no FMA), because these values feed bit-exact device comparisons.
 #include "bvh_build.h"
 #include "sort_replay.h"
+#include "fast_div.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -105,7 +106,7 @@ struct Builder {
 
 }  // namespace
 
-bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err, bool with_leaf_shadow)
+bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err, bool with_leaf_shadow, bool with_recips)
 {
     if (!Vd || !F || nT == 0 || nV == 0) { *err = "empty triangle list or vertex list"; return false; }
     if (nT >= (1ull << 25) || nV > (uint64_t)0x7fffffff) { *err = "mesh too large (< 2^25 triangles; int32 vertex indices as in the reference)"; return false; }
@@ -224,6 +225,18 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
             for (int k = 0; k < 7; k++) { N.n[k][0] = src[k].x; N.n[k][1] = src[k].y; N.n[k][2] = src[k].z; }
         }
     });
+
+    if (with_recips) {
+        out.recips.resize(nT);
+        parallel_for(nT, [&](uint64_t p0, uint64_t p1) {
+            for (uint64_t pos = p0; pos < p1; pos++) {
+                const LeafRecord& L = out.leaves[pos];
+                LeafRecip& R = out.recips[pos];
+                R.inv_a00 = 1.0 / L.a00; R.inv_a11 = 1.0 / L.a11; R.inv_denom = 1.0 / L.denom;
+                R.regular = (in_fast_div_range(L.a00) && in_fast_div_range(L.a11) && in_fast_div_range(L.denom)) ? 1u : 0u;   // false for NaN / 0 / inf
+            }
+        });
+    }
 
     // ---- fp32 shadow of the sphere pairs (filter only), relative to the bounding-box centre
     {

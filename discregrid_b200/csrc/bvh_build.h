@@ -98,6 +98,12 @@ struct alignas(64) LeafF {
 };
 static_assert(sizeof(LeafF) == 64, "LeafF must be 64 bytes");
 
+// Correctly rounded reciprocals of the three per-triangle divisors of the leaf test (a00, a11, a00 - 2 a01 + a11), for the
+// K1_FAST_DIV build of the kernel (fast_div.h).  regular = 1 when all three divisors are finite and inside [2^-300, 2^300];
+// otherwise the kernel takes the plain division for this triangle.
+struct alignas(32) LeafRecip { double inv_a00, inv_a11, inv_denom; uint64_t regular; };
+static_assert(sizeof(LeafRecip) == 32, "LeafRecip must be 32 bytes");
+
 struct PseudoNormals { double n[7][3]; };   // V0 V1 V2 E01 E12 E02 F
 static_assert(sizeof(PseudoNormals) == 168, "PseudoNormals must be 168 bytes");
 
@@ -112,6 +118,7 @@ struct HostBvh {
     RawVec<LeafRecord> leaves;              // [T]
     RawVec<LeafF> leaves_f;                 // [T]  fp32 shadow, relative to `center`
     RawVec<PseudoNormals> normals;          // [T]
+    RawVec<LeafRecip> recips;               // [T]  only when asked for (K1_FAST_DIV)
     std::vector<int32_t> order;             // leaf position -> triangle id
     int max_depth = 0;                      // number of levels (root = 1)
     int flags = 0;                          // bit0: edge with a single triangle; bit1: edge with > 2 triangles
@@ -123,7 +130,7 @@ struct HostBvh {
 
 // Returns false (and leaves *err) on invalid input.
 bool build_host_bvh(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err,
-                    bool with_leaf_shadow = false);
+                    bool with_leaf_shadow = false, bool with_recips = false);
 
 // Re-expresses the implicit tree in the reference's explicit pre-order numbering (diagnostics only).
 void export_reference_tree(const HostBvh& bvh, double* spheres /*(2T-1) x 8*/, int32_t* kids /*(2T-1) x 2*/);

@@ -128,6 +128,9 @@ struct dg_mesh {
     DevBuf<PseudoNormals> d_normals;
     DevBuf<float4> d_nodes_f;
     DevBuf<LeafF> d_leaves_f;
+#if K1_FAST_DIV
+    DevBuf<LeafRecip> d_recips;
+#endif
     DeviceBvh dev;
     int device = 0;
     uint64_t build_us = 0, upload_us = 0;
@@ -253,7 +256,7 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     const auto t0 = std::chrono::steady_clock::now();
     const char* why = "";
     try {
-        if (!build_host_bvh(V, nV, F, nT, m->host, &why, K1_LEAF_FILTER != 0)) { delete m; return fail(DG_ERR_INVALID, "dg_mesh_create: %s", why); }
+        if (!build_host_bvh(V, nV, F, nT, m->host, &why, K1_LEAF_FILTER != 0, K1_FAST_DIV != 0)) { delete m; return fail(DG_ERR_INVALID, "dg_mesh_create: %s", why); }
     } catch (const std::bad_alloc&) { delete m; return fail(DG_ERR_NOMEM, "dg_mesh_create: out of host memory"); }
     const auto t1 = std::chrono::steady_clock::now();
     m->build_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
@@ -269,6 +272,12 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     DG_CUDA_M(m->d_leaves_f.alloc(nT));
     DG_CUDA_M(cudaMemcpy(m->d_leaves_f.p, m->host.leaves_f.data(), nT * sizeof(LeafF), cudaMemcpyHostToDevice));
     m->dev.leaves_f = m->d_leaves_f.p;
+#endif
+#if K1_FAST_DIV
+    DG_CUDA_M(m->d_recips.alloc(nT));
+    DG_CUDA_M(cudaMemcpy(m->d_recips.p, m->host.recips.data(), nT * sizeof(LeafRecip), cudaMemcpyHostToDevice));
+    m->dev.recips = m->d_recips.p;
+    RawVec<LeafRecip>().swap(m->host.recips);
 #endif
     DG_CUDA_M(cudaMemcpy(m->d_spheres.p, m->host.spheres.data(), nT * sizeof(SpherePair), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_leaves.p, m->host.leaves.data(), nT * sizeof(LeafRecord), cudaMemcpyHostToDevice));

@@ -25,6 +25,7 @@
 #include "dg_device.cuh"
 #include "bvh_build.h"
 #include "k1_sdf.h"
+#include "fast_div.h"
 
 #include <cfloat>
 #include <mutex>
@@ -52,8 +53,11 @@ __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterp
 // NaNs fall the same way) producing the outcome code, and the arithmetic is done ONCE for the whole warp: one
 // division (E01: -b0/a00, E02: -b1/a11, E12: numer/denom), one quadratic form (E12 and F), selected per lane.
 // Every value a lane finally uses is produced by exactly the reference's operations in the reference's order.
-__device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec, double px, double py, double pz,
-                                            double& s_out, double& t_out, int& ent_out)
+__device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec,
+#if K1_FAST_DIV
+                                            const LeafRecip* __restrict__ recip,
+#endif
+                                            double px, double py, double pz, double& s_out, double& t_out, int& ent_out)
 {
     const double* r = reinterpret_cast<const double*>(rec);
     const double2 q0 = ldg2(r + 0), q1 = ldg2(r + 2), q2 = ldg2(r + 4), q3 = ldg2(r + 6);
@@ -110,7 +114,16 @@ __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec, 
     if (ent >= 3 && ent <= 5)
 #endif
     {
+#if K1_FAST_DIV
+        // den is one of three per-triangle constants: same IEEE quotient from its precomputed reciprocal (fast_div.h)
+        const double2 y01 = ldg2(reinterpret_cast<const double*>(recip)), y2r = ldg2(reinterpret_cast<const double*>(recip) + 2);
+        const double y = (ent == 3) ? y01.x : ((ent == 5) ? y01.y : ((ent == 4) ? y2r.x : 1.0));
+        q = div_by_known_reciprocal(num, den, y);
+        const bool needs = (ent >= 3 && ent <= 5);
+        if (needs && !(__double_as_longlong(y2r.y) != 0ll && in_fast_div_range(num))) q = num / den;   // irregular triangle or operand: rare, usually no lane
+#else
         q = num / den;
+#endif
     }
     DG_PIN_D(q);
     // ---- (s, t) of the nearest point
@@ -198,6 +211,9 @@ struct MeshDev {
     const float4* nodes_f;                 // [T][K1_NODEF_STRIDE]: sphere pair (2 float4) + box pair (3 float4)
     const LeafF* leaves_f;                 // [T] fp32 triangle shadows
     const LeafRecord* leaves;
+#if K1_FAST_DIV
+    const LeafRecip* recips;
+#endif
     double cx, cy, cz;
     float half_extent;
     int n_tri;
@@ -461,7 +477,11 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
         } else {
             if (state == (K1_LEAF_FILTER ? LEAFX : LEAF)) {                     // leaf (:517-534)
                 double s, t; int ent;
+                #if K1_FAST_DIV
+                const double d2 = tri_dist2(M.leaves + b, M.recips + b, px, py, pz, s, t, ent);
+#else
                 const double d2 = tri_dist2(M.leaves + b, px, py, pz, s, t, ent);
+#endif
                 if (d2 < best_sq) {
                     best = sqrt(d2);
                     best_sq = best * best;
@@ -579,7 +599,14 @@ __global__ void fma_probe_kernel(double a, double b, double c, double* out) { ou
 }  // namespace
 
 static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)); }
-static inline MeshDev mesh_dev(const DeviceBvh& m) { return MeshDev{m.spheres, m.nodes_f, m.leaves_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri}; }
+static inline MeshDev mesh_dev(const DeviceBvh& m)
+{
+#if K1_FAST_DIV
+    return MeshDev{m.spheres, m.nodes_f, m.leaves_f, m.leaves, m.recips, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri};
+#else
+    return MeshDev{m.spheres, m.nodes_f, m.leaves_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri};
+#endif
+}
 
 // The opt-in limit for dynamic shared memory is a per-function attribute: keep it at the maximum any live mesh has needed
 // (per device; meshes with different tree depths can coexist).

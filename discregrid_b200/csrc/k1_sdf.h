@@ -89,11 +89,21 @@ struct K1Work {
     int compact;                   // 0: out[l - l_begin]; 1: interleaved exchange slot (see k1_launch_sample_interleaved)
 };
 
+// K1_FAST_DIV 1: the one division of the leaf test (by a per-triangle constant) is replaced by a multiplication with the constant's
+// precomputed reciprocal + four FMAs that land on the same IEEE quotient (fast_div.h; ~68 -> ~8 instructions of a 253-instruction
+// leaf test).  Needs 32 more bytes per triangle.  Off until measured on the GPU.
+#ifndef K1_FAST_DIV
+#define K1_FAST_DIV 0
+#endif
+
 struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once by dg_mesh_create
     const SpherePair* spheres = nullptr;
     const LeafRecord* leaves = nullptr;
     const PseudoNormals* normals = nullptr;
     const LeafF* leaves_f = nullptr;            // fp32 triangle shadows (leaf filter)
+#if K1_FAST_DIV
+    const LeafRecip* recips = nullptr;          // reciprocals of the leaf test's divisors
+#endif
     const float4* nodes_f = nullptr;          // fp32 record per internal node, K1_NODEF_STRIDE float4s: SpherePairF (2) + BoxPairF (3) [+ pad]
     double ctr[3] = {0, 0, 0};
     float half_extent = 0.f;

@@ -123,3 +123,13 @@ def test_reference_meshes(dg, orc, name, tmp_path):
         pytest.skip("mesh not staged")
     mesh = dg.TriangleMesh(path)
     check_against_oracle(orc, run_builder(tmp_path, mesh.vertices, mesh.faces), mesh.vertices, mesh.faces)
+
+
+def test_division_by_known_reciprocal_is_the_ieee_quotient():
+    """tests/cpp/fast_div_check.cpp: discregrid_b200/csrc/fast_div.h (the K1_FAST_DIV build's replacement of the leaf test's division)
+    gives num / den bit for bit on 3e7 operand pairs, including significands next to 1 and 2 and exactly divisible ones"""
+    exe = os.path.join(ROOT, "build", "bin", "fast_div_check")
+    if not os.path.exists(exe):
+        pytest.skip("build/bin/fast_div_check not built (make cpp)")
+    r = subprocess.run([exe, "30000000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
