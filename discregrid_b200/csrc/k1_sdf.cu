@@ -321,6 +321,15 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
     int b = 0, e = n_tri, depth = 0, sp = 0;
     int state = alive ? ((n_tri == 1) ? LEAF : NODE) : DONE;
     for (;;) {
+#if K1_VOTE_REDUX && !K1_LEAF_FILTER && !K1_NODE_REPEAT
+        // one warp-wide integer sum carries the three lane counts (8 bits each: NODE | LEAF << 8 | POP << 16; DONE adds nothing)
+        const unsigned tally = __reduce_add_sync(0xffffffffu, (state < DONE) ? (1u << (8 * state)) : 0u);
+        if (tally == 0u) break;                                                // every lane DONE
+        const int w_node = K1_NODE_WEIGHT * (int)(tally & 0xffu), w_pop = K1_POP_WEIGHT * (int)(tally >> 16);
+        const int w_leaff = 0;
+        const int w_leafx = K1_LEAF_WEIGHT * (int)((tally >> 8) & 0xffu);
+        const unsigned bit0 = 0u, bit1 = 0u, bit2 = 0u; (void)bit0; (void)bit1; (void)bit2;
+#else
         // three ballots carry the 3-bit state of all 32 lanes
         const unsigned bit0 = __ballot_sync(0xffffffffu, state & 1), bit1 = __ballot_sync(0xffffffffu, state & 2);
         const unsigned bit2 = K1_LEAF_FILTER ? __ballot_sync(0xffffffffu, state & 4) : 0u;
@@ -328,6 +337,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
         const int w_node = K1_NODE_WEIGHT * __popc(~(bit0 | bit1 | bit2)), w_pop = K1_POP_WEIGHT * __popc(~bit0 & bit1);
         const int w_leaff = K1_LEAF_FILTER ? K1_LEAFF_WEIGHT * __popc(bit0 & ~bit1) : 0;
         const int w_leafx = K1_LEAF_WEIGHT * __popc(K1_LEAF_FILTER ? bit2 : (bit0 & ~bit1));
+#endif
         const int w_max = max(max(w_node, w_pop), max(w_leaff, w_leafx));
         if (w_pop == w_max) {
             if (state == POP) {

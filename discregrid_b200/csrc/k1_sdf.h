@@ -96,6 +96,12 @@ struct K1Work {
 #define K1_FAST_DIV 0
 #endif
 
+// K1_VOTE_REDUX 1: the phase vote reads the three lane counts from ONE warp-wide integer sum (redux.sync) instead of two ballots +
+// three popcounts (the loop head is ~19 % of the issued instructions).  Off until measured on the GPU.
+#ifndef K1_VOTE_REDUX
+#define K1_VOTE_REDUX 0
+#endif
+
 struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once by dg_mesh_create
     const SpherePair* spheres = nullptr;
     const LeafRecord* leaves = nullptr;
