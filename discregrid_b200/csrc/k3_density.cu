@@ -19,6 +19,13 @@
 // adjacent points at every step, i.e. one to three cells, so the 256-byte coefficient blocks are L1 hits.
 #include "dg_device.cuh"
 #include "k3_density.h"
+#include "fast_div.h"
+
+// K3_FAST_DIV 1: gamma's d / h (one fp64 division per quadrature point, ~33 of ~400 instructions) through the reciprocal of h.
+// Off until measured on the GPU.
+#ifndef K3_FAST_DIV
+#define K3_FAST_DIV 0
+#endif
 
 #include <cfloat>
 #include <climits>
@@ -49,6 +56,9 @@ struct QuadParams {
     double off[16];      // c0*xi + c1 per axis point (identical on the three axes: the domain is a cube)
     double w[16];
     double h, two_h, six_h_neg, rho0, c0prod, cell_diag;
+#if K3_FAST_DIV
+    double inv_h;        // RN(1/h)
+#endif
 };
 
 // value-only interpolate (cubic_lagrange_discrete_grid.cpp:977-1023) reading the packed block through L1
@@ -122,6 +132,9 @@ density_map_kernel(FieldDev f, QuadParams qp, const double* __restrict__ Wtab, i
     const double dist = interp_value(f, x, y, z);                   // main.cpp:98
     if (dist > qp.two_h) { out[idx] = 0.0; return; }
     double res = 0.0;
+#if K3_FAST_DIV
+    const bool fast_h = in_fast_div_range(qp.h);
+#endif
     for (int i = 0; i < 16; i++) {
         const double wi = qp.w[i], sx = x + qp.off[i];
         for (int j = 0; j < 16; j++) {
@@ -133,7 +146,15 @@ density_map_kernel(FieldDev f, QuadParams qp, const double* __restrict__ Wtab, i
                 if (W == 0.0) continue;                              // contributes exactly +0 (see header)
                 const double wijk = wij * qp.w[k];
                 const double d = interp_value(f, sx, sy, z + qp.off[k]);
+#if K3_FAST_DIV
+                // d / h with h a launch constant: the same IEEE quotient from RN(1/h) and four FMAs (fast_div.h); plain division
+                // when d is zero or outside the range where nothing can over- or underflow
+                double dq = div_by_known_reciprocal(d, qp.h, qp.inv_h);
+                if (!(fast_h && in_fast_div_range(d))) dq = d / qp.h;
+                const double gam = (d > qp.h) ? 0.0 : 1.0 - dq;         // main.cpp:86-93
+#else
                 const double gam = (d > qp.h) ? 0.0 : 1.0 - d / qp.h;   // main.cpp:86-93
+#endif
                 res = res + wijk * (gam * W);                        // gauss_quadrature.cpp:5954
             }
         }
@@ -156,6 +177,9 @@ cudaError_t k3_launch_density(const FieldDev& f, double h, double rho0, int no_r
     const double c0 = 0.5 * (hi - lo), c1 = 0.5 * (lo + hi);
     for (int i = 0; i < 16; i++) { qp.off[i] = c0 * GA16[i] + c1; qp.w[i] = GW16[i]; }
     qp.h = h; qp.two_h = 2.0 * h; qp.six_h_neg = -6.0 * h; qp.rho0 = rho0;
+#if K3_FAST_DIV
+    qp.inv_h = 1.0 / h;
+#endif
     qp.c0prod = c0 * c0 * c0;                                        // Eigen prod(): (c0*c0)*c0
     // cell_diag = cellSize().norm(); Eigen >= 3.3 reduces a Vector3d as (a0 + a1) + a2 (main.cpp:117)
     qp.cell_diag = std::sqrt((f.g.cell[0] * f.g.cell[0] + f.g.cell[1] * f.g.cell[1]) + f.g.cell[2] * f.g.cell[2]);
