@@ -77,6 +77,9 @@ run(os.path.join(REF_BIN, "DiscreteFieldToBitmap"), "-s", "48", "-p", "yx", "-f"
 
 # a real mesh end to end through the reference tool (the mesh itself is not committed: GPU-side tests find it under oracle/_ref/resources)
 run(os.path.join(REF_BIN, "GenerateSDF"), "-r", "12 12 12", "-o", os.path.join(HERE, "ref_bunny_12.cdf"), os.path.join(REF_RES, "bunny.obj"))
+run(os.path.join(REF_BIN, "GenerateSDF"), "-i", "-r", "10 10 10", "-o", os.path.join(HERE, "ref_dragon_10_inverted.cdf"), os.path.join(REF_RES, "dragon.obj"))
+# 855,196 triangles, not watertight (edges with more than two triangles): the sign follows whatever pseudonormals that gives
+run(os.path.join(REF_BIN, "GenerateSDF"), "-r", "8 8 8", "-o", os.path.join(HERE, "ref_buddha_8.cdf"), os.path.join(REF_RES, "happy_buddha.obj"))
 
 rng = np.random.default_rng(77)
 out = {}

@@ -38,16 +38,20 @@ def test_generate_sdf_files_byte_identical(tmp_path):
     assert _same(out, os.path.join(GOLDEN, "ref_sphere_inverted_padded.cdf"))
 
 
-def test_generate_sdf_on_bunny_byte_identical(tmp_path):
-    """BASELINE config 2's mesh through the rebuilt tool vs the reference tool's own output (12^3 to keep the fixture small)"""
+@pytest.mark.parametrize("mesh,args,fixture", [("bunny.obj", ["-r", "12 12 12"], "ref_bunny_12.cdf"),
+                                               ("dragon.obj", ["-i", "-r", "10 10 10"], "ref_dragon_10_inverted.cdf"),
+                                               ("happy_buddha.obj", ["-r", "8 8 8"], "ref_buddha_8.cdf")])
+def test_generate_sdf_on_reference_meshes_byte_identical(tmp_path, mesh, args, fixture):
+    """the reference's own meshes (BASELINE configs 2 / 3; happy_buddha is not watertight) through the rebuilt tool vs the reference
+    tool's own output (small grids to keep the fixtures small)"""
     from conftest import ref_resource
     exe = _tool("GenerateSDF")
-    obj = ref_resource("bunny.obj")
+    obj = ref_resource(mesh)
     if obj is None:
-        pytest.skip("bunny.obj not staged (oracle/_ref/resources)")
-    out = str(tmp_path / "bunny.cdf")
-    assert subprocess.run([exe, "-r", "12 12 12", "-o", out, obj], capture_output=True).returncode == 0
-    assert _same(out, os.path.join(GOLDEN, "ref_bunny_12.cdf"))
+        pytest.skip(f"{mesh} not staged (oracle/_ref/resources)")
+    out = str(tmp_path / "m.cdf")
+    assert subprocess.run([exe] + args + ["-o", out, obj], capture_output=True).returncode == 0
+    assert _same(out, os.path.join(GOLDEN, fixture))
 
 
 def test_generate_density_map_files_byte_identical(tmp_path):

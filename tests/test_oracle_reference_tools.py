@@ -101,15 +101,20 @@ def test_split_api_matches_reference_class(orc):
     assert bits_equal(q["box_split_phi"][ok], q["box_f0_phi"][:1500][ok]) and bits_equal(q["box_split_grad"][ok], q["box_f0_grad"][:1500][ok])
 
 
-def test_bunny_through_reference_tool(orc):
-    """the reference GenerateSDF on bunny.obj (12^3): oracle reproduces the file's coefficients (mesh from oracle/_ref/resources)"""
+REAL_MESH_FIXTURES = [("bunny.obj", "ref_bunny_12.cdf", 1.0), ("dragon.obj", "ref_dragon_10_inverted.cdf", -1.0), ("happy_buddha.obj", "ref_buddha_8.cdf", 1.0)]
+
+
+@pytest.mark.parametrize("mesh,fixture,sign", REAL_MESH_FIXTURES)
+def test_real_meshes_through_reference_tool(orc, mesh, fixture, sign):
+    """the reference GenerateSDF on its own meshes (bunny 12^3; dragon 10^3 --invert; happy_buddha 8^3: 855k triangles, not watertight):
+    the oracle reproduces the files' coefficients (meshes from oracle/_ref/resources)"""
     from conftest import ref_resource
-    path = ref_resource("bunny.obj")
+    path = ref_resource(mesh)
     if path is None:
-        pytest.skip("bunny.obj not staged")
-    g = read_cdf(os.path.join(GOLDEN, "ref_bunny_12.cdf"))
+        pytest.skip(f"{mesh} not staged")
+    g = read_cdf(os.path.join(GOLDEN, fixture))
     V, F = read_obj(path)
     mn, mx = orc.generate_sdf_domain(V)
     assert bits_equal(mn, g["mn"]) and bits_equal(mx, g["mx"])          # non-cubic bounding box: padding arithmetic incl. the norm order of the stand-in
     gd, res = orc.grid_desc(mn, mx, g["res"])
-    assert bits_equal(orc.mesh(V, F).sample_sdf(gd, res), g["nodes"][0])
+    assert bits_equal(orc.mesh(V, F).sample_sdf(gd, res, sign=sign), g["nodes"][0])
