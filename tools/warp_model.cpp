@@ -60,9 +60,10 @@ struct Policy {
     int pop_tries;                  // deferred entries re-tested per POP iteration (4)
     bool merge_node_pop;            // NODE and POP lanes advance in the same iteration (a fused phase)
     int leaf_patience;              // run LEAF only when it wins the vote OR has waited this many iterations (0 = plain vote)
+    bool chain_pop_node = false;    // a lane whose POP finds an internal node takes that node step in the same iteration
 };
 
-struct Tally { long long it_node = 0, it_leaf = 0, it_pop = 0, it_fused = 0, act_node = 0, act_leaf = 0, act_pop = 0, act_fused = 0, bricks = 0, queries = 0; };
+struct Tally { long long it_chain = 0, act_chain = 0; long long lane_steps = 0, max_lane_steps = 0; long long it_node = 0, it_leaf = 0, it_pop = 0, it_fused = 0, act_node = 0, act_leaf = 0, act_pop = 0, act_fused = 0, bricks = 0, queries = 0; };
 
 struct Sim {
     const HostBvh& H; int T;
@@ -115,6 +116,15 @@ struct Sim {
     void run_brick(Lane* lanes, int n, const Policy& P, Tally& t) const
     {
         int waited = 0;
+        {   // how long each lane's own walk is (node steps + leaf tests + pop iterations), independent of the schedule
+            long long mx = 0;
+            for (int i = 0; i < n; i++) {
+                Lane L = lanes[i]; long long steps = 0;
+                while (L.st != DONE) { if (L.st == NODE) node_step(L); else if (L.st == LEAF) leaf_step(L); else pop_step(L, P.pop_tries); steps++; }
+                t.lane_steps += steps; mx = std::max(mx, steps);
+            }
+            t.max_lane_steps += mx;
+        }
         for (;;) {
             int c[4] = {0, 0, 0, 0};
             for (int i = 0; i < n; i++) c[lanes[i].st]++;
@@ -134,7 +144,9 @@ struct Sim {
             // the kernel's order of preference on equal weights: POP, NODE, LEAF
             if (wp == wmax && !(P.leaf_patience && c[LEAF] && waited >= P.leaf_patience)) {
                 t.it_pop++; t.act_pop += c[POP]; if (c[LEAF]) waited++;
-                for (int i = 0; i < n; i++) if (lanes[i].st == POP) pop_step(lanes[i], P.pop_tries);
+                int chained = 0;
+                for (int i = 0; i < n; i++) if (lanes[i].st == POP) { pop_step(lanes[i], P.pop_tries); if (P.chain_pop_node && lanes[i].st == NODE) { node_step(lanes[i]); chained++; } }
+                if (chained) { t.it_chain++; t.act_chain += chained; }
             } else if (wn == wmax && !(P.leaf_patience && c[LEAF] && waited >= P.leaf_patience)) {
                 t.it_node++; t.act_node += c[NODE]; if (c[LEAF]) waited++;
                 for (int i = 0; i < n; i++) if (lanes[i].st == NODE) node_step(lanes[i]);
@@ -209,6 +221,8 @@ int main(int argc, char** argv)
         {"fused node+pop, leaf when heavier (2:3)", 2, 3, 0, 4, true, 0},
         {"fused node+pop, leaf weight 1 (lazy)", 2, 1, 0, 4, true, 0},
         {"fused node+pop, leaf lazy, patience 8", 2, 1, 0, 4, true, 8},
+        {"vote 2/3/4 + pop chains into the node step", 2, 3, 4, 4, false, 0, true},
+        {"vote 2/3/3 + pop chains into the node step", 2, 3, 3, 4, false, 0, true},
     };
     // instruction cost per iteration of each phase, from the SASS/ncu breakdown in profiles/README.md (node 70; the others solved from
     // the issued-instruction shares 21 : 40 : 14 : 18 of node : leaf : pop : loop head with the kernel policy's iteration counts below)
@@ -237,7 +251,7 @@ int main(int argc, char** argv)
                         }
 #pragma omp critical
                 { tot.it_node += t.it_node; tot.it_leaf += t.it_leaf; tot.it_pop += t.it_pop; tot.it_fused += t.it_fused; tot.act_node += t.act_node; tot.act_leaf += t.act_leaf;
-                  tot.act_pop += t.act_pop; tot.act_fused += t.act_fused; tot.bricks += t.bricks; tot.queries += t.queries; }
+                  tot.act_pop += t.act_pop; tot.act_fused += t.act_fused; tot.bricks += t.bricks; tot.queries += t.queries; tot.lane_steps += t.lane_steps; tot.max_lane_steps += t.max_lane_steps; tot.it_chain += t.it_chain; tot.act_chain += t.act_chain; }
             }
             const double B = (double)tot.bricks;
             const long long its = tot.it_node + tot.it_leaf + tot.it_pop + tot.it_fused;
@@ -245,9 +259,11 @@ int main(int argc, char** argv)
                 const double node_instr = 70.0 * tot.it_node;
                 cost_leaf = node_instr * (40.0 / 21.0) / tot.it_leaf; cost_pop = node_instr * (14.0 / 21.0) / tot.it_pop; cost_head = node_instr * (18.0 / 21.0) / its;
                 printf("calibrated instruction cost per iteration: node 70, leaf %.0f, pop %.0f, loop head %.0f\n", cost_leaf, cost_pop, cost_head);
+                printf("steps of a lane's own walk: mean %.1f, mean over bricks of the longest lane %.1f; warp iterations per brick %.1f\n",
+                       (double)tot.lane_steps / tot.queries, (double)tot.max_lane_steps / B, (double)its / B);
             }
             const double fused_cost = 70.0 + cost_pop * 0.8;           // a fused phase issues both bodies (predicated), sharing some setup
-            const double instr = 70.0 * tot.it_node + cost_leaf * tot.it_leaf + cost_pop * tot.it_pop + fused_cost * tot.it_fused + cost_head * its;
+            const double instr = 70.0 * tot.it_node + cost_leaf * tot.it_leaf + cost_pop * tot.it_pop + fused_cost * tot.it_fused + cost_head * its + 70.0 * tot.it_chain;
             printf("brick %2dx%dx%d  %-44s it/brick node %6.1f leaf %6.1f pop %6.1f fused %6.1f | lanes node %4.1f leaf %4.1f pop %4.1f fused %4.1f | instr/query %7.0f\n",
                    sh.f, sh.m, sh.s, P.name, tot.it_node / B, tot.it_leaf / B, tot.it_pop / B, tot.it_fused / B,
                    tot.it_node ? (double)tot.act_node / tot.it_node : 0.0, tot.it_leaf ? (double)tot.act_leaf / tot.it_leaf : 0.0,
