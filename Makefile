@@ -24,13 +24,24 @@ CPPBIN   := build/bin
 CPPFLAGS := -std=c++11 -O2 -ffp-contract=off -I$(EIGEN3_INCLUDE_DIR) -Icpp/include -Iinclude
 CPPLINK  := -Ldiscregrid_b200/lib -ldiscregrid_b200 -Wl,-rpath,'$$ORIGIN/../../discregrid_b200/lib'
 CPPHDRS  := $(wildcard cpp/include/Discregrid/* cpp/include/Discregrid/*/*) include/discregrid_b200.h
-cpp: $(CPPBIN)/GenerateSDF $(CPPBIN)/GenerateDensityMap $(CPPBIN)/DiscreteFieldToBitmap $(CPPBIN)/facade_check $(CPPBIN)/bvh_host_check $(CPPBIN)/reduce_facade_check $(CPPBIN)/sort_replay_check $(CPPBIN)/fast_div_check
+cpp: $(CPPBIN)/GenerateSDF $(CPPBIN)/GenerateDensityMap $(CPPBIN)/DiscreteFieldToBitmap $(CPPBIN)/facade_check $(CPPBIN)/bvh_host_check $(CPPBIN)/reduce_facade_check $(CPPBIN)/sort_replay_check $(CPPBIN)/fast_div_check $(CPPBIN)/libk1emu.so $(CPPBIN)/libk1emu_knobs.so
 $(CPPBIN)/DiscreteFieldToBitmap: cpp/cmd/discrete_field_to_bitmap.cpp $(CPPHDRS) $(LIB)
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK)
 $(CPPBIN)/bvh_host_check: tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp $(SRC)/sort_replay.h $(SRC)/bvh_build.h
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp -o $@ -lpthread
+# test libraries: the K1 translation unit (kernels + launchers) compiled for the CPU by tests/emu -- default knobs, and the prepared
+# knob variants (reciprocal division in the leaf test, redux vote) so that their logic stays checked while they are off in the product
+K1EMU_SRC := tests/emu/k1_emu.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp
+K1EMU_DEP := $(K1EMU_SRC) tests/emu/cuda_emu.h $(SRC)/k1_sdf.cu $(HDRS)
+CUDA_INC  ?= /usr/local/cuda/include
+$(CPPBIN)/libk1emu.so: $(K1EMU_DEP)
+	@mkdir -p $(CPPBIN)
+	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
+$(CPPBIN)/libk1emu_knobs.so: $(K1EMU_DEP)
+	@mkdir -p $(CPPBIN)
+	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DK1_FAST_DIV=1 -DK1_VOTE_REDUX=1 -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
 # test binary: the reciprocal-based exact division of fast_div.h against '/' (brute force)
 $(CPPBIN)/fast_div_check: tests/cpp/fast_div_check.cpp $(SRC)/fast_div.h $(SRC)/dg_device.cuh
 	@mkdir -p $(CPPBIN)

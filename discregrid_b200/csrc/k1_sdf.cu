@@ -30,6 +30,17 @@
 #include <cfloat>
 #include <mutex>
 
+// tests/emu compiles this file for the CPU (DG_EMU): the device code runs unchanged with the lanes of a warp as fibers, so the
+// traversal and the launchers' index mapping can be checked against the oracle without a GPU.  Only the launch syntax, the three
+// inline-PTX helpers and the attribute call differ.
+#ifdef DG_EMU
+#define DG_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) dg_emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+#define DG_AFTER_LAUNCH() cudaSuccess
+#else
+#define DG_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define DG_AFTER_LAUNCH() cudaGetLastError()
+#endif
+
 namespace dgb {
 
 namespace {
@@ -92,7 +103,7 @@ __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec,
     // that follows per outcome (left alone it re-creates ~20 divergent branches, three of them with their own division).
     // K1_LEAF_MODE 0: plain C (compiler's branches); 1: everything straight-line (every lane pays division + quadratic form);
     // 2: predicate-only classification, then ONE guarded block with the division and ONE with the quadratic form.
-#if K1_LEAF_MODE
+#if K1_LEAF_MODE && !defined(DG_EMU)
 #define DG_PIN_I(v) asm volatile("" : "+r"(v))
 #define DG_PIN_D(v) asm volatile("" : "+d"(v))
 #else
@@ -220,14 +231,22 @@ struct MeshDev {
 };
 
 #if K1_PREFETCH
+#ifdef DG_EMU
+__device__ __forceinline__ void prefetch_l1(const void*) {}
+#else
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
 #endif
 
 __device__ __forceinline__ float sqrt_approx(float x)
 {
+#ifdef DG_EMU
+    return std::sqrt(x);
+#else
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
 }
 
 // LEAF FILTER (K1_LEAF_FILTER): certified fp32 LOWER bound of the distance from the query to a triangle.
@@ -508,7 +527,11 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
     return res;
 }
 
+#ifdef DG_EMU
+extern unsigned char k1_smem[];                    // defined by the emulation TU (one block runs at a time)
+#else
 extern __shared__ __align__(16) unsigned char k1_smem[];
+#endif
 
 // addFunction node loop: out[l - l_begin] = sign * signed_distance(indexToNodePosition(l)).distance.
 // Thread mapping: the node array is four row-major 3-D arrays (vertices, x-, y-, z-edge nodes; K1Segment).  A warp
@@ -622,6 +645,9 @@ static inline MeshDev mesh_dev(const DeviceBvh& m)
 // (per device; meshes with different tree depths can coexist).
 cudaError_t k1_configure(int stack_depth)
 {
+#ifdef DG_EMU
+    (void)stack_depth; return cudaSuccess;
+#else
     static std::mutex mu;
     static int configured[64] = {0};              // per device: stack depth the attribute currently allows
     int dev = 0;
@@ -635,6 +661,7 @@ cudaError_t k1_configure(int stack_depth)
     e = cudaFuncSetAttribute(mesh_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = stack_depth;
     return e;
+#endif
 }
 
 // Splits [l_begin, l_begin+count) into the (at most four) node arrays it touches and tiles whole slow-planes of each.
@@ -669,9 +696,8 @@ cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double 
         blocks += S.tiles_f * S.tiles_m * tiles_s;
     }
     for (int k = w.nseg; k < 4; k++) { w.seg[k] = w.seg[0]; w.seg[k].block_begin = 0xffffffffu; }
-    sdf_sample_nodes_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(
-        mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_out);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(sdf_sample_nodes_kernel, blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream, mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_out);
+    return DG_AFTER_LAUNCH();
 }
 
 cudaError_t k1_launch_sample_slab(const DeviceBvh& m, const GridDev& g, double sign, const unsigned plane_begin[4], const unsigned plane_end[4],
@@ -697,8 +723,8 @@ cudaError_t k1_launch_sample_slab(const DeviceBvh& m, const GridDev& g, double s
     }
     if (w.nseg == 0) return cudaSuccess;
     for (int k = w.nseg; k < 4; k++) { w.seg[k] = w.seg[0]; w.seg[k].block_begin = 0xffffffffu; }
-    sdf_sample_nodes_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_full);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(sdf_sample_nodes_kernel, blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream, mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_full);
+    return DG_AFTER_LAUNCH();
 }
 
 static void node_arrays(const GridDev& g, uint64_t base[4], unsigned dims[4][3])
@@ -752,8 +778,8 @@ cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, d
     }
     if (w.nseg == 0) return cudaSuccess;
     for (int k = w.nseg; k < 4; k++) { w.seg[k] = w.seg[0]; w.seg[k].block_begin = 0xffffffffu; }
-    sdf_sample_nodes_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_slot);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(sdf_sample_nodes_kernel, blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream, mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_slot);
+    return DG_AFTER_LAUNCH();
 }
 
 // node id -> (part, position inside that part's slot): the one statement of the exchange layout, shared by the unpack kernel and the host
@@ -795,8 +821,8 @@ void k1_interleaved_node_slots(const GridDev& g, const InterleavedLayout& L, uin
 cudaError_t k1_launch_unpack_interleaved(const GridDev& g, const InterleavedLayout& L, const double* d_slots, double* d_nodes, cudaStream_t stream)
 {
     const unsigned long long n = (unsigned long long)g.nv + 2ull * ((unsigned long long)g.ne_x + g.ne_y + g.ne_z);
-    unpack_interleaved_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(g, L, n, d_slots, d_nodes);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(unpack_interleaved_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, g, L, n, d_slots, d_nodes);
+    return DG_AFTER_LAUNCH();
 }
 
 cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t count, int is_signed, double* d_dist,
@@ -804,30 +830,29 @@ cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t
 {
     if (count == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((count + K1_THREADS - 1) / K1_THREADS);
-    mesh_distance_kernel<<<blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream>>>(
-        mesh_dev(m), m.normals, m.stack_depth, d_pts, (unsigned long long)count, is_signed, d_dist, d_near, d_ent, d_tri);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(mesh_distance_kernel, blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream, mesh_dev(m), m.normals, m.stack_depth, d_pts, (unsigned long long)count, is_signed, d_dist, d_near, d_ent, d_tri);
+    return DG_AFTER_LAUNCH();
 }
 
 cudaError_t k1_launch_node_positions(const GridDev& g, uint64_t l_begin, uint64_t count, double* d_x, cudaStream_t stream)
 {
     if (count == 0) return cudaSuccess;
-    node_positions_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(g, (unsigned)l_begin, (unsigned long long)count, d_x);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(node_positions_kernel, (unsigned)((count + 255) / 256), 256, 0, stream, g, (unsigned)l_begin, (unsigned long long)count, d_x);
+    return DG_AFTER_LAUNCH();
 }
 
 cudaError_t k1_launch_build_cells(const GridDev& g, uint64_t c_begin, uint64_t count, unsigned* d_cells, cudaStream_t stream)
 {
     if (count == 0) return cudaSuccess;
     const unsigned long long n32 = (unsigned long long)count * 32ull;
-    build_cells_kernel<<<(unsigned)((n32 + 255) / 256), 256, 0, stream>>>(g, (unsigned)c_begin, n32, d_cells);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(build_cells_kernel, (unsigned)((n32 + 255) / 256), 256, 0, stream, g, (unsigned)c_begin, n32, d_cells);
+    return DG_AFTER_LAUNCH();
 }
 
 cudaError_t k1_launch_fma_probe(double a, double b, double c, double* d_out, cudaStream_t stream)
 {
-    fma_probe_kernel<<<1, 1, 0, stream>>>(a, b, c, d_out);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(fma_probe_kernel, 1, 1, 0, stream, a, b, c, d_out);
+    return DG_AFTER_LAUNCH();
 }
 
 }  // namespace dgb

@@ -1,0 +1,122 @@
+"""The product's K1 device code and launchers (discregrid_b200/csrc/k1_sdf.cu), compiled for the CPU by tests/emu (lanes of a warp as
+fibers, warp votes resolved exactly) and compared with the oracle / the reference's golden vectors bit for bit -- the kernel logic is
+therefore exercised by the CPU suite too (the real GPU runs are tests/test_gpu_k1_sdf.py).  What is emulated is the logic, not the
+device's fp32 filter arithmetic, which by construction cannot change a result."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, bits_equal, grid_for
+from test_oracle_golden import read_cdf, read_obj
+
+# default knobs, and the prepared-but-off knob variants (K1_FAST_DIV + K1_VOTE_REDUX); DG_K1_EMU_LIB adds any other build of tests/emu/k1_emu.cpp
+LIBS = [os.path.join(ROOT, "build", "bin", "libk1emu.so"), os.path.join(ROOT, "build", "bin", "libk1emu_knobs.so")] + \
+       ([os.environ["DG_K1_EMU_LIB"]] if os.environ.get("DG_K1_EMU_LIB") else [])
+_dp, _u32p, _i32p, _u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+class Emu:
+    def __init__(self, so):
+        if not os.path.exists(so):
+            pytest.skip(f"{so} not built (make cpp)")
+        self.lib = C.CDLL(so)
+        self.lib.emu_mesh_create.restype = C.c_void_p
+        self.lib.emu_mesh_create.argtypes = [_dp, C.c_uint64, _u32p, C.c_uint64]
+        self.lib.emu_mesh_destroy.argtypes = [C.c_void_p]
+        self.lib.emu_sample_sdf.argtypes = [C.c_void_p, _dp, _u32p, C.c_double, C.c_uint64, C.c_uint64, _dp]
+        self.lib.emu_sample_interleaved.argtypes = [C.c_void_p, _dp, _u32p, C.c_double, C.c_uint32, C.c_uint32, _dp, _u64p]
+        self.lib.emu_unpack_interleaved.argtypes = [_dp, _u32p, C.c_uint32, _dp, _dp]
+        self.lib.emu_sample_slab.argtypes = [C.c_void_p, _dp, _u32p, C.c_double, _u32p, _u32p, _dp]
+        self.lib.emu_mesh_distance.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _dp, _dp, _i32p, _i32p]
+        self.lib.emu_node_positions.argtypes = [_dp, _u32p, C.c_uint64, C.c_uint64, _dp]
+        self.lib.emu_build_cells.argtypes = [_dp, _u32p, C.c_uint64, C.c_uint64, _u32p]
+
+    def mesh(self, V, F):
+        V = np.ascontiguousarray(V, np.float64); F = np.ascontiguousarray(F, np.uint32)
+        h = self.lib.emu_mesh_create(_p(V, _dp), len(V), _p(F, _u32p), len(F))
+        assert h
+        return h
+
+    def sample(self, h, gd, res, l0, l1, sign=1.0):
+        out = np.full(l1 - l0, np.nan)
+        assert self.lib.emu_sample_sdf(h, _p(gd, _dp), _p(res, _u32p), sign, l0, l1, _p(out, _dp)) == 0
+        return out
+
+
+@pytest.fixture(scope="module", params=LIBS, ids=[os.path.basename(p) for p in LIBS])
+def emu(request):
+    return Emu(request.param)
+
+
+def test_emulated_kernel_reproduces_box_cdf(emu, orc):
+    """the reference's only golden vector, through the product's kernel code on the CPU: all 1296 coefficients and the connectivity"""
+    g = read_cdf(os.path.join(GOLDEN, "box.cdf"))
+    V, F = read_obj(os.path.join(GOLDEN, "box.obj"))
+    gd, res = orc.grid_desc(g["mn"], g["mx"], g["res"], g["cell"], g["inv"])
+    h = emu.mesh(V, F)
+    assert bits_equal(emu.sample(h, gd, res, 0, len(g["nodes"][0])), g["nodes"][0])
+    cells = np.zeros((125, 32), np.uint32)
+    assert emu.lib.emu_build_cells(_p(gd, _dp), _p(res, _u32p), 0, 125, _p(cells, _u32p)) == 0
+    assert np.array_equal(cells, g["cells"][0])
+    emu.lib.emu_mesh_destroy(h)
+
+
+@pytest.mark.parametrize("res", [(9, 8, 7), (16, 5, 3)])
+def test_emulated_node_loop_ranges_and_shardings(emu, orc, res):
+    """whole grid, ragged node ranges (masked bricks), the slab form and the interleaved deal + unpack: all equal to the oracle"""
+    import discregrid_b200 as dg
+    t = dg.bumpy_torus(24, 20, 1.0, 0.4, 0.05, 7, 5)
+    mn, mx, gd, r = grid_for(orc, t.vertices, res)
+    want = orc.mesh(t.vertices, t.faces).sample_sdf(gd, r)
+    n = len(want)
+    h = emu.mesh(t.vertices, t.faces)
+    assert bits_equal(emu.sample(h, gd, r, 0, n), want)
+    for (a, b) in [(0, 1), (5, 77), (n // 3, n // 3 + 1000), (n - 13, n)]:
+        b = min(b, n)
+        assert bits_equal(emu.sample(h, gd, r, a, b, sign=-1.0), -want[a:b])
+    # interleaved deal over 3 parts + unpack
+    se = C.c_uint64()
+    assert emu.lib.emu_sample_interleaved(h, _p(gd, _dp), _p(r, _u32p), 1.0, 0, 3, None, C.byref(se)) == 0
+    slots = np.full(3 * se.value, np.nan)
+    for part in range(3):
+        assert emu.lib.emu_sample_interleaved(h, _p(gd, _dp), _p(r, _u32p), 1.0, part, 3, _p(slots, _dp), C.byref(se)) == 0
+    full = np.full(n, np.nan)
+    assert emu.lib.emu_unpack_interleaved(_p(gd, _dp), _p(r, _u32p), 3, _p(slots, _dp), _p(full, _dp)) == 0
+    assert bits_equal(full, want)
+    # node positions
+    x = np.zeros((n, 3))
+    assert emu.lib.emu_node_positions(_p(gd, _dp), _p(r, _u32p), 0, n, _p(x, _dp)) == 0
+    assert bits_equal(x, orc.node_positions(gd, r, 0, n))
+    emu.lib.emu_mesh_destroy(h)
+
+
+def test_emulated_distance_queries_match_reference_header(emu):
+    """mesh_distance_kernel on the CPU vs results of the reference's own TriangleMeshDistance.h (golden): distance, nearest point,
+    entity and triangle, signed and unsigned, including points on the surface"""
+    import discregrid_b200 as dg
+    q = np.load(os.path.join(GOLDEN, "ref_torus_queries.npz"))
+    t = dg.bumpy_torus(*[int(a) if i < 2 or i > 4 else float(a) for i, a in enumerate(q["torus_args"])])
+    h = emu.mesh(t.vertices, t.faces)
+    x = np.ascontiguousarray(q["x"][:1500]); n = len(x)
+    dist = np.zeros(n); near = np.zeros((n, 3)); ent = np.zeros(n, np.int32); tri = np.zeros(n, np.int32)
+    assert emu.lib.emu_mesh_distance(h, _p(x, _dp), n, 1, _p(dist, _dp), _p(near, _dp), _p(ent, _i32p), _p(tri, _i32p)) == 0
+    assert bits_equal(dist, q["distance"][:n]) and bits_equal(near, q["nearest"][:n])
+    assert np.array_equal(ent, q["entity"][:n]) and np.array_equal(tri, q["triangle"][:n])
+    assert emu.lib.emu_mesh_distance(h, _p(x, _dp), n, 0, _p(dist, _dp), None, None, None) == 0
+    assert bits_equal(dist, q["unsigned"][:n])
+    emu.lib.emu_mesh_destroy(h)
+    s = np.load(os.path.join(GOLDEN, "ref_sphere_surface.npz"))
+    a = s["sphere_args"]
+    sp = dg.uv_sphere(int(a[0]), int(a[1]), float(a[2]), (float(a[3]), float(a[4]), float(a[5])))
+    h = emu.mesh(sp.vertices, sp.faces)
+    xs = np.ascontiguousarray(s["x"]); n = len(xs)
+    dist = np.zeros(n); near = np.zeros((n, 3)); ent = np.zeros(n, np.int32); tri = np.zeros(n, np.int32)
+    assert emu.lib.emu_mesh_distance(h, _p(xs, _dp), n, 1, _p(dist, _dp), _p(near, _dp), _p(ent, _i32p), _p(tri, _i32p)) == 0
+    assert bits_equal(dist, s["distance"]) and bits_equal(near, s["nearest"]) and np.array_equal(ent, s["entity"]) and np.array_equal(tri, s["triangle"])
+    emu.lib.emu_mesh_destroy(h)
