@@ -30,16 +30,7 @@
 #include <cfloat>
 #include <mutex>
 
-// tests/emu compiles this file for the CPU (DG_EMU): the device code runs unchanged with the lanes of a warp as fibers, so the
-// traversal and the launchers' index mapping can be checked against the oracle without a GPU.  Only the launch syntax, the three
-// inline-PTX helpers and the attribute call differ.
-#ifdef DG_EMU
-#define DG_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) dg_emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
-#define DG_AFTER_LAUNCH() cudaSuccess
-#else
-#define DG_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-#define DG_AFTER_LAUNCH() cudaGetLastError()
-#endif
+#include "dg_launch.h"       // DG_KERNEL_LAUNCH: <<<>>> on the device, fibers under tests/emu (DG_EMU)
 
 namespace dgb {
 

@@ -22,9 +22,12 @@
 // removes six fp64 divisions per query without changing a bit.
 #include "dg_device.cuh"
 #include "k2_interp.h"
+#include "dg_launch.h"
 
 #include <cfloat>
 #include <climits>
+#include <cstdint>
+#include <cstring>
 
 namespace dgb {
 
@@ -33,6 +36,18 @@ namespace {
 constexpr int K2_SLOT_BYTES = 272;          // 256-byte block + 16 bytes of padding (bank spreading)
 constexpr int K2_WARPS = K2_THREADS / 32;
 
+#ifdef DG_EMU
+// CPU emulation: "shared" addresses are plain pointers, the bulk copy is a memcpy that has completed when it returns, the mbarrier
+// has nothing left to wait for (each lane only reads the slot it copied itself)
+typedef uintptr_t smem_addr_t;
+inline smem_addr_t smem_u32(const void* p) { return (smem_addr_t)p; }
+inline void mbar_init(smem_addr_t, unsigned) {}
+inline void mbar_expect_tx(smem_addr_t, unsigned) {}
+inline void bulk_g2s(smem_addr_t dst, const void* src, unsigned bytes, smem_addr_t) { std::memcpy((void*)dst, src, bytes); }
+inline void mbar_wait(smem_addr_t, unsigned) {}
+inline void __syncwarp() {}
+#else
+typedef unsigned smem_addr_t;
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
@@ -61,6 +76,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
         "WAIT_DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+#endif
 
 // Gathers the packed per-cell blocks.  One thread per (kept cell, local node).
 __global__ void pack_cells_kernel(GridDev g, const double* __restrict__ nodes, const unsigned* __restrict__ cells /*nullable*/,
@@ -110,7 +126,7 @@ interpolate_kernel(GridDev g, const double* __restrict__ packed, const unsigned*
     const bool live = q0 < n;
     const unsigned long long q = live ? q0 : n - 1;         // tail lanes shadow the last query (no store)
 
-    const unsigned bar = smem_u32(&bars[warp]);
+    const smem_addr_t bar = smem_u32(&bars[warp]);
     if (lane == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, 32u * 256u); }
     __syncwarp();
 
@@ -132,7 +148,7 @@ interpolate_kernel(GridDev g, const double* __restrict__ packed, const unsigned*
     }
 
     // ---- one bulk copy per lane: packed[cell][0..31] -> stage[warp][lane]
-    const unsigned slot = smem_u32(&stage[warp][lane * K2_SLOT_BYTES]);
+    const smem_addr_t slot = smem_u32(&stage[warp][lane * K2_SLOT_BYTES]);
     bulk_g2s(slot, packed + (size_t)cell * 32, 256u, bar);
 
     // ---- reference-cell coordinates (:996-1003) and every coefficient-independent temporary (:344-385, :440-460)
@@ -339,15 +355,15 @@ cudaError_t k2_launch_pack(const GridDev& g, const double* d_nodes, const unsign
 {
     if (n_cells_kept == 0) return cudaSuccess;
     const unsigned long long n32 = (unsigned long long)n_cells_kept * 32ull;
-    pack_cells_kernel<<<(unsigned)((n32 + 255) / 256), 256, 0, stream>>>(g, d_nodes, d_cells, n32, d_packed);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(pack_cells_kernel, (unsigned)((n32 + 255) / 256), 256, 0, stream, g, d_nodes, d_cells, n32, d_packed);
+    return DG_AFTER_LAUNCH();
 }
 
 cudaError_t k2_launch_axis_tables(const GridDev& g, double2* d_tab, cudaStream_t stream)
 {
     const unsigned n = g.n[0] + g.n[1] + g.n[2];
-    axis_tables_kernel<<<(n + 127) / 128, 128, 0, stream>>>(g, d_tab);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(axis_tables_kernel, (n + 127) / 128, 128, 0, stream, g, d_tab);
+    return DG_AFTER_LAUNCH();
 }
 
 cudaError_t k2_launch_interpolate(const FieldDev& f, const double* d_x, uint64_t n, double* d_phi, double* d_grad,
@@ -356,17 +372,17 @@ cudaError_t k2_launch_interpolate(const FieldDev& f, const double* d_x, uint64_t
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + K2_THREADS - 1) / K2_THREADS);
     if (d_grad)
-        interpolate_kernel<true><<<blocks, K2_THREADS, 0, stream>>>(f.g, f.packed, f.cell_map, f.tab, d_x, (unsigned long long)n, d_phi, d_grad);
+        DG_KERNEL_LAUNCH((interpolate_kernel<true>), blocks, K2_THREADS, 0, stream, f.g, f.packed, f.cell_map, f.tab, d_x, (unsigned long long)n, d_phi, d_grad);
     else
-        interpolate_kernel<false><<<blocks, K2_THREADS, 0, stream>>>(f.g, f.packed, f.cell_map, f.tab, d_x, (unsigned long long)n, d_phi, nullptr);
-    return cudaGetLastError();
+        DG_KERNEL_LAUNCH((interpolate_kernel<false>), blocks, K2_THREADS, 0, stream, f.g, f.packed, f.cell_map, f.tab, d_x, (unsigned long long)n, d_phi, nullptr);
+    return DG_AFTER_LAUNCH();
 }
 
 cudaError_t k2_launch_shape_functions(const double* d_xi, uint64_t n, double* d_N, double* d_dN, cudaStream_t stream)
 {
     if (n == 0) return cudaSuccess;
-    shape_functions_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_xi, (unsigned long long)n, d_N, d_dN);
-    return cudaGetLastError();
+    DG_KERNEL_LAUNCH(shape_functions_kernel, (unsigned)((n + 127) / 128), 128, 0, stream, d_xi, (unsigned long long)n, d_N, d_dN);
+    return DG_AFTER_LAUNCH();
 }
 
 }  // namespace dgb

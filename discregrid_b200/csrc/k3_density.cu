@@ -20,6 +20,7 @@
 #include "dg_device.cuh"
 #include "k3_density.h"
 #include "fast_div.h"
+#include "dg_launch.h"
 
 // K3_FAST_DIV 1: gamma's d / h (one fp64 division per quadrature point, ~33 of ~400 instructions) through the reciprocal of h.
 // Off until measured on the GPU.
@@ -201,18 +202,23 @@ cudaError_t k3_launch_density(const FieldDev& f, double h, double rho0, int no_r
                 }
                 W[(i * 16 + j) * 16 + k] = res;
             }
+    const unsigned blocks = (unsigned)((count + 127) / 128);
+#ifdef DG_EMU
+    DG_KERNEL_LAUNCH(density_map_kernel, blocks, 128, 0, stream, f, qp, W.data(), no_reduction, (unsigned)l_begin, (unsigned long long)count, d_out);
+    return cudaSuccess;
+#else
     double* d_W = nullptr;
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_W), 4096 * sizeof(double), stream);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(d_W, W.data(), 4096 * sizeof(double), cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) {
         // the pageable source is staged synchronously by the runtime, so W may go out of scope afterwards
-        const unsigned blocks = (unsigned)((count + 127) / 128);
-        density_map_kernel<<<blocks, 128, 0, stream>>>(f, qp, d_W, no_reduction, (unsigned)l_begin, (unsigned long long)count, d_out);
-        e = cudaGetLastError();
+        DG_KERNEL_LAUNCH(density_map_kernel, blocks, 128, 0, stream, f, qp, d_W, no_reduction, (unsigned)l_begin, (unsigned long long)count, d_out);
+        e = DG_AFTER_LAUNCH();
     }
     cudaFreeAsync(d_W, stream);
     return e;
+#endif
 }
 
 }  // namespace dgb
