@@ -89,6 +89,15 @@ def test_emulated_node_loop_ranges_and_shardings(emu, orc, res):
     full = np.full(n, np.nan)
     assert emu.lib.emu_unpack_interleaved(_p(gd, _dp), _p(r, _u32p), 3, _p(slots, _dp), _p(full, _dp)) == 0
     assert bits_equal(full, want)
+    # slab form: whole slow-plane pairs of each of the four node arrays, three parts, written at their final positions
+    nx, ny, nz = res
+    ds = [nz + 1, nz + 1, nx + 1, ny + 1]                         # slow dimension of the vertex / x-edge / y-edge / z-edge arrays
+    full2 = np.full(n, np.nan)
+    for part in range(3):
+        pb = np.array([2 * ((((d + 1) // 2) * part) // 3) for d in ds], np.uint32)
+        pe = np.array([min(d, 2 * ((((d + 1) // 2) * (part + 1)) // 3)) for d in ds], np.uint32)
+        assert emu.lib.emu_sample_slab(h, _p(gd, _dp), _p(r, _u32p), 1.0, _p(pb, _u32p), _p(pe, _u32p), _p(full2, _dp)) == 0
+    assert bits_equal(full2, want)
     # node positions
     x = np.zeros((n, 3))
     assert emu.lib.emu_node_positions(_p(gd, _dp), _p(r, _u32p), 0, n, _p(x, _dp)) == 0
