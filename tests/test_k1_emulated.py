@@ -129,3 +129,53 @@ def test_emulated_distance_queries_match_reference_header(emu):
     assert emu.lib.emu_mesh_distance(h, _p(xs, _dp), n, 1, _p(dist, _dp), _p(near, _dp), _p(ent, _i32p), _p(tri, _i32p)) == 0
     assert bits_equal(dist, s["distance"]) and bits_equal(near, s["nearest"]) and np.array_equal(ent, s["entity"]) and np.array_equal(tri, s["triangle"])
     emu.lib.emu_mesh_destroy(h)
+
+
+def _rand_mesh(rng, n_tri, scale=1.0, offset=0.0, degenerate=False):
+    V = rng.standard_normal((n_tri + 2, 3)) * scale + offset
+    F = np.array([[i, i + 1, i + 2] for i in range(n_tri)], np.uint32)        # a strip: neighbours share edges and vertices (ties)
+    if degenerate and n_tri >= 3:
+        V[3] = V[2]                                                            # zero-length edge -> zero-area triangles
+        F[-1] = [0, 0, 1]                                                      # a triangle with a repeated vertex
+    return np.ascontiguousarray(V), F
+
+
+@pytest.mark.parametrize("n_tri,scale,offset,degenerate", [(1, 1.0, 0.0, False), (2, 1.0, 0.0, False), (3, 1.0, 0.0, False), (7, 1e-9, 0.0, False),
+                                                           (40, 1.0, 1e9, False), (33, 1e6, -3e7, False), (9, 1.0, 0.0, True), (64, 1.0, 0.0, True)])
+def test_emulated_queries_on_awkward_meshes_vs_reference_header(emu, n_tri, scale, offset, degenerate):
+    """corner cases against the reference's own TriangleMeshDistance.h where it is compiled (oracle/_ref): one- and two-triangle meshes
+    (the root is a leaf / has leaf children), tiny and huge coordinates (the fp32 filter's error bound scales with them), far-away and
+    non-finite queries (filter switched off / NaN comparisons), degenerate triangles (0/0 in the reference's formulas): same distance
+    bits -- NaN for NaN --, same nearest entity and triangle"""
+    from oracle_api import REF_SO, RefMesh
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/libdgref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(1000 + n_tri)
+    V, F = _rand_mesh(rng, n_tri, scale, offset, degenerate)
+    x = np.concatenate([rng.standard_normal((300, 3)) * scale * 2 + offset,                    # around the mesh
+                        V[:min(len(V), 20)],                                                  # exactly on vertices
+                        0.5 * (V[F[:, 0]] + V[F[:, 1]])[:20],                                  # on edges
+                        rng.standard_normal((40, 3)) * scale * 1e6 + offset,                   # far
+                        np.array([[1e19, -1e19, 3e18], [0.0, 0.0, 0.0], [-0.0, 0.0, -0.0]])])
+    x = np.ascontiguousarray(x)
+    # queries for which the reference accepts no triangle (NaN, infinite, or so large that the squared distance overflows) make it index
+    # triangles[-1] (undefined behaviour: it crashes for some meshes): not sent to the reference; the kernel must answer DBL_MAX / -1
+    lost = np.ascontiguousarray(np.array([[1e300, 0, 0], [np.nan, 0, 0], [np.inf, 1, 2], [0, -np.inf, 0]]))
+    ref = RefMesh(V, F)
+    h = emu.mesh(V, F)
+    for signed in (1, 0):
+        want_d, want_near, want_ent, want_tri = ref.distance(x, signed=bool(signed))
+        n = len(x)
+        dist = np.zeros(n); near = np.zeros((n, 3)); ent = np.zeros(n, np.int32); tri = np.zeros(n, np.int32)
+        assert emu.lib.emu_mesh_distance(h, _p(x, _dp), n, signed, _p(dist, _dp), _p(near, _dp), _p(ent, _i32p), _p(tri, _i32p)) == 0
+        found = want_tri >= 0
+        assert found.all()
+        same_d = (dist.view(np.uint64) == want_d.view(np.uint64)) | (np.isnan(dist) & np.isnan(want_d))
+        assert same_d.all(), (np.nonzero(~same_d)[0][:5], dist[~same_d][:5], want_d[~same_d][:5], x[~same_d][:5])
+        d2 = np.zeros(len(lost)); t2 = np.zeros(len(lost), np.int32)
+        assert emu.lib.emu_mesh_distance(h, _p(lost, _dp), len(lost), signed, _p(d2, _dp), None, None, _p(t2, _i32p)) == 0
+        assert (d2 == np.finfo(np.float64).max).all() and (t2 == -1).all()
+        assert np.array_equal(tri[found], want_tri[found]) and np.array_equal(ent[found], want_ent[found])
+        same_p = (near.view(np.uint64) == want_near.view(np.uint64)) | (np.isnan(near) & np.isnan(want_near))
+        assert same_p[found].all()
+    emu.lib.emu_mesh_destroy(h)
