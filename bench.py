@@ -59,9 +59,15 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ helpers
-def reduce_field_leg(capi, desc, values, cells, lo, hi, with_reference, tmp_dir="/tmp"):
+def reduce_field_leg(capi, desc, values, cells, lo, hi, with_reference, tmp_dir=None):
     """reduceField(field, lo <= v <= hi) (cmd/generate_density_map/main.cpp:141-144) on a sampled field -- host code on
     both sides: dg_reduce_field (index passes, multithreaded) vs the reference class's own reduceField (oracle/_ref, when built)."""
+    if tmp_dir is None:                                     # the repo's own volume (build/ is git-ignored); /tmp can be a slow copy-on-write layer
+        tmp_dir = os.path.join(ROOT, "build")
+        try:
+            os.makedirs(tmp_dir, exist_ok=True)
+        except OSError:
+            tmp_dir = "/tmp"
     keep = np.ascontiguousarray((lo <= values) & (values <= hi) & (values != np.finfo(np.float64).max), np.uint8)
     n_grid_cells = int(desc.resolution[0]) * int(desc.resolution[1]) * int(desc.resolution[2])
     best, out = None, None

@@ -9,6 +9,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# Several tests exchange a few hundred MB with helper binaries through tmp_path.  In the build container /tmp sits on a copy-on-write
+# layer that writes at ~15-75 MB/s while the repo's own volume does > 1 GB/s, so the temporary root goes under build/ (git-ignored).
+_TMPROOT = os.path.join(ROOT, "build", "pytest-tmp")
+try:
+    os.makedirs(_TMPROOT, exist_ok=True)
+    os.environ.setdefault("PYTEST_DEBUG_TEMPROOT", _TMPROOT)
+except OSError:
+    pass
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
