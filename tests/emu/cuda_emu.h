@@ -2,7 +2,7 @@
 // (warp-synchronous traversal, index mapping of the launchers, interleaved layouts) is checked against the oracle WITHOUT a GPU.
 //
 // The emulation TU defines DG_EMU, includes this header and then the .cu file itself.  A kernel "launch" runs the blocks one after the
-// other; the 32 lanes of a warp are ucontext fibers on one OS thread, resumed round-robin, and a warp collective (__ballot_sync,
+// other; the 32 lanes of a warp are fibers on one OS thread, resumed round-robin, and a warp collective (__ballot_sync,
 // __reduce_add_sync) parks a lane until all live lanes of its warp have arrived -- i.e. the code sees exactly the values it would see
 // on the device.  fp64 arithmetic is the host's IEEE arithmetic (the TU is built with -ffp-contract=off, like -fmad=false); the fp32
 // directed-rounding intrinsics are emulated exactly where that is cheap (products) and to within a double rounding elsewhere -- they
@@ -10,7 +10,6 @@
 // Not emulated: block-level barriers and shared-memory exchange between warps (K1 has none), inline PTX (guarded in the sources).
 #pragma once
 #include <cuda_runtime.h>          // vector types, cudaError_t ... (declarations only; nothing of the runtime is called)
-#include <ucontext.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -25,28 +24,57 @@ namespace dg_emu {
 struct Idx { unsigned x = 0, y = 0, z = 0; };
 inline Idx g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 
+// Fiber switch: callee-saved registers + stack pointer, no system call (glibc's swapcontext does a sigprocmask per switch, which made a
+// warp vote cost ~60 us).  x86-64 System V only -- what the build container and the GPU boxes are.
+#if !defined(__x86_64__)
+#error "tests/emu needs x86-64 (hand-written fiber switch)"
+#endif
+extern "C" void dg_emu_switch(void** save_sp, void* load_sp);
+__asm__(R"(
+    .text
+    .weak dg_emu_switch
+    .type dg_emu_switch,@function
+dg_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size dg_emu_switch, .-dg_emu_switch
+)");
+
 struct WarpRun {
     static constexpr int N = 32;
-    ucontext_t sched;
-    ucontext_t ctx[N];
+    void* sched_sp = nullptr;
+    void* lane_sp[N];
     std::vector<unsigned char> stacks;
     bool finished[N];
     bool waiting[N];
     unsigned contrib[N];           // predicate (ballot) or addend (reduce)
     unsigned result_ballot = 0, result_sum = 0;
     int n_lanes = 0, cur = -1;
-    unsigned warp_first_thread = 0;
     const std::function<void()>* body = nullptr;
 };
 inline WarpRun* g_warp = nullptr;
 
-inline void lane_trampoline()
+extern "C" inline void dg_emu_lane_entry()
 {
     WarpRun* w = g_warp;
     const int lane = w->cur;
     (*w->body)();
     w->finished[lane] = true;
-    swapcontext(&w->ctx[lane], &w->sched);
+    dg_emu_switch(&w->lane_sp[lane], w->sched_sp);        // never resumed
+    std::abort();
 }
 
 // park the calling lane at a warp collective; returns when every live lane has arrived and the result is available
@@ -56,23 +84,25 @@ inline void collective_wait(unsigned value)
     const int lane = w->cur;
     w->contrib[lane] = value;
     w->waiting[lane] = true;
-    swapcontext(&w->ctx[lane], &w->sched);
+    dg_emu_switch(&w->lane_sp[lane], w->sched_sp);
 }
 
 inline void run_warp(unsigned first_thread, int n_lanes, const std::function<void()>& body)
 {
     static WarpRun w;
     const size_t STACK = 256 * 1024;
-    if (w.stacks.empty()) w.stacks.resize(STACK * WarpRun::N);
-    w.n_lanes = n_lanes; w.body = &body; w.warp_first_thread = first_thread;
+    if (w.stacks.empty()) w.stacks.resize(STACK * WarpRun::N + 64);
+    w.n_lanes = n_lanes; w.body = &body;
     g_warp = &w;
     for (int l = 0; l < n_lanes; l++) {
         w.finished[l] = false; w.waiting[l] = false;
-        getcontext(&w.ctx[l]);
-        w.ctx[l].uc_stack.ss_sp = w.stacks.data() + STACK * l;
-        w.ctx[l].uc_stack.ss_size = STACK;
-        w.ctx[l].uc_link = &w.sched;
-        makecontext(&w.ctx[l], lane_trampoline, 0);
+        uintptr_t top = (uintptr_t)(w.stacks.data() + STACK * (l + 1));
+        top &= ~(uintptr_t)15;
+        void** sp = (void**)top;
+        *--sp = nullptr;                                   // padding: the entry function sees the stack as after a call
+        *--sp = (void*)&dg_emu_lane_entry;                 // popped by `ret`
+        for (int r = 0; r < 6; r++) *--sp = nullptr;       // rbp rbx r12 r13 r14 r15
+        w.lane_sp[l] = sp;
     }
     for (;;) {
         bool any_live = false;
@@ -81,7 +111,7 @@ inline void run_warp(unsigned first_thread, int n_lanes, const std::function<voi
             any_live = true;
             w.cur = l;
             g_threadIdx.x = first_thread + (unsigned)l;
-            swapcontext(&w.sched, &w.ctx[l]);                 // runs until the lane parks at a collective or returns
+            dg_emu_switch(&w.sched_sp, w.lane_sp[l]);         // runs until the lane parks at a collective or returns
         }
         bool all_done = true, any_waiting = false;
         for (int l = 0; l < n_lanes; l++) { if (!w.finished[l]) all_done = false; if (w.waiting[l]) any_waiting = true; }
@@ -89,8 +119,6 @@ inline void run_warp(unsigned first_thread, int n_lanes, const std::function<voi
         if (any_waiting) {                                    // every live lane is parked: resolve the collective
             unsigned mask = 0, sum = 0;
             for (int l = 0; l < n_lanes; l++) if (w.waiting[l]) { if (w.contrib[l]) mask |= 1u << l; sum += w.contrib[l]; }
-            // lanes of a partial warp that do not exist behave like exited lanes: they contribute nothing; a ballot over the FULL
-            // mask then sees zeros for them -- the kernels under test tolerate that only if they never run partial warps (they do not)
             w.result_ballot = mask; w.result_sum = sum;
             for (int l = 0; l < n_lanes; l++) w.waiting[l] = false;
         } else if (!any_live) {
