@@ -56,7 +56,7 @@ DGEMU_SRC := tests/emu/dgapi_emu.cpp tests/emu/k1_emu.cpp tests/emu/k2_emu.cpp t
              $(SRC)/bvh_build.cpp $(SRC)/reduce_field.cpp $(SRC)/obj_reader.cpp $(SRC)/sort_replay.cpp
 $(CPPBIN)/libdgemu.so: $(DGEMU_SRC) tests/emu/cuda_emu.h $(wildcard $(SRC)/*.cu) $(HDRS)
 	@mkdir -p $(CPPBIN)
-	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -I$(CUDA_INC) -Itests/emu -I$(SRC) -Iinclude $(DGEMU_SRC) -o $@ -lpthread
+	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -Wl,-Bsymbolic -Wno-subobject-linkage -I$(CUDA_INC) -Itests/emu -I$(SRC) -Iinclude $(DGEMU_SRC) -o $@ -lpthread
 # test binary: the reciprocal-based exact division of fast_div.h against '/' (brute force)
 $(CPPBIN)/fast_div_check: tests/cpp/fast_div_check.cpp $(SRC)/fast_div.h $(SRC)/dg_device.cuh
 	@mkdir -p $(CPPBIN)

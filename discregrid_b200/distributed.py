@@ -33,6 +33,20 @@ class NodeSharding:
         return out
 
 
+
+def _stream_ptr(t):
+    """the current CUDA stream's handle for a device tensor; the default stream (0) for a host tensor -- host tensors only occur when the
+    multi-GPU logic is rehearsed on the CPU against the emulated library (tests/emu, gloo)"""
+    import ctypes as C
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream) if t.is_cuda else C.c_void_p(0)
+
+
+def _side_streams(t, n):
+    """n side streams on t's device; none for a host tensor (its launches have completed when they return)"""
+    import torch
+    return [torch.cuda.Stream() for _ in range(n)] if (t.is_cuda and n > 0) else []
+
 def make_sharding(n, world, rows=None, align=1024):
     """Equal chunks of a size that is a multiple of `align` nodes (keeps every chunk 8 KiB-aligned in the fp64 array)."""
     if world == 1:
@@ -67,19 +81,22 @@ class ShardedSdfSampler:
         import torch
         self.md, self.desc, self.sh, self.rank = md, desc, sharding, rank
         self.chunks = [(j, b, e) for (j, b, e) in sharding.chunks_of(rank) if e > b]
-        self.streams = [torch.cuda.Stream() for _ in range(min(n_streams, max(1, len(self.chunks))))] if len(self.chunks) > 1 else []
+        self.n_streams = min(n_streams, max(1, len(self.chunks))) if len(self.chunks) > 1 else 0
+        self.streams = None                                # created at the first launch, on the output tensor's device
 
     def launch(self, full, sign=1.0):
         """enqueue this rank's kernels; `full` = fp64 CUDA tensor of sharding.padded elements; returns #launches"""
         import ctypes as C
         import torch
         from . import _capi as capi
-        cur = torch.cuda.current_stream()
+        if self.streams is None:
+            self.streams = _side_streams(full, self.n_streams)
         if not self.streams:
             for (_j, b, e) in self.chunks:
                 capi.check(capi.lib.dg_sample_sdf_device(self.md.handle, C.byref(self.desc), sign, b, e,
-                                                         C.c_void_p(full.data_ptr() + 8 * b), C.c_void_p(cur.cuda_stream)))
+                                                         C.c_void_p(full.data_ptr() + 8 * b), _stream_ptr(full)))
             return len(self.chunks)
+        cur = torch.cuda.current_stream()
         for st in self.streams:
             st.wait_stream(cur)
         for k, (_j, b, e) in enumerate(self.chunks):
@@ -111,7 +128,7 @@ class ShardedDensityMap:
         import ctypes as C
         import torch
         from . import _capi as capi
-        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        sp = _stream_ptr(out)
         for (_j, b, e) in self.chunks:
             capi.check(capi.lib.dg_density_map_device(self.fh, h, rho0, int(no_reduction), b, e, C.c_void_p(out.data_ptr() + 8 * b), sp))
         return len(self.chunks)
@@ -189,7 +206,7 @@ class SlabSdfSampler:
         import torch
         from . import _capi as capi
         capi.check(capi.lib.dg_sample_sdf_slab_device(self.md.handle, C.byref(self.desc), sign, self.rank, self.world,
-                                                      C.c_void_p(full.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                                      C.c_void_p(full.data_ptr()), _stream_ptr(full)))
         return 1
 
     def step(self, full, sign=1.0, group=None):
@@ -251,21 +268,21 @@ class InterleavedSdfSampler:
         import torch
         if self.slots is None:
             self.slots = torch.empty(self.parts * self.slot, dtype=full.dtype, device=full.device)
-            self.streams = [torch.cuda.Stream() for _ in range(self.splits)] if self.splits > 1 else []
+            self.streams = _side_streams(full, self.splits if self.splits > 1 else 0)
 
     def launch(self, full, sign=1.0):
         import ctypes as C
         import torch
         from . import _capi as capi
         self._buffers(full)
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream() if self.streams else None
         for st in self.streams:
             st.wait_stream(cur)
         for k in range(self.splits):
             part = self.rank * self.splits + k
-            st = self.streams[k] if self.streams else cur
+            sp = C.c_void_p(self.streams[k].cuda_stream) if self.streams else _stream_ptr(full)
             capi.check(capi.lib.dg_sample_sdf_interleaved_device(self.md.handle, C.byref(self.desc), sign, part, self.parts,
-                                                                 C.c_void_p(self.slots.data_ptr() + 8 * part * self.slot), C.c_void_p(st.cuda_stream)))
+                                                                 C.c_void_p(self.slots.data_ptr() + 8 * part * self.slot), sp))
         for st in self.streams:
             cur.wait_stream(st)
         return self.splits
@@ -276,7 +293,6 @@ class InterleavedSdfSampler:
         from . import _capi as capi
         self.launch(full, sign)
         allgather_slots(self.slots, self.slot * self.splits, self.rank, self.world, group)
-        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         capi.check(capi.lib.dg_interleaved_unpack_device(C.byref(self.desc), self.parts, C.c_void_p(self.slots.data_ptr()),
-                                                         C.c_void_p(full.data_ptr()), sp))
+                                                         C.c_void_p(full.data_ptr()), _stream_ptr(full)))
         return self.splits + 1

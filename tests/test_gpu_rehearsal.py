@@ -27,3 +27,17 @@ def test_gpu_suite_passes_on_the_emulated_library():
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+def test_multi_gpu_worker_on_two_gloo_ranks(tmp_path):
+    """the worker script of tests/test_gpu_multi.py (node-id chunks, slabs, interleaved plane pairs, sharded density map, each compared
+    with a single launch) on two gloo ranks with host tensors against the emulated library: the N > 1 plumbing end to end"""
+    if not os.path.exists(EMU):
+        pytest.skip("build/bin/libdgemu.so not built (make cpp)")
+    from test_gpu_multi import WORKER
+    script = tmp_path / "w.py"
+    script.write_text(f"ROOT = {ROOT!r}\n" + WORKER)
+    env = dict(os.environ, DISCREGRID_B200_LIB=EMU, DG_REHEARSAL="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29641")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29641", str(script)], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0 and "MULTI_OK 2" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
