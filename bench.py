@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--resolution", type=int, default=0, help="override the SDF grid resolution (diagnostics)")
     ap.add_argument("--interp-resolution", type=int, default=0, help="override the interpolate grid resolution (diagnostics)")
+    ap.add_argument("--target-resolution", type=int, default=256, help="grid resolution of the target-config leg (diagnostics / rehearsal; the config is 256)")
+    ap.add_argument("--real-resolution", type=int, default=0, help="override the grid resolution of the reference-mesh leg (diagnostics / rehearsal)")
     ap.add_argument("--no-interp", action="store_true", help="skip the interpolate half (diagnostics / profiling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (diagnostics / profiling)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (diagnostics / profiling)")
@@ -59,15 +61,22 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ helpers
+def scratch_dir():
+    """for the few hundred MB the CPU legs exchange with the reference class through files: the repo's own volume (build/ is git-ignored);
+    /tmp can be a slow copy-on-write layer"""
+    d = os.path.join(ROOT, "build")
+    try:
+        os.makedirs(d, exist_ok=True)
+        return d
+    except OSError:
+        return "/tmp"
+
+
 def reduce_field_leg(capi, desc, values, cells, lo, hi, with_reference, tmp_dir=None):
     """reduceField(field, lo <= v <= hi) (cmd/generate_density_map/main.cpp:141-144) on a sampled field -- host code on
     both sides: dg_reduce_field (index passes, multithreaded) vs the reference class's own reduceField (oracle/_ref, when built)."""
-    if tmp_dir is None:                                     # the repo's own volume (build/ is git-ignored); /tmp can be a slow copy-on-write layer
-        tmp_dir = os.path.join(ROOT, "build")
-        try:
-            os.makedirs(tmp_dir, exist_ok=True)
-        except OSError:
-            tmp_dir = "/tmp"
+    if tmp_dir is None:
+        tmp_dir = scratch_dir()
     keep = np.ascontiguousarray((lo <= values) & (values <= hi) & (values != np.finfo(np.float64).max), np.uint8)
     n_grid_cells = int(desc.resolution[0]) * int(desc.resolution[1]) * int(desc.resolution[2])
     best, out = None, None
@@ -479,13 +488,13 @@ def main():
             os.environ["OMP_NUM_THREADS"] = os.environ.get("DG_CPU_THREADS") or str(len(os.sched_getaffinity(0)))
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             from oracle_api import Oracle, RefGrid, have_ref_grid
-            cres = [128, 128, 128]                               # a 256^3 .cdf is 3 GB on disk: the CPU arm reads the 128^3 field of the same mesh
+            cres = [min(128, r_) for r_ in ires]                 # a 256^3 .cdf is 3 GB on disk: the CPU arm reads the 128^3 field of the same mesh
             cgrid = dg.CubicLagrangeDiscreteGrid(mn, mx, cres)
             cgrid.addFunction(dg.MeshSignedDistance(md))
             nq_cpu = 2_000_000
             xc = np.ascontiguousarray(splitmix_points(nq_cpu, INTERP["seed"], mn, mx))
             if have_ref_grid():
-                tmpf = "/tmp/_dg_bench_field.cdf"
+                tmpf = os.path.join(scratch_dir(), f"_dg_bench_field_{os.getpid()}.cdf")
                 cgrid.save(tmpf)
                 rg = RefGrid(tmpf)
                 rg.interpolate(0, xc[:100000], grad=True)
@@ -498,7 +507,7 @@ def main():
                 kind = "port"
             pg, gg = cgrid.interpolate(0, xc, gradient=True)
             interp["cpu_baseline"] = {"value": nq_cpu / t_cpu / 1e6, "unit": "Mqueries/s", "kind": kind, "cores": int(os.environ["OMP_NUM_THREADS"]),
-                                      "sample": f"{nq_cpu} of the 10M queries on the 128^3 field of the same mesh (OpenMP parallel for, value+gradient)",
+                                      "sample": f"{nq_cpu} of the 10M queries on the {cres[0]}^3 field of the same mesh (OpenMP parallel for, value+gradient)",
                                       "bit_exact_vs_gpu": bool(np.array_equal(pr.view(np.uint64), pg.view(np.uint64)) and np.array_equal(gr.view(np.uint64), gg.view(np.uint64)))}
             del cgrid
 
@@ -508,17 +517,18 @@ def main():
         tmesh = dg.bumpy_torus()                               # 250 x 200 quads = exactly 100,000 triangles
         tmd = dg.TriangleMeshDistance(tmesh)
         tmn, tmx = dg.generate_sdf_domain(tmesh.vertices)
-        tdesc = dg.grid_desc(tmn, tmx, [256, 256, 256])
+        tres = [args.target_resolution] * 3
+        tdesc = dg.grid_desc(tmn, tmx, tres)
         tn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(tdesc.resolution, C.byref(tn))); tn = tn.value
         tsampler = make_sampler(tmd, tdesc, tn)
         tfull = torch.empty(tsampler.sh.padded, dtype=torch.float64, device=dev)
         t_ms, _ = timed(lambda: tsampler.step(tfull), 3, 1)
         t_ms = float(np.mean(t_ms))
-        target = {"workload": "north_star target: 256^3 grid (118,425,857 nodes), synthetic bumpy torus with exactly 100,000 triangles, "
+        target = {"workload": f"north_star target: {tres[0]}^3 grid ({tn} nodes), synthetic bumpy torus with exactly 100,000 triangles, "
                               "strong scaling, sharding as config.parallelism", "ms_per_step": t_ms, "value": tn / (t_ms * 1e-3), "unit": "nodes/s",
                   "n_gpus": world, "sharded_equals_single_launch": same_as_single_launch(tmd, tdesc, tn, tfull)}
         if rank == 0 and world == 1 and not args.no_cpu:
-            rates, info = cpu_sample_rate(tmesh, tmn, tmx, [256, 256, 256], args.cpu_seconds)
+            rates, info = cpu_sample_rate(tmesh, tmn, tmx, tres, args.cpu_seconds)
             target["cpu_baseline"] = dict(info, value=float(np.mean(rates)), unit="nodes/s")
         del tfull, tsampler, tmd
 
@@ -534,6 +544,7 @@ def main():
             rmesh = dg.TriangleMesh(path)
             t0 = time.perf_counter(); rmd = dg.TriangleMeshDistance(rmesh); t_create = time.perf_counter() - t0
             rmn, rmx = dg.generate_sdf_domain(rmesh.vertices)
+            r3 = args.real_resolution or r3
             rdesc = dg.grid_desc(rmn, rmx, [r3] * 3)
             rn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(rdesc.resolution, C.byref(rn))); rn = rn.value
             rs = make_sampler(rmd, rdesc, rn)
@@ -579,7 +590,7 @@ def main():
             coeff_h = full[:n_nodes].cpu().numpy()
             t_cpu, n_cpu, ok = 0.0, 0, True
             for k in range(8):                                 # eight 192-node windows spread over the node index space
-                l0 = int((k + 0.5) * n_nodes / 8); l1 = l0 + 192
+                l0 = int((k + 0.5) * n_nodes / 8); l1 = min(l0 + 192, n_nodes)
                 t0 = time.perf_counter()
                 ref = orc.density_map(gd, r, coeff_h, h_dm, 1000.0, False, l0, l1)
                 t_cpu += time.perf_counter() - t0; n_cpu += l1 - l0

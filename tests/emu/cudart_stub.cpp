@@ -10,7 +10,7 @@ extern "C" {
 
 cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }                  // every rehearsal rank "owns" the one emulated device
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA runtime error"; }
