@@ -31,6 +31,11 @@
 #include <mutex>
 
 #include "dg_launch.h"       // DG_KERNEL_LAUNCH: <<<>>> on the device, fibers under tests/emu (DG_EMU)
+#ifdef DG_EMU
+#define DG_EMU_COUNT(i) (dg_emu::g_counters[(i)]++)        // event counters of the emulation (tests/emu, tools): nothing on the device
+#else
+#define DG_EMU_COUNT(i)
+#endif
 
 namespace dgb {
 
@@ -349,6 +354,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
         const int w_leafx = K1_LEAF_WEIGHT * __popc(K1_LEAF_FILTER ? bit2 : (bit0 & ~bit1));
 #endif
         const int w_max = max(max(w_node, w_pop), max(w_leaff, w_leafx));
+        DG_EMU_COUNT(0);
         if (w_pop == w_max) {
             if (state == POP) {
                 // deferred siblings: the reference's second `if (d < result.distance)` (:549, :557) with the updated best
@@ -356,10 +362,12 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                 for (int attempt = 0; attempt < K1_POP_TRIES; attempt++) {
                     if (sp == 0) { state = DONE; break; }
                     sp--;
+                    DG_EMU_COUNT(5);
                     const float df = stack_d[sp * stride];
                     bool visit = (df + E < best_lo);                           // certainly d < best
                     const bool skip = (df - E >= best_hi);                     // certainly d >= best
                     if (!K1_FILTER || !(visit || skip)) {                      // undecided in fp32: the reference's fp64 value
+                        DG_EMU_COUNT(6);
                         const unsigned r = stack_rng[sp * stride];
                         const int rb = (int)(r & 0x01ffffffu), rd = (int)((r >> 25) & 31u);
                         const int re = rb + (n_tri >> rd) + (int)((r >> 30) & 1u);
@@ -378,7 +386,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                             const float* bx = reinterpret_cast<const float*>(M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE + 2) + (is_left ? 0 : 6);
                             const float gx = fmaxf(fmaxf(__ldg(bx) - qx, qx - __ldg(bx + 3)), 0.f), gy = fmaxf(fmaxf(__ldg(bx + 1) - qy, qy - __ldg(bx + 4)), 0.f),
                                         gz = fmaxf(fmaxf(__ldg(bx + 2) - qz, qz - __ldg(bx + 5)), 0.f);
-                            if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) continue;   // visiting it could not change anything
+                            if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
                         }
 #endif
                         b = rb; depth = rd; e = re;
@@ -395,6 +403,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
           for (int rep = 0;; rep++) {
 #endif
             if (state == NODE) {                                                // internal (:537-561)
+                DG_EMU_COUNT(1);
                 const int m = (b + e) >> 1;
                 bool left_first, go_first, go_second = false, defer = true;
                 float d_second_f;
@@ -453,6 +462,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                 }
 #endif
                 if (!decided) {                                                 // fp64, exactly the reference
+                    DG_EMU_COUNT(2);
                     const double* sp8 = reinterpret_cast<const double*>(M.spheres + m);
                     const double2 a0 = ldg2(sp8), a1 = ldg2(sp8 + 2), a2 = ldg2(sp8 + 4), a3 = ldg2(sp8 + 6);
                     const double d_left = sphere_dist(px, py, pz, a0.x, a0.y, a1.x, a1.y);      // :539
@@ -469,6 +479,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                 depth++;
                 if (go_first) {                        // visit first now; second is re-tested when popped (:545-551)
                     if (defer) {
+                        DG_EMU_COUNT(9);
                         stack_rng[sp * stride] = left_first ? pack_range(m, e, depth, n_tri, false) : pack_range(b, m, depth, n_tri, true);
                         stack_d[sp * stride] = d_second_f;
                         sp++;
@@ -497,12 +508,14 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
         } else {
             if (state == (K1_LEAF_FILTER ? LEAFX : LEAF)) {                     // leaf (:517-534)
                 double s, t; int ent;
+                DG_EMU_COUNT(3);
                 #if K1_FAST_DIV
                 const double d2 = tri_dist2(M.leaves + b, M.recips + b, px, py, pz, s, t, ent);
 #else
                 const double d2 = tri_dist2(M.leaves + b, px, py, pz, s, t, ent);
 #endif
                 if (d2 < best_sq) {
+                    DG_EMU_COUNT(4);
                     best = sqrt(d2);
                     best_sq = best * best;
                     best_lo = __double2float_rd(best); best_hi = __double2float_ru(best);

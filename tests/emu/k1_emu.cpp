@@ -96,6 +96,7 @@ int emu_build_cells(const double* gd, const uint32_t* res, uint64_t c_begin, uin
     GridDev g; if (!to_grid(gd, res, g)) return -1;
     return (int)k1_launch_build_cells(g, c_begin, c_end - c_begin, cells, nullptr);
 }
+void emu_counters(unsigned long long* out /*32*/, int reset) { for (int i = 0; i < 32; i++) { out[i] = dg_emu::g_counters[i]; if (reset) dg_emu::g_counters[i] = 0; } }
 int emu_knobs(int* fast_div, int* vote_redux) { *fast_div = K1_FAST_DIV; *vote_redux = K1_VOTE_REDUX; return 0; }
 
 }  // extern "C"
