@@ -31,6 +31,17 @@
 #include <mutex>
 
 #include "dg_launch.h"       // DG_KERNEL_LAUNCH: <<<>>> on the device, fibers under tests/emu (DG_EMU)
+#if K1_BRICK_AUTO
+#define SEG_BF(S) (1u << (S).lf)
+#define SEG_BM(S) (1u << (S).lm)
+#define SEG_BS(S) (32u >> ((S).lf + (S).lm))
+#define LAY_BS(L, a) (32u >> ((L).lf[a] + (L).lm[a]))
+#else
+#define SEG_BF(S) ((unsigned)K1_BRICK_F)
+#define SEG_BM(S) ((unsigned)K1_BRICK_M)
+#define SEG_BS(S) ((unsigned)K1_BRICK_S)
+#define LAY_BS(L, a) ((unsigned)K1_BRICK_S)
+#endif
 #ifdef DG_EMU
 #define DG_EMU_COUNT(i) (dg_emu::g_counters[(i)]++)        // event counters of the emulation (tests/emu, tools): nothing on the device
 #else
@@ -557,10 +568,17 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
     const unsigned tf = t % S.tiles_f; t /= S.tiles_f;
     const unsigned tm = t % S.tiles_m; const unsigned ts = t / S.tiles_m;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#if K1_BRICK_AUTO
+    const unsigned f = tf * (SEG_BF(S) * (unsigned)(K1_THREADS / 32)) + warp * SEG_BF(S) + (lane & (SEG_BF(S) - 1u));
+    const unsigned m = tm * SEG_BM(S) + ((lane >> S.lf) & (SEG_BM(S) - 1u));
+    const unsigned lane_s = lane >> (S.lf + S.lm);
+    const unsigned sl = S.s0 + ts * S.pl_stride * SEG_BS(S) + lane_s;
+#else
     const unsigned f = tf * (unsigned)(K1_BRICK_F * (K1_THREADS / 32)) + warp * (unsigned)K1_BRICK_F + (lane % K1_BRICK_F);
     const unsigned m = tm * (unsigned)K1_BRICK_M + ((lane / K1_BRICK_F) % K1_BRICK_M);
     const unsigned lane_s = lane / (K1_BRICK_F * K1_BRICK_M);
     const unsigned sl = S.s0 + ts * S.pl_stride * (unsigned)K1_BRICK_S + lane_s;
+#endif
     const unsigned l = S.l_base + (sl * S.Dm + m) * S.Df + f;
     const bool alive = (f < S.Df) && (m < S.Dm) && (sl < S.s1) && (l >= w.l_begin) && (l < w.l_end);
 
@@ -583,7 +601,7 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
     if (!alive) return;
     double dist, qx, qy, qz; int tri;
     finish_query(mesh.leaves, normals, r, px, py, pz, true, dist, qx, qy, qz, tri);
-    const unsigned out_idx = w.compact ? S.out_base + ((ts * (unsigned)K1_BRICK_S + lane_s) * S.Dm + m) * S.Df + f : l - w.l_begin;
+    const unsigned out_idx = w.compact ? S.out_base + ((ts * SEG_BS(S) + lane_s) * S.Dm + m) * S.Df + f : l - w.l_begin;
     out[out_idx] = (sign == 1.0) ? dist : sign * dist;           // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
 }
 
@@ -668,6 +686,28 @@ cudaError_t k1_configure(int stack_depth)
 #endif
 }
 
+#if K1_BRICK_AUTO
+// brick shape of node array `kind`: (lf, lm, ls) with lf + lm + ls = 5 and lf >= 1 minimising the physical diagonal of the 32 nodes.
+// Node spacing along (f, m, s): vertices (cx, cy, cz); x-edge nodes (cx/2, cy, cz); y-edge (cy/2, cz, cx); z-edge (cz/2, cx, cy).
+static void choose_brick(const GridDev& g, int kind, unsigned& lf, unsigned& lm)
+{
+    const double c[3] = {g.cell[0], g.cell[1], g.cell[2]};
+    const double h[4][3] = {{c[0], c[1], c[2]}, {0.5 * c[0], c[1], c[2]}, {0.5 * c[1], c[2], c[0]}, {0.5 * c[2], c[0], c[1]}};
+    lf = 2; lm = 2;                                               // 4 x 4 x 2: kept on ties
+    auto diag2 = [&](unsigned a, unsigned b) { const double x = (double)(1u << a) * h[kind][0], y = (double)(1u << b) * h[kind][1],
+                                                              z = (double)(32u >> (a + b)) * h[kind][2]; return x * x + y * y + z * z; };
+    double best = diag2(lf, lm);
+    for (unsigned a = 1; a <= 4; a++)
+        for (unsigned b = 0; a + b <= 5; b++) {
+            const double d = diag2(a, b);
+            if (d < best * (1.0 - 1e-9)) { best = d; lf = a; lm = b; }
+        }
+}
+#define SEG_SET_BRICK(S, g) choose_brick((g), (S).kind, (S).lf, (S).lm)
+#else
+#define SEG_SET_BRICK(S, g)
+#endif
+
 // Splits [l_begin, l_begin+count) into the (at most four) node arrays it touches and tiles whole slow-planes of each.
 cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double sign, uint64_t l_begin, uint64_t count,
                                    double* d_out, cudaStream_t stream)
@@ -693,9 +733,10 @@ cudaError_t k1_launch_sample_nodes(const DeviceBvh& m, const GridDev& g, double 
         S.pl_stride = 1u; S.out_base = 0u;
         S.s0 = (unsigned)((a - base[k]) / plane);
         S.s1 = (unsigned)((b - 1 - base[k]) / plane) + 1;
-        const unsigned bf = K1_BRICK_F * (K1_THREADS / 32);
-        S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + K1_BRICK_M - 1) / K1_BRICK_M;
-        const unsigned tiles_s = (S.s1 - S.s0 + K1_BRICK_S - 1) / K1_BRICK_S;
+        SEG_SET_BRICK(S, g);
+        const unsigned bf = SEG_BF(S) * (K1_THREADS / 32);
+        S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + SEG_BM(S) - 1) / SEG_BM(S);
+        const unsigned tiles_s = (S.s1 - S.s0 + SEG_BS(S) - 1) / SEG_BS(S);
         S.block_begin = blocks;
         blocks += S.tiles_f * S.tiles_m * tiles_s;
     }
@@ -719,9 +760,10 @@ cudaError_t k1_launch_sample_slab(const DeviceBvh& m, const GridDev& g, double s
         S.kind = k; S.l_base = (unsigned)base[k];
         S.Ds = dims[k][0]; S.Dm = dims[k][1]; S.Df = dims[k][2];
         S.s0 = plane_begin[k]; S.s1 = plane_end[k]; S.pl_stride = 1u; S.out_base = 0u;
-        const unsigned bf = K1_BRICK_F * (K1_THREADS / 32);
-        S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + K1_BRICK_M - 1) / K1_BRICK_M;
-        const unsigned tiles_s = (S.s1 - S.s0 + K1_BRICK_S - 1) / K1_BRICK_S;
+        SEG_SET_BRICK(S, g);
+        const unsigned bf = SEG_BF(S) * (K1_THREADS / 32);
+        S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + SEG_BM(S) - 1) / SEG_BM(S);
+        const unsigned tiles_s = (S.s1 - S.s0 + SEG_BS(S) - 1) / SEG_BS(S);
         S.block_begin = blocks;
         blocks += S.tiles_f * S.tiles_m * tiles_s;
     }
@@ -745,13 +787,16 @@ bool k1_interleaved_layout(const GridDev& g, unsigned n_parts, InterleavedLayout
     uint64_t base[4]; unsigned dims[4][3];
     node_arrays(g, base, dims);
     L.n_parts = n_parts; L.slot_elems = 0;
-    for (int a = 0; a < 4; a++) { L.pairs[a] = (dims[a][0] + K1_BRICK_S - 1) / K1_BRICK_S; L.plane[a] = dims[a][1] * dims[a][2]; }
+#if K1_BRICK_AUTO
+    for (int a = 0; a < 4; a++) choose_brick(g, a, L.lf[a], L.lm[a]);
+#endif
+    for (int a = 0; a < 4; a++) { L.pairs[a] = (dims[a][0] + LAY_BS(L, a) - 1) / LAY_BS(L, a); L.plane[a] = dims[a][1] * dims[a][2]; }
     for (unsigned r = 0; r < n_parts; r++) {
         uint64_t off = 0;
         for (int a = 0; a < 4; a++) {
             L.off[a][r] = (unsigned)off;
             const uint64_t mine = (L.pairs[a] > r) ? (L.pairs[a] - r + n_parts - 1) / n_parts : 0;      // pairs r, r + n_parts, ...
-            off += mine * K1_BRICK_S * (uint64_t)L.plane[a];
+            off += mine * LAY_BS(L, a) * (uint64_t)L.plane[a];
         }
         if (off > 0xffffffffull) return false;
         if (off > L.slot_elems) L.slot_elems = off;
@@ -774,9 +819,12 @@ cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, d
         K1Segment& S = w.seg[w.nseg++];
         S.kind = k; S.l_base = (unsigned)base[k];
         S.Ds = dims[k][0]; S.Dm = dims[k][1]; S.Df = dims[k][2];
-        S.s0 = part * K1_BRICK_S; S.s1 = S.Ds; S.pl_stride = L.n_parts; S.out_base = L.off[k][part];
-        const unsigned bf = K1_BRICK_F * (K1_THREADS / 32);
-        S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + K1_BRICK_M - 1) / K1_BRICK_M;
+#if K1_BRICK_AUTO
+        S.lf = L.lf[k]; S.lm = L.lm[k];
+#endif
+        S.s0 = part * SEG_BS(S); S.s1 = S.Ds; S.pl_stride = L.n_parts; S.out_base = L.off[k][part];
+        const unsigned bf = SEG_BF(S) * (K1_THREADS / 32);
+        S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + SEG_BM(S) - 1) / SEG_BM(S);
         S.block_begin = blocks;
         blocks += S.tiles_f * S.tiles_m * mine;
     }
@@ -794,9 +842,10 @@ __host__ __device__ inline unsigned long long interleaved_slot_of(const GridDev&
     const unsigned long long rel = l - ((a == 0) ? 0ull : ((a == 1) ? b1 : ((a == 2) ? b2 : b3)));
     const unsigned plane = L.plane[a];
     const unsigned s = (unsigned)(rel / plane), inplane = (unsigned)(rel - (unsigned long long)s * plane);
-    const unsigned pair = s / K1_BRICK_S, j = pair / L.n_parts;
+    const unsigned bs = LAY_BS(L, a);
+    const unsigned pair = s / bs, j = pair / L.n_parts;
     part = pair % L.n_parts;
-    return (unsigned long long)L.off[a][part] + (unsigned long long)(j * K1_BRICK_S + (s % K1_BRICK_S)) * plane + inplane;
+    return (unsigned long long)L.off[a][part] + (unsigned long long)(j * bs + (s % bs)) * plane + inplane;
 }
 
 namespace {

@@ -76,8 +76,20 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 
 // One of the four row-major 3-D node arrays of the grid (vertex nodes, x-/y-/z-edge nodes), restricted to the
 // slow-planes [s0, s1) that a node range touches.  l = l_base + (s*Dm + m)*Df + f.
+// K1_BRICK_AUTO 1: the warp's brick is chosen per node array at launch time -- the power-of-two shape (f x m x s, 32 nodes) whose PHYSICAL
+// diagonal is shortest -- instead of the fixed K1_BRICK_F x K1_BRICK_M x K1_BRICK_S.  On cubic cells that is the default 4 x 4 x 2
+// (x-edge arrays: their node spacing along f is half a cell); on strongly anisotropic cells (a flat bounding box sampled with a cubic
+// resolution) a flatter brick keeps the 32 queries closer together (CPU schedule model: -6 % issued instructions on the bench torus).
+// Off until measured on the GPU; checked against the oracle by the emulated test build.
+#ifndef K1_BRICK_AUTO
+#define K1_BRICK_AUTO 0
+#endif
+
 struct K1Segment {
     unsigned l_base, Ds, Dm, Df, s0, s1, tiles_f, tiles_m, block_begin;
+#if K1_BRICK_AUTO
+    unsigned lf, lm;               // log2 of the brick's extents along f and m (s extent = 32 >> (lf + lm))
+#endif
     unsigned pl_stride;            // plane groups between consecutive brick layers (1 = contiguous slab, n_parts = interleaved deal)
     unsigned out_base;             // interleaved mode: element offset of this array inside the part's exchange slot
     int kind;                      // 0 vertex (s,m,f)=(k,j,i); 1 x-edge (k,j,2i+b); 2 y-edge (i,k,2j+b); 3 z-edge (j,i,2k+b)
@@ -131,6 +143,9 @@ struct InterleavedLayout {
     unsigned pairs[4];             // plane pairs of array a
     unsigned plane[4];             // elements per plane of array a
     uint64_t slot_elems = 0;       // elements per slot (max over parts)
+#if K1_BRICK_AUTO
+    unsigned lf[4], lm[4];         // brick shape of array a (its plane groups are 32 >> (lf + lm) planes thick)
+#endif
 };
 bool k1_interleaved_layout(const GridDev& g, unsigned n_parts, InterleavedLayout& L);
 cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, double sign, const InterleavedLayout& L, unsigned part,
