@@ -179,3 +179,16 @@ def test_emulated_queries_on_awkward_meshes_vs_reference_header(emu, n_tri, scal
         same_p = (near.view(np.uint64) == want_near.view(np.uint64)) | (np.isnan(near) & np.isnan(want_near))
         assert same_p[found].all()
     emu.lib.emu_mesh_destroy(h)
+
+
+def test_tie_rich_fuzz_against_reference_header():
+    """a short run of tools/k1_fuzz.py (regular coplanar grids, cubes / octahedra with lattice-aligned queries, duplicated triangles,
+    slivers, random soups at random scales): emulated kernel == reference header in distance bits, nearest point, entity, triangle id"""
+    import subprocess
+    import sys
+    from oracle_api import REF_SO
+    so = LIBS[0]
+    if not os.path.exists(REF_SO) or not os.path.exists(so):
+        pytest.skip("needs oracle/_ref/libdgref.so and build/bin/libk1emu.so")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k1_fuzz.py"), "42", "7", so], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
