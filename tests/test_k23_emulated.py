@@ -97,3 +97,15 @@ def test_emulated_density_map_equals_reference_tool_output(emu, orc):
     assert emu.lib.emu_density_map(h, 0.15, 1000.0, 0, l0, l1, _p(part, _dp)) == 0
     assert bits_equal(part, want) and (part == DBL_MAX).any()
     emu.lib.emu_field_destroy(h)
+
+
+def test_interpolate_fuzz_against_reference_class():
+    """a short run of tools/k2_fuzz.py: random anisotropic grids and fields (DBL_MAX sentinels, reduced fields), queries on cell faces / domain
+    corners / outside / non-finite -- emulated interpolate kernel == the reference class, value, gradient and value-only, bit for bit"""
+    import subprocess
+    import sys
+    from oracle_api import REF_GRID_SO
+    if not os.path.exists(REF_GRID_SO) or not os.path.exists(LIBS[0]):
+        pytest.skip("needs oracle/_ref/libdiscregrid_ref.so and build/bin/libk23emu.so")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k2_fuzz.py"), "24", "5"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
