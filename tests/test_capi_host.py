@@ -200,41 +200,22 @@ def test_slab_sharding_partition(dg):
                     assert ((e - base[a]) // plane[a]) % 2 == 0                                  # interior boundaries on plane pairs
 
 
-def test_allgather_slabs_gloo_world2(tmp_path):
+def test_exchanges_gloo_world2(tmp_path):
+    """N > 1 host logic on CPU, two gloo ranks, one torchrun for all three shardings' exchange steps: every rank fills what it owns with a
+    known function of the node id, runs the sampler's own collective call, and must end up with the whole array --
+    node-id chunks (allgather_rows), slabs (allgather_slabs), interleaved plane pairs with 1 and 2 parts per rank (allgather_slots +
+    the host statement of the slot layout)."""
     script = tmp_path / "w.py"
     script.write_text(f'''
-import os, sys, numpy as np, torch, torch.distributed as dist
+import os, sys, ctypes as C, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, {ROOT!r})
 import discregrid_b200 as dg
-from discregrid_b200.distributed import SlabSharding, allgather_slabs
+from discregrid_b200 import _capi as capi
+from discregrid_b200.distributed import make_sharding, allgather_rows, SlabSharding, allgather_slabs, allgather_slots, interleaved_node_slots
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-desc = dg.grid_desc([0, 0, 0], [1, 2, 3], (9, 5, 7))
-sh = SlabSharding(desc, world)
-full = torch.full((sh.padded,), -1.0, dtype=torch.float64)
-for (b, e) in sh.ranges[rank]:
-    full[b:e] = torch.arange(b, e, dtype=torch.float64) * 0.25 - 3.0
-allgather_slabs(full, sh)
-want = torch.arange(sh.n, dtype=torch.float64) * 0.25 - 3.0
-assert torch.equal(full[:sh.n], want), (rank, (full[:sh.n] != want).nonzero()[:5])
-dist.barrier()
-if rank == 0: print("SLAB_OK")
-''')
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29615")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29615", str(script)], capture_output=True, text=True, env=env, timeout=300)
-    assert r.returncode == 0 and "SLAB_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
-
-def test_allgather_rows_gloo_world2(tmp_path):
-    """N > 1 host logic on CPU: two gloo ranks fill their chunks with a known function of the node id and gather."""
-    script = tmp_path / "w.py"
-    script.write_text(f'''
-import os, sys, numpy as np, torch, torch.distributed as dist
-sys.path.insert(0, {ROOT!r})
-from discregrid_b200.distributed import make_sharding, allgather_rows
-dist.init_process_group("gloo")
-rank, world = dist.get_rank(), dist.get_world_size()
+# ---- node-id chunks
 n = 100003
 sh = make_sharding(n, world, rows=3, align=64)
 full = torch.full((sh.padded,), -1.0, dtype=torch.float64)
@@ -242,74 +223,35 @@ for (j, b, e) in sh.chunks_of(rank):
     full[b:e] = torch.arange(b, e, dtype=torch.float64) * 0.5 + 1.0      # "node value" = f(node id)
 allgather_rows(full, sh)
 want = torch.arange(n, dtype=torch.float64) * 0.5 + 1.0
-assert torch.equal(full[:n], want), (rank, (full[:n] != want).nonzero()[:5])
-dist.barrier()
-if rank == 0: print("GLOO_OK")
-''')
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29613", str(script)], capture_output=True, text=True, env=env, timeout=300)
-    assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+assert torch.equal(full[:n], want), ("rows", rank, (full[:n] != want).nonzero()[:5])
 
-
-@pytest.mark.parametrize("res,world", [((9, 5, 7), 2), ((4, 4, 4), 3), ((3, 2, 1), 8), ((16, 16, 16), 16), ((6, 7, 8), 1)])
-def test_interleaved_layout_is_a_bijection_into_the_slots(dg, res, world):
-    """dg_interleaved_node_slots (host, no GPU; the function the unpack kernel also runs): every node lands in exactly one slot
-    position < slot_elems, pair p of each node array belongs to part p % world, and the parts' loads differ by at most one plane pair
-    per node array"""
-    import ctypes as C
-    from discregrid_b200 import _capi as capi
-    from discregrid_b200.distributed import interleaved_node_slots
-    desc = dg.grid_desc([0, 0, 0], [1, 2, 3], res)
-    n = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(n))); n = n.value
-    se = C.c_uint64(); capi.check(capi.lib.dg_interleaved_slot_elems(C.byref(desc), world, C.byref(se))); se = se.value
-    part, pos = interleaved_node_slots(desc, world, 0, n)
-    assert part.max() < world and pos.max() < se
-    key = part.astype(np.uint64) * np.uint64(se) + pos
-    assert len(np.unique(key)) == n                                            # no two nodes share a slot position
-    nx, ny, nz = res
-    # the vertex array: node (i, j, k) -> z-plane k, pair k // 2 -> part (k // 2) % world
-    k = np.arange((nx + 1) * (ny + 1) * (nz + 1)) // ((nx + 1) * (ny + 1))
-    assert np.array_equal(part[:len(k)], (k // 2) % world)
-    loads = np.bincount(part, minlength=world)
-    planes = [(nx + 1) * (ny + 1), 2 * nx * (ny + 1), 2 * ny * (nz + 1), 2 * nz * (nx + 1)]
-    assert loads.max() - loads.min() <= 2 * sum(planes)
-    assert capi.lib.dg_interleaved_node_slots(C.byref(desc), world, 0, n + 1, None, None) == capi.DG_ERR_INVALID
-    assert capi.lib.dg_interleaved_node_slots(C.byref(desc), 17, 0, n, None, None) == capi.DG_ERR_INVALID
-
-
-@pytest.mark.parametrize("splits", [1, 2])
-def test_allgather_slots_gloo_world2(tmp_path, splits):
-    """N > 1 host logic of the interleaved sharding on CPU: two gloo ranks fill the slots of their parts (splits consecutive parts per
-    rank) with f(node id) at the positions the host layout names, exchange them with the sampler's own collective call, and unpack
-    through the same layout."""
-    script = tmp_path / "w.py"
-    script.write_text(f'''
-import os, sys, ctypes as C, numpy as np, torch, torch.distributed as dist
-sys.path.insert(0, {ROOT!r})
-import discregrid_b200 as dg
-from discregrid_b200 import _capi as capi
-from discregrid_b200.distributed import allgather_slots, interleaved_node_slots
-dist.init_process_group("gloo")
-rank, world = dist.get_rank(), dist.get_world_size()
-splits = {splits}
-parts = world * splits
+# ---- slabs
 desc = dg.grid_desc([0, 0, 0], [1, 2, 3], (9, 5, 7))
-n = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(n))); n = n.value
-se = C.c_uint64(); capi.check(capi.lib.dg_interleaved_slot_elems(C.byref(desc), parts, C.byref(se))); se = se.value
-part, pos = interleaved_node_slots(desc, parts, 0, n)
-f = np.arange(n, dtype=np.float64) * 0.25 - 3.0
-slots = torch.full((parts * se,), -1.0, dtype=torch.float64)
-mine = (part // splits) == rank                          # rank r owns parts r*splits .. r*splits + splits - 1
-slots[torch.from_numpy(part[mine].astype(np.int64) * se + pos[mine].astype(np.int64))] = torch.from_numpy(f[mine])
-allgather_slots(slots, se * splits, rank, world)
-got = slots[torch.from_numpy(part.astype(np.int64) * se + pos.astype(np.int64))].numpy()
-assert np.array_equal(got, f), (rank, np.nonzero(got != f)[0][:5])
+ss = SlabSharding(desc, world)
+full = torch.full((ss.padded,), -1.0, dtype=torch.float64)
+for (b, e) in ss.ranges[rank]:
+    full[b:e] = torch.arange(b, e, dtype=torch.float64) * 0.25 - 3.0
+allgather_slabs(full, ss)
+want = torch.arange(ss.n, dtype=torch.float64) * 0.25 - 3.0
+assert torch.equal(full[:ss.n], want), ("slabs", rank, (full[:ss.n] != want).nonzero()[:5])
+
+# ---- interleaved plane pairs, `splits` consecutive parts per rank
+nn = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(nn))); nn = nn.value
+f = np.arange(nn, dtype=np.float64) * 0.25 - 3.0
+for splits in (1, 2):
+    parts = world * splits
+    se = C.c_uint64(); capi.check(capi.lib.dg_interleaved_slot_elems(C.byref(desc), parts, C.byref(se))); se = se.value
+    part, pos = interleaved_node_slots(desc, parts, 0, nn)
+    slots = torch.full((parts * se,), -1.0, dtype=torch.float64)
+    mine = (part // splits) == rank                          # rank r owns parts r*splits .. r*splits + splits - 1
+    slots[torch.from_numpy(part[mine].astype(np.int64) * se + pos[mine].astype(np.int64))] = torch.from_numpy(f[mine])
+    allgather_slots(slots, se * splits, rank, world)
+    got = slots[torch.from_numpy(part.astype(np.int64) * se + pos.astype(np.int64))].numpy()
+    assert np.array_equal(got, f), ("slots", splits, rank, np.nonzero(got != f)[0][:5])
 dist.barrier()
-if rank == 0: print("SLOTS_OK")
+if rank == 0: print("EXCHANGES_OK")
 ''')
-    port = str(29617 + splits)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29615")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", port, str(script)], capture_output=True, text=True, env=env, timeout=300)
-    assert r.returncode == 0 and "SLOTS_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+                        "--master-port", "29615", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "EXCHANGES_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

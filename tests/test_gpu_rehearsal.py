@@ -94,7 +94,7 @@ def test_bench_runs_end_to_end_two_ranks(sharding):
         pytest.skip("build/bin/libdgemu.so not built (make cpp)")
     port = {"chunks": "29661", "interleaved": "29663"}[sharding]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", port,
-                        os.path.join(ROOT, "tests", "emu", "bench_rehearsal.py"), "--gpus", "2", "--sharding", sharding] + TOY, cwd=ROOT,
+                        os.path.join(ROOT, "tests", "emu", "bench_rehearsal.py"), "--gpus", "2", "--sharding", sharding, "--no-real"] + TOY, cwd=ROOT,
                        env=dict(os.environ, DISCREGRID_B200_LIB=EMU, MASTER_ADDR="127.0.0.1", MASTER_PORT=port), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     d = _bench_line(r.stdout)
