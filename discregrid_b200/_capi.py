@@ -33,6 +33,12 @@ if not os.path.exists(LIB_PATH):
                       "discregrid_b200 has no pure-Python / CPU fallback")
 
 lib = C.CDLL(LIB_PATH)
+# The test suite can build the whole library with every kernel emulated on the CPU (tests/emu -> build/bin/libdgemu.so) to rehearse the GPU
+# tests.  That build is test infrastructure: the package refuses it unless the rehearsal says so explicitly, so that no user -- and no
+# benchmark -- can end up on it by accident.  There is no CPU fallback.
+if hasattr(lib, "emu_mesh_create") and os.environ.get("DG_ALLOW_EMULATED_LIBRARY") != "1":
+    raise ImportError(f"{LIB_PATH} is the CPU-emulated TEST build of the library (tests/emu); discregrid_b200 only runs on the CUDA build "
+                      "(set DG_ALLOW_EMULATED_LIBRARY=1 only from the test rehearsal)")
 
 _dp, _u32p, _i32p, _u64p, _vp = (C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_uint64), C.c_void_p)

@@ -21,7 +21,7 @@ SKIP = "not full_size and not slab_parts and not interleaved_parts and not refer
 def test_gpu_suite_passes_on_the_emulated_library():
     if not os.path.exists(EMU):
         pytest.skip("build/bin/libdgemu.so not built (make cpp)")
-    env = dict(os.environ, DISCREGRID_B200_LIB=EMU, LD_PRELOAD=EMU)
+    env = dict(os.environ, DISCREGRID_B200_LIB=EMU, LD_PRELOAD=EMU, DG_ALLOW_EMULATED_LIBRARY="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-k", SKIP, "-p", "no:cacheprovider"] + FILES,
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
@@ -37,7 +37,7 @@ def test_multi_gpu_worker_on_two_gloo_ranks(tmp_path):
     from test_gpu_multi import WORKER
     script = tmp_path / "w.py"
     script.write_text(f"ROOT = {ROOT!r}\n" + WORKER)
-    env = dict(os.environ, DISCREGRID_B200_LIB=EMU, DG_REHEARSAL="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29641")
+    env = dict(os.environ, DISCREGRID_B200_LIB=EMU, DG_ALLOW_EMULATED_LIBRARY="1", DG_REHEARSAL="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29641")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29641", str(script)], capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0 and "MULTI_OK 2" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
@@ -58,7 +58,7 @@ def test_smoke_entry_point_on_the_emulated_library():
     """__graft_entry__.smoke() (K1 + K2 + K3 against the oracle through the C-ABI) as the driver will call it, kernels emulated"""
     if not os.path.exists(EMU):
         pytest.skip("build/bin/libdgemu.so not built (make cpp)")
-    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=dict(os.environ, DISCREGRID_B200_LIB=EMU),
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=dict(os.environ, DISCREGRID_B200_LIB=EMU, DG_ALLOW_EMULATED_LIBRARY="1"),
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "smoke OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
@@ -70,7 +70,7 @@ def test_bench_runs_end_to_end_single_rank():
     if not os.path.exists(EMU):
         pytest.skip("build/bin/libdgemu.so not built (make cpp)")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_rehearsal.py")] + TOY, cwd=ROOT,
-                       env=dict(os.environ, DISCREGRID_B200_LIB=EMU), capture_output=True, text=True, timeout=1200)
+                       env=dict(os.environ, DISCREGRID_B200_LIB=EMU, DG_ALLOW_EMULATED_LIBRARY="1"), capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     d = _bench_line(r.stdout)
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
@@ -95,8 +95,17 @@ def test_bench_runs_end_to_end_two_ranks(sharding):
     port = {"chunks": "29661", "interleaved": "29663"}[sharding]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", port,
                         os.path.join(ROOT, "tests", "emu", "bench_rehearsal.py"), "--gpus", "2", "--sharding", sharding, "--no-real"] + TOY, cwd=ROOT,
-                       env=dict(os.environ, DISCREGRID_B200_LIB=EMU, MASTER_ADDR="127.0.0.1", MASTER_PORT=port), capture_output=True, text=True, timeout=1500)
+                       env=dict(os.environ, DISCREGRID_B200_LIB=EMU, DG_ALLOW_EMULATED_LIBRARY="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=port), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     d = _bench_line(r.stdout)
     assert d["n_gpus"] == 2 and d["sharded_equals_single_launch"] is True and d["target_config"]["sharded_equals_single_launch"] is True
     assert d["density_map"].get("ms", 0) > 0 and d["interpolate"]["value"] > 0
+
+
+def test_package_refuses_the_emulated_library_by_default():
+    """no accidental CPU path: pointing DISCREGRID_B200_LIB at the emulated test build without the rehearsal's explicit opt-in fails at import"""
+    if not os.path.exists(EMU):
+        pytest.skip("build/bin/libdgemu.so not built (make cpp)")
+    env = {k: v for k, v in os.environ.items() if k != "DG_ALLOW_EMULATED_LIBRARY"}
+    r = subprocess.run([sys.executable, "-c", "import discregrid_b200"], cwd=ROOT, env=dict(env, DISCREGRID_B200_LIB=EMU), capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "CPU-emulated TEST build" in r.stderr
