@@ -109,3 +109,12 @@ def test_interpolate_fuzz_against_reference_class():
         pytest.skip("needs oracle/_ref/libdiscregrid_ref.so and build/bin/libk23emu.so")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k2_fuzz.py"), "24", "5"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_density_map_fuzz_against_oracle(emu):
+    """a short run of tools/k3_fuzz.py on each emulated build (default, K3_FAST_DIV): random grids / fields / support radii / node ranges"""
+    import subprocess
+    import sys
+    so = LIBS[0] if "knobs" not in emu.lib._name else LIBS[1]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k3_fuzz.py"), "10", "3", so], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
