@@ -152,6 +152,10 @@ inline unsigned __reduce_add_sync(unsigned, unsigned v) { dg_emu::collective_wai
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }
+// atomics: lanes run one at a time, so plain read-modify-write is atomic here
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
 inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, 8); return r; }
 
 // directed rounding to fp32 of a value held exactly (or nearly) in a double

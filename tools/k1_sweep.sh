@@ -2,7 +2,7 @@
 # GPU box: for every build/variants/*.so (tools/build_variants.py) -- parity first (the K1 GPU tests against that library), then the K1-only
 # bench on the 128^3 workload and on the 256^3 / 100k-triangle target.  Typical round-2 opening:
 #   python tools/build_variants.py base: fastdiv:-DK1_FAST_DIV=1 redux:-DK1_VOTE_REDUX=1 auto:-DK1_BRICK_AUTO=1 \
-#          all:-DK1_FAST_DIV=1,-DK1_VOTE_REDUX=1,-DK1_BRICK_AUTO=1 k3div:-DK3_FAST_DIV=1          (here, no GPU needed)
+#          all:-DK1_FAST_DIV=1,-DK1_VOTE_REDUX=1,-DK1_BRICK_AUTO=1 cost:-DK1_COST_ORDER=1 k3div:-DK3_FAST_DIV=1          (here, no GPU needed)
 #   gpurun --timeout 900 -- 'bash tools/k1_sweep.sh > gpurun_out/sweep.txt 2>&1'
 for so in build/variants/*.so; do
   n=$(basename $so .so)
