@@ -44,8 +44,10 @@
 #endif
 #ifdef DG_EMU
 #define DG_EMU_COUNT(i) (dg_emu::g_counters[(i)]++)        // event counters of the emulation (tests/emu, tools): nothing on the device
+#define DG_EMU_TRACE_BLOCK(b) do { if (threadIdx.x == 0) dg_emu::g_block_trace.push_back(b); } while (0)
 #else
 #define DG_EMU_COUNT(i)
+#define DG_EMU_TRACE_BLOCK(b)
 #endif
 
 namespace dgb {
@@ -566,6 +568,7 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
 #else
     const unsigned this_block = blockIdx.x;
 #endif
+    DG_EMU_TRACE_BLOCK(this_block);
     float* stack_d = reinterpret_cast<float*>(k1_smem);
     unsigned* stack_rng = reinterpret_cast<unsigned*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(float));
     // which segment does this block belong to (<= 4, uniform per block)

@@ -24,6 +24,7 @@ namespace dg_emu {
 struct Idx { unsigned x = 0, y = 0, z = 0; };
 inline Idx g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 inline unsigned long long g_counters[32];        // DG_EMU_COUNT(i) in the kernel sources
+inline std::vector<unsigned> g_block_trace;      // DG_EMU_TRACE_BLOCK: block ids in the order the sampling kernel ran them
 
 // Fiber switch: callee-saved registers + stack pointer, no system call (glibc's swapcontext does a sigprocmask per switch, which made a
 // warp vote cost ~60 us).  x86-64 System V only -- what the build container and the GPU boxes are.

@@ -97,6 +97,8 @@ int emu_build_cells(const double* gd, const uint32_t* res, uint64_t c_begin, uin
     return (int)k1_launch_build_cells(g, c_begin, c_end - c_begin, cells, nullptr);
 }
 void emu_counters(unsigned long long* out /*32*/, int reset) { for (int i = 0; i < 32; i++) { out[i] = dg_emu::g_counters[i]; if (reset) dg_emu::g_counters[i] = 0; } }
+// block ids in the order the last sampling launches ran them (cleared by reading)
+uint64_t emu_block_trace(uint32_t* out, uint64_t cap) { const uint64_t n = dg_emu::g_block_trace.size(); for (uint64_t i = 0; i < n && i < cap; i++) out[i] = dg_emu::g_block_trace[i]; dg_emu::g_block_trace.clear(); return n; }
 int emu_knobs(int* fast_div, int* vote_redux) { *fast_div = K1_FAST_DIV; *vote_redux = K1_VOTE_REDUX; return 0; }
 
 }  // extern "C"
