@@ -28,12 +28,12 @@ cpp: $(CPPBIN)/GenerateSDF $(CPPBIN)/GenerateDensityMap $(CPPBIN)/DiscreteFieldT
 $(CPPBIN)/DiscreteFieldToBitmap: cpp/cmd/discrete_field_to_bitmap.cpp $(CPPHDRS) $(LIB)
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CPPFLAGS) $< -o $@ $(CPPLINK)
-$(CPPBIN)/bvh_host_check: tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp $(SRC)/sort_replay.h $(SRC)/bvh_build.h
+$(CPPBIN)/bvh_host_check: tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/host_threads.cpp $(SRC)/sort_replay.cpp $(SRC)/sort_replay.h $(SRC)/bvh_build.h
 	@mkdir -p $(CPPBIN)
-	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp -o $@ -lpthread
+	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/host_threads.cpp $(SRC)/sort_replay.cpp -o $@ -lpthread
 # test libraries: the K1 translation unit (kernels + launchers) compiled for the CPU by tests/emu -- default knobs, and the prepared
 # knob variants (reciprocal division in the leaf test, redux vote, per-array brick shape, cost-ordered launch) so that their logic stays checked while off
-K1EMU_SRC := tests/emu/k1_emu.cpp $(SRC)/bvh_build.cpp $(SRC)/sort_replay.cpp
+K1EMU_SRC := tests/emu/k1_emu.cpp $(SRC)/bvh_build.cpp $(SRC)/host_threads.cpp $(SRC)/sort_replay.cpp
 K1EMU_DEP := $(K1EMU_SRC) tests/emu/cuda_emu.h $(SRC)/k1_sdf.cu $(HDRS)
 CUDA_INC  ?= /usr/local/cuda/include
 $(CPPBIN)/libk1emu.so: $(K1EMU_DEP)
@@ -53,7 +53,7 @@ $(CPPBIN)/libk23emu_knobs.so: $(K23EMU_DEP)
 # test library: the WHOLE product library with every kernel emulated and the CUDA runtime stubbed on host memory -- lets the Python-level
 # and tool-level `-m gpu` tests be rehearsed on the CPU (tests/test_gpu_rehearsal.py); never loaded by the product
 DGEMU_SRC := tests/emu/dgapi_emu.cpp tests/emu/k1_emu.cpp tests/emu/k2_emu.cpp tests/emu/k3_emu.cpp tests/emu/cudart_stub.cpp \
-             $(SRC)/bvh_build.cpp $(SRC)/reduce_field.cpp $(SRC)/obj_reader.cpp $(SRC)/sort_replay.cpp
+             $(SRC)/bvh_build.cpp $(SRC)/host_threads.cpp $(SRC)/reduce_field.cpp $(SRC)/obj_reader.cpp $(SRC)/sort_replay.cpp
 $(CPPBIN)/libdgemu.so: $(DGEMU_SRC) tests/emu/cuda_emu.h $(wildcard $(SRC)/*.cu) $(HDRS)
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -Wl,-Bsymbolic -Wno-subobject-linkage -I$(CUDA_INC) -Itests/emu -I$(SRC) -Iinclude $(DGEMU_SRC) -o $@ -lpthread
@@ -62,9 +62,9 @@ $(CPPBIN)/fast_div_check: tests/cpp/fast_div_check.cpp $(SRC)/fast_div.h $(SRC)/
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CXXFLAGS) -I$(SRC) tests/cpp/fast_div_check.cpp -o $@
 # test binary: the threaded std::sort replay of reduce_field.cpp against std::sort (ties, depth exhaustion)
-$(CPPBIN)/sort_replay_check: tests/cpp/sort_replay_check.cpp $(SRC)/reduce_field.cpp $(SRC)/sort_replay.cpp $(SRC)/sort_replay.h $(SRC)/reduce_field.h $(SRC)/dg_device.cuh
+$(CPPBIN)/sort_replay_check: tests/cpp/sort_replay_check.cpp $(SRC)/reduce_field.cpp $(SRC)/host_threads.cpp $(SRC)/sort_replay.cpp $(SRC)/sort_replay.h $(SRC)/reduce_field.h $(SRC)/dg_device.cuh
 	@mkdir -p $(CPPBIN)
-	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default -I$(SRC) tests/cpp/sort_replay_check.cpp $(SRC)/reduce_field.cpp $(SRC)/sort_replay.cpp -o $@ -lpthread
+	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default -I$(SRC) tests/cpp/sort_replay_check.cpp $(SRC)/reduce_field.cpp $(SRC)/host_threads.cpp $(SRC)/sort_replay.cpp -o $@ -lpthread
 # test binary: the facade's reduceField with dg_node_positions interposed by the oracle (runs without a GPU)
 $(CPPBIN)/reduce_facade_check: tests/cpp/reduce_facade_check.cpp $(CPPHDRS) $(LIB) oracle/liboracle.so
 	@mkdir -p $(CPPBIN)
@@ -88,7 +88,7 @@ $(OBJ)/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p $(OBJ)
 	$(HOSTCXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/bvh_build.o $(OBJ)/reduce_field.o $(OBJ)/obj_reader.o $(OBJ)/sort_replay.o
+$(LIB): $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/bvh_build.o $(OBJ)/host_threads.o $(OBJ)/reduce_field.o $(OBJ)/obj_reader.o $(OBJ)/sort_replay.o
 	@mkdir -p $(dir $(LIB))
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $^ -Xlinker --exclude-libs=ALL
 

@@ -37,6 +37,21 @@ namespace Discregrid {
 
 class CubicLagrangeDiscreteGrid;
 
+// std::vector whose resize() leaves trivially-constructible elements uninitialised.  The field arrays (947 MB of coefficients and a
+// 2 GiB connectivity table at 256^3) are written exactly once, by the library: value-initialising them first would touch every page
+// serially before the real fill does.  Same interface as std::vector; the members are private in the reference too
+// (cubic_lagrange_discrete_grid.hpp:69-71), so no caller sees the allocator.
+template <class T>
+struct FieldAllocator : std::allocator<T> {
+    template <class U> struct rebind { using other = FieldAllocator<U>; };
+    using std::allocator<T>::allocator;
+    FieldAllocator() = default;
+    template <class U> FieldAllocator(FieldAllocator<U> const&) noexcept {}
+    template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using FieldVector = std::vector<T, FieldAllocator<T>>;
+
 // GenerateDensityMap's density functor + sample predicate (cmd/generate_density_map/main.cpp:96-133) as a recognisable type
 struct DensityMapFunction {
     const CubicLagrangeDiscreteGrid* grid;
@@ -92,16 +107,27 @@ public:
         const dg_grid_desc d = desc();
         std::uint64_t n_nodes = 0;
         check(dg_grid_num_nodes(d.resolution, &n_nodes));
-        std::vector<double> coeffs(n_nodes);
         if (auto const* sdf = func.target<MeshSignedDistanceFunction>()) {
             if (pred) throw std::invalid_argument("addFunction: a sample predicate is only supported with DensityMapFunction");
-            check(dg_sample_sdf(sdf->md->handle(), &d, sdf->sign, 0, n_nodes, coeffs.data()));
-        } else if (auto const* dm = func.target<DensityMapFunction>()) {
+            // the whole of :780-899 in one library call: node loop on the GPU; connectivity (:833-886) and cell map (:888-891) written by
+            // the library's host threads into these arrays while the GPU works
+            FieldVector<double> coeffs(n_nodes);
+            FieldVector<std::array<unsigned int, 32>> cells(m_n_cells);
+            FieldVector<unsigned int> cell_map(m_n_cells);
+            check(dg_add_function_sdf(sdf->md->handle(), &d, sdf->sign, coeffs.data(), reinterpret_cast<std::uint32_t*>(cells.data()), cell_map.data(),
+                                      m_last_add_function_ms));
+            if (verbose) std::cout << "Construction: " << n_nodes << " nodes sampled on the GPU in " << m_last_add_function_ms[0] << " ms" << std::endl;
+            invalidate();
+            m_nodes.push_back(std::move(coeffs)); m_cells.push_back(std::move(cells)); m_cell_map.push_back(std::move(cell_map));
+            return static_cast<unsigned int>(m_n_fields++);
+        }
+        FieldVector<double> coeffs(n_nodes);
+        if (auto const* dm = func.target<DensityMapFunction>()) {
             check(dg_density_map(dm->grid->deviceField(dm->sdf_field_id), dm->smoothing_length, dm->rest_density, dm->no_reduction ? 1 : 0,
                                  0, n_nodes, coeffs.data()));
         } else {
 #ifdef DISCREGRID_B200_ALLOW_HOST_CALLBACK
-            std::vector<double> x(3 * n_nodes);
+            FieldVector<double> x(3 * n_nodes);
             check(dg_node_positions(&d, 0, n_nodes, x.data()));
             for (std::uint64_t l = 0; l < n_nodes; l++) {
                 const Eigen::Vector3d p(x[3 * l], x[3 * l + 1], x[3 * l + 2]);
@@ -117,7 +143,7 @@ public:
         return addSampledFunction(std::move(coeffs));
     }
     // appends a field from node values + the closed-form connectivity (:833-886, built on the GPU) + identity cell map (:888-891)
-    unsigned int addSampledFunction(std::vector<double> coeffs)
+    unsigned int addSampledFunction(FieldVector<double> coeffs)
     {
         invalidate();
         m_nodes.push_back(std::move(coeffs));
@@ -200,9 +226,11 @@ public:
     }
 
     // ---- accessors used by tools / tests
-    std::vector<double> const& nodeData(unsigned int f) const { return m_nodes[f]; }
-    std::vector<std::array<unsigned int, 32>> const& cellData(unsigned int f) const { return m_cells[f]; }
-    std::vector<unsigned int> const& cellMap(unsigned int f) const { return m_cell_map[f]; }
+    FieldVector<double> const& nodeData(unsigned int f) const { return m_nodes[f]; }
+    FieldVector<std::array<unsigned int, 32>> const& cellData(unsigned int f) const { return m_cells[f]; }
+    FieldVector<unsigned int> const& cellMap(unsigned int f) const { return m_cell_map[f]; }
+    // ms since entry of the last addFunction(MeshSignedDistanceFunction): total, node pipeline, index tables, pre-fault; workers
+    const double* lastAddFunctionTimings() const { return m_last_add_function_ms; }
     std::size_t nFields() const { return m_n_fields; }
     dg_grid_desc desc() const
     {
@@ -224,9 +252,10 @@ public:
     }
 
 private:
-    std::vector<std::vector<double>> m_nodes;
-    std::vector<std::vector<std::array<unsigned int, 32>>> m_cells;
-    std::vector<std::vector<unsigned int>> m_cell_map;
+    std::vector<FieldVector<double>> m_nodes;
+    std::vector<FieldVector<std::array<unsigned int, 32>>> m_cells;
+    std::vector<FieldVector<unsigned int>> m_cell_map;
+    double m_last_add_function_ms[6] = {0, 0, 0, 0, 0, 0};
     mutable std::map<unsigned int, dg_field*> m_dev;
 
     static void check(int rc) { if (rc != DG_OK) throw std::runtime_error(std::string("discregrid_b200: ") + dg_last_error()); }

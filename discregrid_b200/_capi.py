@@ -51,6 +51,7 @@ SIGNATURES = {
     "dg_device_count": (C.c_int, []),
     "dg_set_device": (C.c_int, [C.c_int]),
     "dg_selftest": (C.c_int, []),
+    "dg_fp64_rate_probe": (C.c_int, [_dp]),
     "dg_kernel_launch_count": (C.c_uint64, []),
     "dg_kernel_launch_count_reset": (None, []),
     "dg_grid_init": (C.c_int, [_dp, _dp, _u32p, _gp]),
@@ -66,6 +67,7 @@ SIGNATURES = {
     "dg_mesh_distance": (C.c_int, [_vp, _dp, C.c_uint64, C.c_int, _dp, _dp, _i32p, _i32p]),
     "dg_mesh_distance_device": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "dg_sample_sdf": (C.c_int, [_vp, _gp, C.c_double, C.c_uint64, C.c_uint64, _dp]),
+    "dg_add_function_sdf": (C.c_int, [_vp, _gp, C.c_double, _dp, _u32p, _u32p, _dp]),
     "dg_sample_sdf_device": (C.c_int, [_vp, _gp, C.c_double, C.c_uint64, C.c_uint64, _vp, _vp]),
     "dg_slab_ranges": (C.c_int, [_gp, C.c_uint32, C.c_uint32, _u64p]),
     "dg_sample_sdf_slab_device": (C.c_int, [_vp, _gp, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp]),

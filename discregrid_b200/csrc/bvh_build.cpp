@@ -124,7 +124,7 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
 
     Builder bld{V, F, out, out.order};
     bld.keys.resize(nT);
-    { unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 1; if (hw > 64) hw = 64;
+    { unsigned hw = host_threads(); if (hw == 0) hw = 1; if (hw > 64) hw = 64;
       int lv = 0; while ((1u << (lv + 1)) <= hw && lv < 6) lv++; bld.par_levels = lv; bld.hw_threads = hw;
       bld.replay_ok = nT >= 32768 && sort_replay_matches_std_sort(); }
     double root_c[3], root_r, root_box[6];

@@ -37,11 +37,15 @@ struct DefaultInitAllocator : std::allocator<T> {
 };
 template <class T> using RawVec = std::vector<T, DefaultInitAllocator<T>>;
 
-// static partition of [0, n) over the hardware threads; fn(begin, end)
+// Host threads this process can really run: the scheduler affinity mask, capped by the cgroup CPU quota (a container that sees 128
+// logical CPUs but is throttled to a 16-CPU quota runs 128 busy threads SLOWER than 16).  host_threads.cpp.
+unsigned host_threads();
+
+// static partition of [0, n) over the usable host threads; fn(begin, end)
 template <class Fn>
 void parallel_for(uint64_t n, Fn fn)
 {
-    unsigned nt = std::thread::hardware_concurrency();
+    unsigned nt = host_threads();
     if (nt == 0) nt = 1;
     if (nt > 32) nt = 32;
     if (n < 4096 || nt == 1) { fn(0, n); return; }

@@ -14,9 +14,13 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include "bvh_build.h"
 #include "dg_device.cuh"
@@ -71,6 +75,15 @@ int require_device()
         return fail(DG_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
+    return DG_OK;
+}
+
+// a handle's device arrays (and K1's dynamic shared-memory attribute) belong to the device it was created on
+int check_handle_device(int handle_device, const char* who)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(DG_ERR_NO_DEVICE, "%s: no current CUDA device", who); }
+    if (dev != handle_device) return fail(DG_ERR_INVALID, "%s: the handle lives on device %d but the current device is %d (dg_set_device)", who, handle_device, dev);
     return DG_OK;
 }
 
@@ -185,6 +198,35 @@ int dg_selftest(void)
                     "build with -fmad=false", r);
     }
     g_selftest_state = 1;
+    return DG_OK;
+}
+
+// Measured fp64 issue rate of the current device for the library's own instruction mix (DMUL + DADD, no FMA): Tflop/s.
+int dg_fp64_rate_probe(double* tflops)
+{
+    if (int rc = require_device()) return rc;
+    if (!tflops) return fail(DG_ERR_INVALID, "dg_fp64_rate_probe: NULL argument");
+    int dev = 0, n_sm = 0;
+    DG_CUDA(cudaGetDevice(&dev));
+    DG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = n_sm * 8, iters = 1 << 14;
+    DevBuf<double> out;
+    DG_CUDA(out.alloc(1));
+    cudaEvent_t e0, e1;
+    DG_CUDA(cudaEventCreate(&e0)); DG_CUDA(cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 4; rep++) {                       // first repetition warms up
+        DG_CUDA(cudaEventRecord(e0, nullptr));
+        DG_LAUNCH(k1_launch_fp64_rate_probe(blocks, iters, out.p, nullptr));
+        DG_CUDA(cudaEventRecord(e1, nullptr));
+        DG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        DG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double flops = (double)blocks * 256.0 * 8.0 * 2.0 * (double)iters;
+    *tflops = best > 0.f ? flops / (best * 1e-3) / 1e12 : 0.0;
     return DG_OK;
 }
 
@@ -359,6 +401,7 @@ int dg_mesh_distance_device(const dg_mesh* m, const double* d_pts, uint64_t n, i
 {
     if (!m) return fail(DG_ERR_INVALID, "dg_mesh_distance: mesh is NULL (not constructed)");
     if (n && !d_pts) return fail(DG_ERR_INVALID, "dg_mesh_distance: points is NULL");
+    if (int rc = check_handle_device(m->device, "dg_mesh_distance")) return rc;
     DG_LAUNCH(k1_launch_distance(m->dev, d_pts, n, is_signed, d_dist, d_near, d_ent, d_tri, (cudaStream_t)stream));
     return DG_OK;
 }
@@ -405,6 +448,7 @@ int dg_sample_sdf_device(const dg_mesh* m, const dg_grid_desc* grid, double sign
     GridDev g;
     if (int rc = check_range(grid, l_begin, l_end, g, "dg_sample_sdf")) return rc;
     if (l_end > l_begin && !d_out) return fail(DG_ERR_INVALID, "dg_sample_sdf: output is NULL");
+    if (int rc = check_handle_device(m->device, "dg_sample_sdf")) return rc;
     DG_LAUNCH(k1_launch_sample_nodes(m->dev, g, sign, l_begin, l_end - l_begin, d_out, (cudaStream_t)stream));
     return DG_OK;
 }
@@ -434,7 +478,7 @@ struct HostPathPool {
             if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_c, cudaStreamNonBlocking);
             for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&dma_ev[i], cudaEventDisableTiming);
             for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaMallocHost(reinterpret_cast<void**>(&stage[i]), kPiece * sizeof(double));
-            if (e != cudaSuccess) return e;
+            if (e != cudaSuccess) { release(); return e; }          // never leave a half-built pool behind
         }
         if (n > d_cap) {
             if (d_out) cudaFree(d_out);
@@ -466,15 +510,10 @@ struct HostPathPool {
 HostPathPool g_pool;
 }  // namespace
 
-int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* out_host)
+// the pipeline of the host-buffer path; the caller holds g_pool.mu.  copy_threads > 1: the copy from the pinned piece into the
+// caller's memory is split over that many threads (fresh pageable memory: the page faults, not the bytes, are the cost)
+static int sample_sdf_host_locked(const dg_mesh* m, const GridDev& g, double sign, uint64_t l_begin, uint64_t n, double* out_host, unsigned copy_threads)
 {
-    if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf: mesh is NULL (not constructed)");
-    GridDev g;
-    if (int rc = check_range(grid, l_begin, l_end, g, "dg_sample_sdf")) return rc;
-    const uint64_t n = l_end - l_begin;
-    if (n == 0) return DG_OK;
-    if (!out_host) return fail(DG_ERR_INVALID, "dg_sample_sdf: output is NULL");
-    std::lock_guard<std::mutex> lock(g_pool.mu);
     // kernel chunks: a handful, each a multiple of the staging piece so that pieces never straddle chunks
     const uint64_t piece = HostPathPool::kPiece;
     const uint64_t n_pieces = (n + piece - 1) / piece;
@@ -497,10 +536,137 @@ int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint6
         if (i >= 1) {
             const uint64_t off = (i - 1) * piece, cnt = (off + piece <= n) ? piece : n - off;
             DG_CUDA(cudaEventSynchronize(g_pool.dma_ev[(i - 1) & 1]));
-            std::memcpy(out_host + off, g_pool.stage[(i - 1) & 1], cnt * sizeof(double));
+            const double* src = g_pool.stage[(i - 1) & 1];
+            if (copy_threads > 1 && cnt >= (1u << 16)) {
+                std::vector<std::thread> th;
+                const uint64_t per = (cnt + copy_threads - 1) / copy_threads;
+                for (unsigned k = 1; k < copy_threads; k++) {
+                    const uint64_t b = k * per, e = std::min<uint64_t>(cnt, b + per);
+                    if (b < e) th.emplace_back([=]() { std::memcpy(out_host + off + b, src + b, (e - b) * sizeof(double)); });
+                }
+                std::memcpy(out_host + off, src, std::min<uint64_t>(cnt, per) * sizeof(double));
+                for (auto& t : th) t.join();
+            } else {
+                std::memcpy(out_host + off, src, cnt * sizeof(double));
+            }
         }
     }
     return DG_OK;
+}
+
+int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* out_host)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf: mesh is NULL (not constructed)");
+    GridDev g;
+    if (int rc = check_range(grid, l_begin, l_end, g, "dg_sample_sdf")) return rc;
+    const uint64_t n = l_end - l_begin;
+    if (n == 0) return DG_OK;
+    if (!out_host) return fail(DG_ERR_INVALID, "dg_sample_sdf: output is NULL");
+    if (int rc = check_handle_device(m->device, "dg_sample_sdf")) return rc;
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    return sample_sdf_host_locked(m, g, sign, l_begin, n, out_host, 1);
+}
+
+// Makes the pages of [p, p + bytes) present and writable WITHOUT changing their content (safe against a concurrent writer).
+static void prefault_preserving(char* p, uint64_t bytes)
+{
+    if (bytes == 0) return;
+#if defined(__linux__) && !defined(DG_EMU)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(4095), z = (reinterpret_cast<uintptr_t>(p) + bytes + 4095) & ~uintptr_t(4095);
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+    if (madvise(reinterpret_cast<void*>(a), z - a, MADV_POPULATE_WRITE) == 0) return;
+#endif
+    for (uint64_t o = 0; o < bytes; o += 4096) __atomic_fetch_or(reinterpret_cast<unsigned char*>(p + o), 0, __ATOMIC_RELAXED);
+    __atomic_fetch_or(reinterpret_cast<unsigned char*>(p + bytes - 1), 0, __ATOMIC_RELAXED);
+}
+
+// closed-form connectivity of cells [c0, c1) (cubic_lagrange_discrete_grid.cpp:833-886), host side: plain index algebra
+static void fill_cells_host(const GridDev& g, uint64_t c0, uint64_t c1, uint32_t* out /* (c1 - c0) x 32 */)
+{
+    const unsigned nx = g.n[0], ny = g.n[1], nz = g.n[2];
+    const unsigned nv = g.nv, off_x = nv, off_y = nv + 2u * g.ne_x, off_z = off_y + 2u * g.ne_y;
+    unsigned k = (unsigned)(c0 / ((uint64_t)nx * ny)), rem = (unsigned)(c0 % ((uint64_t)nx * ny)), j = rem / nx, i = rem % nx;
+    for (uint64_t c = c0; c < c1; c++) {
+        uint32_t* cell = out + 32 * (c - c0);
+        const unsigned v00 = (nx + 1) * (ny + 1) * k + (nx + 1) * j + i, v10 = v00 + (nx + 1), v01 = v00 + (nx + 1) * (ny + 1), v11 = v01 + (nx + 1);
+        cell[0] = v00; cell[1] = v00 + 1; cell[2] = v10; cell[3] = v10 + 1; cell[4] = v01; cell[5] = v01 + 1; cell[6] = v11; cell[7] = v11 + 1;
+        const unsigned x0 = off_x + 2 * (nx * (ny + 1) * k + nx * j + i), x1 = off_x + 2 * (nx * (ny + 1) * (k + 1) + nx * j + i);
+        const unsigned x2 = off_x + 2 * (nx * (ny + 1) * k + nx * (j + 1) + i), x3 = off_x + 2 * (nx * (ny + 1) * (k + 1) + nx * (j + 1) + i);
+        cell[8] = x0; cell[9] = x0 + 1; cell[10] = x1; cell[11] = x1 + 1; cell[12] = x2; cell[13] = x2 + 1; cell[14] = x3; cell[15] = x3 + 1;
+        const unsigned y0 = off_y + 2 * (ny * (nz + 1) * i + ny * k + j), y1 = off_y + 2 * (ny * (nz + 1) * (i + 1) + ny * k + j);
+        const unsigned y2 = off_y + 2 * (ny * (nz + 1) * i + ny * (k + 1) + j), y3 = off_y + 2 * (ny * (nz + 1) * (i + 1) + ny * (k + 1) + j);
+        cell[16] = y0; cell[17] = y0 + 1; cell[18] = y1; cell[19] = y1 + 1; cell[20] = y2; cell[21] = y2 + 1; cell[22] = y3; cell[23] = y3 + 1;
+        const unsigned z0 = off_z + 2 * (nz * (nx + 1) * j + nz * i + k), z1 = off_z + 2 * (nz * (nx + 1) * (j + 1) + nz * i + k);
+        const unsigned z2 = off_z + 2 * (nz * (nx + 1) * j + nz * (i + 1) + k), z3 = off_z + 2 * (nz * (nx + 1) * (j + 1) + nz * (i + 1) + k);
+        cell[24] = z0; cell[25] = z0 + 1; cell[26] = z1; cell[27] = z1 + 1; cell[28] = z2; cell[29] = z2 + 1; cell[30] = z3; cell[31] = z3 + 1;
+        if (++i == nx) { i = 0; if (++j == ny) { j = 0; ++k; } }
+    }
+}
+
+// The whole of CubicLagrangeDiscreteGrid::addFunction(GenerateSDF functor) into the caller's three arrays
+// (cubic_lagrange_discrete_grid.cpp:780-899): node loop on the GPU (K1 chunks on two streams, D2H through the pinned double
+// buffer), and -- while the GPU works -- the host threads write the 32-index connectivity table (:833-886) and the identity cell
+// map (:888-891) straight into the caller's memory and pre-fault the coefficient array, so that the call ends one D2H piece after
+// the last kernel chunk.
+int dg_add_function_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host, uint32_t* cell_map_host,
+                        double* timings_ms)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_add_function_sdf: mesh is NULL (not constructed)");
+    GridDev g;
+    uint64_t n_nodes = 0;
+    if (grid && dg_grid_num_nodes(grid->resolution, &n_nodes)) return DG_ERR_INVALID;
+    if (int rc = check_range(grid, 0, n_nodes, g, "dg_add_function_sdf")) return rc;
+    if (!nodes_host) return fail(DG_ERR_INVALID, "dg_add_function_sdf: nodes output is NULL");
+    if (int rc = check_handle_device(m->device, "dg_add_function_sdf")) return rc;
+    const uint64_t n_cells = (uint64_t)g.n[0] * g.n[1] * g.n[2];
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+    const unsigned hw = host_threads();
+    const unsigned n_workers = std::max(1u, std::min(hw > 2 ? hw - 2 : 1u, 24u));      // the calling thread drives the GPU pipeline
+    std::atomic<uint64_t> next_task{0};
+    double ms_prefault = 0.0, ms_cells = 0.0;
+    // tasks, in this order: pre-fault the coefficient array (one write per page: the pages are about to be overwritten by the
+    // pipeline's memcpy), then the cell table, then the cell map -- 4 MiB blocks dealt dynamically to the workers
+    const uint64_t blk = 4u << 20;
+    const uint64_t nb_nodes = (n_nodes * 8 + blk - 1) / blk;
+    const uint64_t nb_cells = cells_host ? (n_cells * 128 + blk - 1) / blk : 0;
+    const uint64_t nb_map = cell_map_host ? (n_cells * 4 + blk - 1) / blk : 0;
+    const uint64_t n_tasks = nb_nodes + nb_cells + nb_map;
+    std::atomic<int> prefault_left{(int)std::min<uint64_t>(nb_nodes, 0x7fffffff)};
+    auto worker = [&]() {
+        for (;;) {
+            const uint64_t t = next_task.fetch_add(1);
+            if (t >= n_tasks) break;
+            if (t < nb_nodes) {
+                // content-preserving (the pipeline's memcpy may already be writing here): MADV_POPULATE_WRITE, else a locked `or 0` per page
+                char* p = reinterpret_cast<char*>(nodes_host);
+                const uint64_t b = t * blk, e = std::min<uint64_t>(n_nodes * 8, b + blk);
+                prefault_preserving(p + b, e - b);
+                if (prefault_left.fetch_sub(1) == 1) ms_prefault = ms_since(t0);
+            } else if (t < nb_nodes + nb_cells) {
+                const uint64_t per = blk / 128, c0 = (t - nb_nodes) * per, c1 = std::min<uint64_t>(n_cells, c0 + per);
+                fill_cells_host(g, c0, c1, cells_host + 32 * c0);
+            } else {
+                const uint64_t per = blk / 4, c0 = (t - nb_nodes - nb_cells) * per, c1 = std::min<uint64_t>(n_cells, c0 + per);
+                for (uint64_t c = c0; c < c1; c++) cell_map_host[c] = (uint32_t)c;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    try { for (unsigned k = 0; k < n_workers; k++) th.emplace_back(worker); } catch (...) { /* fewer workers: the calling thread finishes the tasks below */ }
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        rc = sample_sdf_host_locked(m, g, sign, 0, n_nodes, nodes_host, std::min(4u, std::max(1u, hw / 4)));
+    }
+    const double ms_nodes = ms_since(t0);
+    worker();                                           // whatever is left
+    for (auto& t : th) t.join();
+    ms_cells = ms_since(t0);
+    if (timings_ms) { timings_ms[0] = ms_since(t0); timings_ms[1] = ms_nodes; timings_ms[2] = ms_cells; timings_ms[3] = ms_prefault; timings_ms[4] = (double)n_workers; timings_ms[5] = 0.0; }
+    return rc;
 }
 
 // plane ranges of part `part` of `n_parts`: boundaries fall on even plane indices (a brick spans K1_BRICK_S = 2 planes)
@@ -535,6 +701,7 @@ int dg_sample_sdf_slab_device(const dg_mesh* m, const dg_grid_desc* grid, double
     GridDev g; const char* why = "";
     if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_sample_sdf_slab: %s", why);
     if (n_parts == 0 || part >= n_parts || !d_full) return fail(DG_ERR_INVALID, "dg_sample_sdf_slab: bad part / n_parts / output");
+    if (int rc = check_handle_device(m->device, "dg_sample_sdf_slab")) return rc;
     unsigned pb[4], pe[4];
     slab_planes(g, part, n_parts, pb, pe);
     DG_LAUNCH(k1_launch_sample_slab(m->dev, g, sign, pb, pe, d_full, (cudaStream_t)stream));
@@ -570,6 +737,7 @@ int dg_sample_sdf_interleaved_device(const dg_mesh* m, const dg_grid_desc* grid,
     if (!grid_to_dev(grid, g, &why)) return fail(DG_ERR_INVALID, "dg_sample_sdf_interleaved: %s", why);
     InterleavedLayout L;
     if (!k1_interleaved_layout(g, n_parts, L) || part >= n_parts || !d_slot) return fail(DG_ERR_INVALID, "dg_sample_sdf_interleaved: bad part / n_parts (1..16) / output");
+    if (int rc = check_handle_device(m->device, "dg_sample_sdf_interleaved")) return rc;
     DG_LAUNCH(k1_launch_sample_interleaved(m->dev, g, sign, L, part, d_slot, (cudaStream_t)stream));
     return DG_OK;
 }
@@ -620,8 +788,9 @@ int dg_build_cells(const uint32_t res[3], uint64_t c_begin, uint64_t c_end, uint
     std::lock_guard<std::mutex> lock(g_pool.mu);
     const uint64_t piece_cells = HostPathPool::kPiece * sizeof(double) / (32 * sizeof(uint32_t));    // cells per staging buffer
     const uint64_t n_pieces = (n + piece_cells - 1) / piece_cells;
-    DG_CUDA(g_pool.prepare(2 * HostPathPool::kPiece, 2));                 // device scratch: two pieces
-    uint32_t* d_piece[2] = {reinterpret_cast<uint32_t*>(g_pool.d_out), reinterpret_cast<uint32_t*>(g_pool.d_out + HostPathPool::kPiece)};
+    const uint64_t piece_doubles = std::min<uint64_t>(HostPathPool::kPiece, n * 16);      // 32 uint32 = 16 doubles per cell
+    DG_CUDA(g_pool.prepare(2 * piece_doubles, 2));                        // device scratch: two pieces, no larger than the request
+    uint32_t* d_piece[2] = {reinterpret_cast<uint32_t*>(g_pool.d_out), reinterpret_cast<uint32_t*>(g_pool.d_out + piece_doubles)};
     for (uint64_t i = 0; i <= n_pieces; i++) {
         if (i < n_pieces) {
             const uint64_t off = i * piece_cells, cnt = (off + piece_cells <= n) ? piece_cells : n - off;
@@ -681,6 +850,8 @@ int dg_field_create(const dg_grid_desc* grid, const double* nodes, uint64_t n_no
     const uint64_t n_cells = (uint64_t)grid->resolution[0] * grid->resolution[1] * grid->resolution[2];
     if (!nodes && n_nodes) return bail(fail(DG_ERR_INVALID, "dg_field_create: nodes is NULL"));
     if (!cells && n_cells_kept != n_cells) return bail(fail(DG_ERR_INVALID, "dg_field_create: cells == NULL requires n_cells_kept == nx*ny*nz"));
+    if (!cell_map && n_cells_kept != n_cells)      // K2/K3 read a NULL cell map as the identity: it must then cover every grid cell
+        return bail(fail(DG_ERR_INVALID, "dg_field_create: cell_map == NULL requires n_cells_kept == nx*ny*nz (pass the reduced field's cell map)"));
     if (!cells) {
         uint64_t nn = 0; dg_grid_num_nodes(grid->resolution, &nn);
         if (n_nodes != nn) return bail(fail(DG_ERR_INVALID, "dg_field_create: closed-form cells need all %llu nodes (got %llu)",
@@ -745,23 +916,126 @@ int dg_interpolate_batch_device(const dg_field* f, const double* d_x, uint64_t n
 {
     if (!f) return fail(DG_ERR_INVALID, "dg_interpolate_batch: field is NULL");
     if (n && (!d_x || !d_phi)) return fail(DG_ERR_INVALID, "dg_interpolate_batch: x / phi is NULL");
+    if (int rc = check_handle_device(f->device, "dg_interpolate_batch")) return rc;
     DG_LAUNCH(k2_launch_interpolate(f->dev, d_x, n, d_phi, d_grad, (cudaStream_t)stream));
     return DG_OK;
 }
+
+// Host-buffer path of K2: a three-slot pipeline.  Each slot owns device buffers for one chunk of queries, a stream and an event;
+// chunk c runs H2D -> kernel -> D2H on slot c % 3, so the uploads, kernels and downloads of neighbouring chunks overlap on the two
+// DMA directions of the link.  Caller memory that is already page-locked (cudaMallocHost / cudaHostRegister / torch pin_memory) is
+// DMA'd directly; pageable memory goes through pooled pinned staging buffers, copied in and out by a few host threads while the
+// other slots are in flight.  Calls are serialised per process (pool mutex).
+namespace {
+struct InterpPool {
+    static constexpr int kSlots = 3;
+    static constexpr uint64_t kChunk = 1u << 19;                 // queries per chunk: 12 MiB up, 16 MiB down
+    std::mutex mu;
+    int device = -1;
+    uint64_t cap = 0;                                            // queries per slot currently allocated
+    double* d_x[kSlots] = {}; double* d_phi[kSlots] = {}; double* d_grad[kSlots] = {};
+    double* h_in[kSlots] = {}; double* h_out[kSlots] = {};       // pinned staging (allocated on first pageable call)
+    cudaStream_t st[kSlots] = {}; cudaEvent_t done[kSlots] = {};
+    void release()
+    {
+        for (int i = 0; i < kSlots; i++) {
+            if (d_x[i]) cudaFree(d_x[i]); if (d_phi[i]) cudaFree(d_phi[i]); if (d_grad[i]) cudaFree(d_grad[i]);
+            if (h_in[i]) cudaFreeHost(h_in[i]); if (h_out[i]) cudaFreeHost(h_out[i]);
+            if (st[i]) cudaStreamDestroy(st[i]); if (done[i]) cudaEventDestroy(done[i]);
+            d_x[i] = d_phi[i] = d_grad[i] = h_in[i] = h_out[i] = nullptr; st[i] = nullptr; done[i] = nullptr;
+        }
+        cap = 0;
+    }
+    cudaError_t prepare(uint64_t chunk, bool need_stage_in, bool need_stage_out)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev != device) { release(); device = dev; }
+        if (chunk > cap) { release(); device = dev; }
+        if (cap == 0) {
+            for (int i = 0; i < kSlots && e == cudaSuccess; i++) {
+                e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_x[i]), chunk * 3 * sizeof(double));
+                if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_phi[i]), chunk * sizeof(double));
+                if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_grad[i]), chunk * 3 * sizeof(double));
+            }
+            if (e != cudaSuccess) { release(); return e; }
+            cap = chunk;
+        }
+        for (int i = 0; i < kSlots && e == cudaSuccess; i++) {
+            if (need_stage_in && !h_in[i]) e = cudaMallocHost(reinterpret_cast<void**>(&h_in[i]), cap * 3 * sizeof(double));
+            if (e == cudaSuccess && need_stage_out && !h_out[i]) e = cudaMallocHost(reinterpret_cast<void**>(&h_out[i]), cap * 4 * sizeof(double));
+        }
+        if (e != cudaSuccess) release();
+        return e;
+    }
+};
+InterpPool g_ipool;
+
+bool is_pinned_host(const void* p)
+{
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+void threaded_copy(void* dst, const void* src, size_t bytes, unsigned nt)
+{
+    if (nt <= 1 || bytes < (1u << 20)) { std::memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes + nt - 1) / nt + 63) & ~size_t(63);
+    for (unsigned k = 1; k < nt; k++) {
+        const size_t b = k * per, e = std::min(bytes, b + per);
+        if (b < e) th.emplace_back([=]() { std::memcpy(static_cast<char*>(dst) + b, static_cast<const char*>(src) + b, e - b); });
+    }
+    std::memcpy(dst, src, std::min(bytes, per));
+    for (auto& t : th) t.join();
+}
+}  // namespace
 
 int dg_interpolate_batch(const dg_field* f, const double* x, uint64_t n, double* phi, double* grad)
 {
     if (!f) return fail(DG_ERR_INVALID, "dg_interpolate_batch: field is NULL");
     if (n == 0) return DG_OK;
     if (!x || !phi) return fail(DG_ERR_INVALID, "dg_interpolate_batch: x / phi is NULL");
-    DevBuf<double> d_x, d_phi, d_grad;
-    DG_CUDA(d_x.alloc(3 * n));
-    DG_CUDA(d_phi.alloc(n));
-    if (grad) DG_CUDA(d_grad.alloc(3 * n));
-    DG_CUDA(cudaMemcpy(d_x.p, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
-    if (int rc = dg_interpolate_batch_device(f, d_x.p, n, d_phi.p, grad ? d_grad.p : nullptr, nullptr)) return rc;
-    DG_CUDA(cudaMemcpy(phi, d_phi.p, n * sizeof(double), cudaMemcpyDeviceToHost));
-    if (grad) DG_CUDA(cudaMemcpy(grad, d_grad.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (int rc = check_handle_device(f->device, "dg_interpolate_batch")) return rc;
+    std::lock_guard<std::mutex> lock(g_ipool.mu);
+    constexpr int S = InterpPool::kSlots;
+    const uint64_t chunk = std::min<uint64_t>(InterpPool::kChunk, n);
+    const bool x_direct = is_pinned_host(x), out_direct = is_pinned_host(phi) && is_pinned_host(grad);
+    DG_CUDA(g_ipool.prepare(std::max<uint64_t>(chunk, g_ipool.cap), !x_direct, !out_direct));
+    const unsigned nt = std::max(1u, std::min(8u, host_threads() / 2));
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    auto unstage = [&](uint64_t c) {                      // results of chunk c: pinned staging -> caller memory
+        const uint64_t off = c * chunk, cnt = std::min(chunk, n - off);
+        const double* src = g_ipool.h_out[c % S];
+        threaded_copy(phi + off, src, cnt * sizeof(double), nt);
+        if (grad) threaded_copy(grad + 3 * off, src + g_ipool.cap, 3 * cnt * sizeof(double), nt);
+    };
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        const int s = (int)(c % S);
+        const uint64_t off = c * chunk, cnt = std::min(chunk, n - off);
+        if (c >= (uint64_t)S) {                           // the slot's previous chunk must have left the device buffers (and staging)
+            DG_CUDA(cudaEventSynchronize(g_ipool.done[s]));
+            if (!out_direct) unstage(c - S);
+        }
+        const double* src = x + 3 * off;
+        if (!x_direct) { threaded_copy(g_ipool.h_in[s], src, 3 * cnt * sizeof(double), nt); src = g_ipool.h_in[s]; }
+        DG_CUDA(cudaMemcpyAsync(g_ipool.d_x[s], src, 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, g_ipool.st[s]));
+        DG_LAUNCH(k2_launch_interpolate(f->dev, g_ipool.d_x[s], cnt, g_ipool.d_phi[s], grad ? g_ipool.d_grad[s] : nullptr, g_ipool.st[s]));
+        double* dst_phi = out_direct ? phi + off : g_ipool.h_out[s];
+        double* dst_grad = out_direct ? grad + 3 * off : g_ipool.h_out[s] + g_ipool.cap;
+        DG_CUDA(cudaMemcpyAsync(dst_phi, g_ipool.d_phi[s], cnt * sizeof(double), cudaMemcpyDeviceToHost, g_ipool.st[s]));
+        if (grad) DG_CUDA(cudaMemcpyAsync(dst_grad, g_ipool.d_grad[s], 3 * cnt * sizeof(double), cudaMemcpyDeviceToHost, g_ipool.st[s]));
+        DG_CUDA(cudaEventRecord(g_ipool.done[s], g_ipool.st[s]));
+    }
+    for (uint64_t c = (n_chunks > (uint64_t)S ? n_chunks - S : 0); c < n_chunks; c++) {
+        DG_CUDA(cudaEventSynchronize(g_ipool.done[c % S]));
+        if (!out_direct) unstage(c);
+    }
     return DG_OK;
 }
 
@@ -791,6 +1065,7 @@ int dg_density_map_device(const dg_field* f, double h, double rho0, int no_reduc
     if (int rc = check_range(&f->desc, l_begin, l_end, g, "dg_density_map")) return rc;
     if (!(h > 0.0)) return fail(DG_ERR_INVALID, "dg_density_map: smoothing length must be > 0");
     if (l_end > l_begin && !d_out) return fail(DG_ERR_INVALID, "dg_density_map: output is NULL");
+    if (int rc = check_handle_device(f->device, "dg_density_map")) return rc;
     DG_LAUNCH(k3_launch_density(f->dev, h, rho0, no_reduction, l_begin, l_end - l_begin, d_out, (cudaStream_t)stream));
     return DG_OK;
 }

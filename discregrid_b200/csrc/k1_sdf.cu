@@ -741,6 +741,21 @@ __global__ void build_cells_kernel(GridDev g, unsigned c_begin, unsigned long lo
 // FMA-contraction probe: a*b+c with operands for which the fused and unfused roundings differ.
 __global__ void fma_probe_kernel(double a, double b, double c, double* out) { out[0] = a * b + c; }
 
+// fp64 issue-rate probe: 8 independent chains of x = x * a + b per thread, compiled (like the whole library) WITHOUT contraction,
+// i.e. one DMUL + one DADD per step -- the instruction mix the bit-exact kernels are restricted to.  Used by bench.py as the measured
+// denominator of K1's / K3's fp64 roofline (there is no fp64 figure in MEASURED_PEAKS.json).
+__global__ void __launch_bounds__(256) fp64_rate_probe_kernel(double a, double b, int iters, double* out)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+        x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;                      // never true: keeps the chains alive
+}
+
 }  // namespace
 
 static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)); }
@@ -1034,6 +1049,12 @@ cudaError_t k1_launch_build_cells(const GridDev& g, uint64_t c_begin, uint64_t c
     if (count == 0) return cudaSuccess;
     const unsigned long long n32 = (unsigned long long)count * 32ull;
     DG_KERNEL_LAUNCH(build_cells_kernel, (unsigned)((n32 + 255) / 256), 256, 0, stream, g, (unsigned)c_begin, n32, d_cells);
+    return DG_AFTER_LAUNCH();
+}
+
+cudaError_t k1_launch_fp64_rate_probe(int blocks, int iters, double* d_out, cudaStream_t stream)
+{
+    DG_KERNEL_LAUNCH(fp64_rate_probe_kernel, blocks, 256, 0, stream, 0.999999, 1.0e-6, iters, d_out);
     return DG_AFTER_LAUNCH();
 }
 

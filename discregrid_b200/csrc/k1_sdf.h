@@ -174,6 +174,7 @@ cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t
                                double* d_near, int* d_ent, int* d_tri, cudaStream_t stream);
 cudaError_t k1_launch_node_positions(const GridDev& g, uint64_t l_begin, uint64_t count, double* d_x, cudaStream_t stream);
 cudaError_t k1_launch_build_cells(const GridDev& g, uint64_t c_begin, uint64_t count, unsigned* d_cells, cudaStream_t stream);
+cudaError_t k1_launch_fp64_rate_probe(int blocks, int iters, double* d_out, cudaStream_t stream);
 cudaError_t k1_launch_fma_probe(double a, double b, double c, double* d_out, cudaStream_t stream);
 
 }  // namespace dgb

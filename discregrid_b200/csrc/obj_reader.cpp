@@ -2,6 +2,7 @@
 #include "obj_reader.h"
 
 #include <algorithm>
+namespace dgb { unsigned host_threads(); }   // host_threads.cpp: affinity mask capped by the cgroup CPU quota
 #include <charconv>
 #include <climits>
 #include <cstdio>
@@ -89,7 +90,7 @@ bool read_obj(const char* path, ObjData& out, std::string& err)
     std::fclose(fp);
     if (got != buf.size()) { err = std::string("short read on ") + path; return false; }
 
-    unsigned nt = std::thread::hardware_concurrency();
+    unsigned nt = dgb::host_threads();
     if (nt == 0) nt = 1;
     if (nt > 32) nt = 32;
     if (buf.size() < (1u << 20)) nt = 1;

@@ -3,6 +3,7 @@
 #include "sort_replay.h"
 
 #include <algorithm>
+namespace dgb { unsigned host_threads(); }   // host_threads.cpp: affinity mask capped by the cgroup CPU quota
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -18,7 +19,7 @@ namespace {
 
 unsigned n_threads()
 {
-    unsigned nt = std::thread::hardware_concurrency();
+    unsigned nt = dgb::host_threads();
     if (nt == 0) nt = 1;
     return nt > 32 ? 32 : nt;
 }

@@ -125,9 +125,16 @@ class CubicLagrangeDiscreteGrid:
         if isinstance(func, MeshSignedDistance):
             if pred is not None:
                 raise TypeError("a sample predicate is only supported with DensityMapFunction")
+            # the whole addFunction in one call: node loop on the GPU, connectivity + cell map written by the library's host threads meanwhile
             coeffs = np.empty(self.nNodes())
-            capi.check(capi.lib.dg_sample_sdf(func.md.handle, C.byref(self._desc), func.sign, 0, len(coeffs),
-                                              capi.ptr(coeffs, capi.F64P)))
+            cells = np.empty((self.m_n_cells, 32), np.uint32)
+            cmap = np.empty(self.m_n_cells, np.uint32)
+            self.last_add_function_ms = np.zeros(6)
+            capi.check(capi.lib.dg_add_function_sdf(func.md.handle, C.byref(self._desc), func.sign, capi.ptr(coeffs, capi.F64P),
+                                                    capi.ptr(cells, capi.U32P), capi.ptr(cmap, capi.U32P), capi.ptr(self.last_add_function_ms, capi.F64P)))
+            self.m_nodes.append(coeffs); self.m_cells.append(cells); self.m_cell_map.append(cmap)
+            self.m_n_fields += 1
+            return self.m_n_fields - 1
         elif isinstance(func, DensityMapFunction):
             coeffs = np.empty(self.nNodes())
             capi.check(capi.lib.dg_density_map(self._device_field(func.field_id), func.h, func.rho0, int(func.no_reduction), 0,

@@ -79,6 +79,9 @@ DG_API int         dg_device_count(void);
 DG_API int         dg_set_device(int device);
 /* Runs the device self-test (FMA-contraction probe + trivial kernel) on the current device. */
 DG_API int         dg_selftest(void);
+/* Measures the fp64 issue rate of the current device for the library's instruction mix (DMUL + DADD, no FMA contraction -- the
+ * numerical contract forbids fused operations): Tflop/s.  bench.py uses it as the measured denominator of the fp64 rooflines. */
+DG_API int         dg_fp64_rate_probe(double* tflops);
 /* Kernels launched by this library in this process since load / last reset (all streams). */
 DG_API uint64_t    dg_kernel_launch_count(void);
 DG_API void        dg_kernel_launch_count_reset(void);
@@ -139,6 +142,15 @@ DG_API int dg_mesh_distance_device(const dg_mesh* mesh, const double* d_points, 
 DG_API int dg_sample_sdf(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* out_host);
 DG_API int dg_sample_sdf_device(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end,
                          double* d_out, void* stream);
+/* The WHOLE of CubicLagrangeDiscreteGrid::addFunction with the GenerateSDF functor (cubic_lagrange_discrete_grid.cpp:780-899) into
+ * the three arrays the reference appends to m_nodes / m_cells / m_cell_map: nodes_host[n_nodes] (the node loop :806-817, on the GPU),
+ * cells_host[n_cells x 32] (connectivity :833-886) and cell_map_host[n_cells] (identity :888-891) -- the two index tables are written
+ * by host threads straight into the caller's memory WHILE the GPU samples the nodes, so the call ends one D2H piece after the last
+ * kernel chunk.  cells_host / cell_map_host may be NULL (skipped).  timings_ms: NULL or 6 doubles = total, node pipeline done,
+ * index tables done, coefficient array pre-faulted (all ms since entry), worker threads used, 0.
+ * This is what the C++ facade's addFunction(MeshSignedDistanceFunction) calls and what bench.py times as `e2e`. */
+DG_API int dg_add_function_sdf(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host,
+                        uint32_t* cell_map_host, double* timings_ms);
 /* Slab sharding of the same loop for one-process-per-GPU jobs ("P1"): part `part` of `n_parts` samples, in ONE launch,
  * whole slow-plane PAIRS of each of the four row-major node arrays (vertex / x-edge nodes: z-slabs; y-edge nodes: x-slabs; z-edge
  * nodes: y-slabs), i.e. no partially filled bricks and a single launch tail per rank.  Results are written at their final positions

@@ -3,8 +3,34 @@
 // cubic_lagrange_discrete_grid.cpp, compiled by oracle/Makefile against the Eigen stand-in oracle/ref_eigen).  Used to pin the
 // oracle's interpolate / shape functions to the reference's code, to generate golden vectors, and as the "reference" CPU
 // baseline of interpolate (the OpenMP pixel-loop pattern of cmd/discrete_field_to_bitmap/main.cpp:118-135).
+// every standard / Eigen header the reference headers pull in is included BEFORE `private` is opened, so only the reference's own
+// class bodies are affected
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <cassert>
+#include <cmath>
+#include <fstream>
+#include <functional>
+#include <future>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+#include <Eigen/Dense>
+#define private public          // only to copy m_nodes / m_cells / m_cell_map out after the reference's own addFunction; no reference code is modified
 #include <Discregrid/All>
+#undef private
 #include <chrono>
+#include <cstring>
 #include <cstdint>
 #include <limits>
 #ifdef _OPENMP
@@ -70,6 +96,51 @@ double refg_reduce_window(void* h, unsigned field, double lo, double hi)
     const auto t0 = std::chrono::steady_clock::now();
     g->reduceField(field, [lo, hi](Vector3d const&, double v) { return lo <= v && v <= hi; });
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// The reference's REAL addFunction with the GenerateSDF functor, exactly as cmd/generate_sdf/main.cpp:74,92-105 drives it:
+// TriangleMeshDistance md(vertices, triangles) (the std::vector overload, TriangleMeshDistance.h:251-267 -- the one the
+// TriangleMesh ctor forwards to, :227-230), CubicLagrangeDiscreteGrid sdf(domain, resolution), func = [&md](x){ return md.signed_distance(x).distance; }
+// (or -1.0 * for --invert), sdf.addFunction(func, verbose=false).  Only the addFunction call is timed (steady_clock), i.e. the
+// OpenMP node loop :806-831, the serial connectivity loop :833-886 and the cell map :888-891 -- what SURVEY 8(d) calls the
+// addFunction wall-clock.  The mesh-distance object is built once and reused (it is outside addFunction's timer in the reference too).
+void* refg_md_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT)
+{
+    std::vector<std::array<double, 3>> v(nV);
+    std::vector<std::array<int, 3>> f(nT);
+    for (uint64_t i = 0; i < nV; i++) v[i] = {V[3 * i], V[3 * i + 1], V[3 * i + 2]};
+    for (uint64_t i = 0; i < nT; i++) f[i] = {(int)F[3 * i], (int)F[3 * i + 1], (int)F[3 * i + 2]};
+    return new Discregrid::TriangleMeshDistance(v, f);
+}
+void refg_md_destroy(void* md) { delete (Discregrid::TriangleMeshDistance*)md; }
+// returns the seconds addFunction took; nodes_out (nullable) receives m_nodes[0], cells_out (nullable) m_cells[0], n_nodes_out the count
+double refg_add_function_sdf(void* md_, const double* dom_min, const double* dom_max, const uint32_t* res, int invert, int nthreads,
+                             double* nodes_out, uint32_t* cells_out, uint64_t* n_nodes_out)
+{
+    auto& md = *(Discregrid::TriangleMeshDistance*)md_;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    Eigen::AlignedBox3d domain(Vector3d(dom_min[0], dom_min[1], dom_min[2]), Vector3d(dom_max[0], dom_max[1], dom_max[2]));
+    std::array<unsigned int, 3> resolution = {{res[0], res[1], res[2]}};
+    CubicLagrangeDiscreteGrid sdf(domain, resolution);
+    auto func = Discregrid::DiscreteGrid::ContinuousFunction{};
+    if (invert) func = [&md](Vector3d const& xi) { return -1.0 * md.signed_distance(xi).distance; };
+    else        func = [&md](Vector3d const& xi) { return md.signed_distance(xi).distance; };
+    const auto t0 = std::chrono::steady_clock::now();
+    sdf.addFunction(func, false);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (n_nodes_out) *n_nodes_out = sdf.m_nodes[0].size();
+    if (nodes_out) std::memcpy(nodes_out, sdf.m_nodes[0].data(), sdf.m_nodes[0].size() * sizeof(double));
+    if (cells_out) std::memcpy(cells_out, sdf.m_cells[0].data(), sdf.m_cells[0].size() * 32 * sizeof(uint32_t));
+    return dt;
+}
+int refg_omp_max_threads()
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
 }
 void refg_save(void* h, const char* path) { ((CubicLagrangeDiscreteGrid*)h)->save(std::string(path)); }
 // the reference's OBJ loader, Discregrid::TriangleMesh(path) (src/mesh/triangle_mesh.cpp:90-124), timed

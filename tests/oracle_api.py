@@ -259,3 +259,42 @@ class RefGrid:
         f.argtypes = [C.c_void_p, C.c_uint, _dp, C.c_uint64, _i32p, _dp, _dp, _dp, _u32p, _dp, _dp]
         f(self.h, field, _p(x, _dp), n, _p(ok, _i32p), _p(N, _dp), _p(dN, _dp), _p(c0, _dp), _p(cell, _u32p), _p(phi, _dp), _p(grad, _dp))
         return ok, N, dN, c0, cell, phi, grad
+
+
+class RefAddFunction:
+    """The reference's REAL CubicLagrangeDiscreteGrid::addFunction with the GenerateSDF functor (oracle/ref_grid_wrapper.cpp:
+    refg_md_create / refg_add_function_sdf; cmd/generate_sdf/main.cpp:74,92-105, cubic_lagrange_discrete_grid.cpp:780-899)."""
+
+    def __init__(self, V, F):
+        self.lib = C.CDLL(REF_GRID_SO)
+        V, F = _f64(V).reshape(-1, 3), _u32(F).reshape(-1, 3)
+        self.lib.refg_md_create.restype = C.c_void_p
+        self.lib.refg_md_create.argtypes = [_dp, C.c_uint64, _u32p, C.c_uint64]
+        self.h = self.lib.refg_md_create(_p(V, _dp), len(V), _p(F, _u32p), len(F))
+        self.lib.refg_add_function_sdf.restype = C.c_double
+        self.lib.refg_add_function_sdf.argtypes = [C.c_void_p, _dp, _dp, _u32p, C.c_int, C.c_int, _dp, _u32p, C.POINTER(C.c_uint64)]
+        self.lib.refg_omp_max_threads.restype = C.c_int
+
+    def max_threads(self):
+        return self.lib.refg_omp_max_threads()
+
+    def add_function(self, mn, mx, res, invert=False, nthreads=0, want_nodes=False, want_cells=False):
+        """-> (seconds of the reference's addFunction call, nodes or None, cells or None)"""
+        mn, mx, res = _f64(mn), _f64(mx), _u32(res)
+        nx, ny, nz = (int(r) for r in res)
+        n_nodes = (nx + 1) * (ny + 1) * (nz + 1) + 2 * (nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz)
+        nodes = np.empty(n_nodes) if want_nodes else None
+        cells = np.empty((nx * ny * nz, 32), np.uint32) if want_cells else None
+        n_out = C.c_uint64()
+        dt = self.lib.refg_add_function_sdf(self.h, _p(mn, _dp), _p(mx, _dp), _p(res, _u32p), int(invert), int(nthreads),
+                                            _p(nodes, _dp), _p(cells, _u32p), C.byref(n_out))
+        assert n_out.value == n_nodes
+        return dt, nodes, cells
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.refg_md_destroy.argtypes = [C.c_void_p]
+            self.lib.refg_md_destroy(self.h)
+            self.h = None
+
+    __del__ = close
