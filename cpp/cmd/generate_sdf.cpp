@@ -1,5 +1,6 @@
 // GenerateSDF -- same command line and output as the reference tool (cmd/generate_sdf/main.cpp:28-130), sampling on the GPU.
-//   GenerateSDF [-r "nx ny nz"] [-d "minx miny minz maxx maxy maxz"] [-i] [-o out.cdf] input.obj
+//   GenerateSDF [-r "nx ny nz"] [-d "minx miny minz maxx maxy maxz"] [-i] [-o out.cdf] [--gpus N] input.obj
+// --gpus N (new, SURVEY 5 "same flags + --gpus N"): the node loop is dealt to N GPUs of this node (dg_add_function_sdf_multi); same file.
 // The one functional change against the reference source: the functor handed to addFunction is the recognisable
 // MeshSignedDistanceFunction instead of an anonymous lambda (main.cpp:94-102).
 #include <Discregrid/All>
@@ -15,18 +16,20 @@ int main(int argc, char* argv[])
     std::array<unsigned int, 3> resolution = {{10, 10, 10}};               // reference default "10 10 10"
     std::string domain_str, output_file, filename;
     bool invert = false;
+    int n_gpus = 1;
     for (int a = 1; a < argc; a++) {
         const std::string s = argv[a];
         auto next = [&]() -> std::string { if (a + 1 >= argc) { std::cerr << "missing value for " << s << std::endl; std::exit(1); } return argv[++a]; };
         if (s == "-h" || s == "--help") {
             std::cout << "Generates a signed distance field from a closed two-manifold triangle mesh.\n"
-                         "  -r, --resolution \"nx ny nz\"   -d, --domain \"minx miny minz maxx maxy maxz\"   -i, --invert   -o, --output file.cdf\n"
+                         "  -r, --resolution \"nx ny nz\"   -d, --domain \"minx miny minz maxx maxy maxz\"   -i, --invert   -o, --output file.cdf   --gpus N\n"
                          "Example: GenerateSDF -r \"50 50 50\" dragon.obj" << std::endl;
             return 0;
         } else if (s == "-r" || s == "--resolution") { std::istringstream is(next()); is >> resolution[0] >> resolution[1] >> resolution[2]; }
         else if (s == "-d" || s == "--domain") domain_str = next();
         else if (s == "-i" || s == "--invert") invert = true;
         else if (s == "-o" || s == "--output") output_file = next();
+        else if (s == "--gpus") n_gpus = std::atoi(next().c_str());
         else filename = s;
     }
     if (filename.empty()) { std::cout << "ERROR: No input mesh given." << std::endl; return 1; }
@@ -37,6 +40,7 @@ int main(int argc, char* argv[])
         std::cout << "DONE" << std::endl;
         std::cout << "Set up data structures...";
         Discregrid::TriangleMeshDistance md(mesh);
+        if (n_gpus > 1) md.useGpus(n_gpus);
         std::cout << "DONE" << std::endl;
 
         AlignedBox3d domain;

@@ -114,8 +114,12 @@ public:
             FieldVector<double> coeffs(n_nodes);
             FieldVector<std::array<unsigned int, 32>> cells(m_n_cells);
             FieldVector<unsigned int> cell_map(m_n_cells);
-            check(dg_add_function_sdf(sdf->md->handle(), &d, sdf->sign, coeffs.data(), reinterpret_cast<std::uint32_t*>(cells.data()), cell_map.data(),
-                                      m_last_add_function_ms));
+            if (sdf->md->group())             // TriangleMeshDistance::useGpus(n): the same call spread over n GPUs
+                check(dg_add_function_sdf_multi(sdf->md->group(), &d, sdf->sign, coeffs.data(), reinterpret_cast<std::uint32_t*>(cells.data()), cell_map.data(),
+                                                m_last_add_function_ms));
+            else
+                check(dg_add_function_sdf(sdf->md->handle(), &d, sdf->sign, coeffs.data(), reinterpret_cast<std::uint32_t*>(cells.data()), cell_map.data(),
+                                          m_last_add_function_ms));
             if (verbose) std::cout << "Construction: " << n_nodes << " nodes sampled on the GPU in " << m_last_add_function_ms[0] << " ms" << std::endl;
             invalidate();
             m_nodes.push_back(std::move(coeffs)); m_cells.push_back(std::move(cells)); m_cell_map.push_back(std::move(cell_map));

@@ -43,7 +43,7 @@ public:
     TriangleMeshDistance() = default;
     TriangleMeshDistance(const TriangleMeshDistance&) = delete;
     TriangleMeshDistance& operator=(const TriangleMeshDistance&) = delete;
-    ~TriangleMeshDistance() { if (m_mesh) dg_mesh_destroy(m_mesh); }
+    ~TriangleMeshDistance() { if (m_group) dg_mesh_group_destroy(m_group); if (m_mesh) dg_mesh_destroy(m_mesh); }
 
     template <typename FLOAT, typename INT, typename SIZE_T>
     TriangleMeshDistance(const FLOAT* vertices, const SIZE_T n_vertices, const INT* triangles, const SIZE_T n_triangles) { construct(vertices, n_vertices, triangles, n_triangles); }
@@ -79,12 +79,22 @@ public:
 
     bool is_constructed() const { return m_mesh != nullptr; }
     const dg_mesh* handle() const { require(); return m_mesh; }
+    // new: spread addFunction over n GPUs of this node (`GenerateSDF --gpus N`): the device records are replicated once, by peer copies
+    void useGpus(int n_gpus)
+    {
+        require();
+        if (m_group) { dg_mesh_group_destroy(m_group); m_group = nullptr; }
+        if (n_gpus > 1 && dg_mesh_group_create(m_mesh, n_gpus, nullptr, &m_group) != DG_OK) throw std::runtime_error(std::string("TriangleMeshDistance: ") + dg_last_error());
+    }
+    dg_mesh_group* group() const { return m_group; }
 
 private:
     dg_mesh* m_mesh = nullptr;
+    dg_mesh_group* m_group = nullptr;
     void require() const { if (!m_mesh) throw std::runtime_error("DistanceTriangleMesh error: not constructed."); }
     void upload(const std::vector<double>& V, const std::vector<uint32_t>& F)
     {
+        if (m_group) { dg_mesh_group_destroy(m_group); m_group = nullptr; }
         if (m_mesh) { dg_mesh_destroy(m_mesh); m_mesh = nullptr; }
         if (F.empty()) throw std::runtime_error("DistanceTriangleMesh error: Empty triangle list.");
         if (dg_mesh_create(V.data(), V.size() / 3, F.data(), F.size() / 3, &m_mesh) != DG_OK) throw std::runtime_error(std::string("TriangleMeshDistance: ") + dg_last_error());

@@ -68,6 +68,11 @@ SIGNATURES = {
     "dg_mesh_distance_device": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "dg_sample_sdf": (C.c_int, [_vp, _gp, C.c_double, C.c_uint64, C.c_uint64, _dp]),
     "dg_add_function_sdf": (C.c_int, [_vp, _gp, C.c_double, _dp, _u32p, _u32p, _dp]),
+    "dg_mesh_group_create": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]),
+    "dg_mesh_group_destroy": (C.c_int, [_vp]),
+    "dg_mesh_group_size": (C.c_int, [_vp]),
+    "dg_add_function_sdf_multi": (C.c_int, [_vp, _gp, C.c_double, _dp, _u32p, _u32p, _dp]),
+    "dg_sample_sdf_multi_device": (C.c_int, [_vp, _gp, C.c_double, C.POINTER(_vp)]),
     "dg_sample_sdf_device": (C.c_int, [_vp, _gp, C.c_double, C.c_uint64, C.c_uint64, _vp, _vp]),
     "dg_slab_ranges": (C.c_int, [_gp, C.c_uint32, C.c_uint32, _u64p]),
     "dg_sample_sdf_slab_device": (C.c_int, [_vp, _gp, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp]),

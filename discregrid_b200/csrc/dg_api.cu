@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -20,6 +21,15 @@
 #include <cuda_runtime.h>
 #if defined(__linux__)
 #include <sys/mman.h>
+#endif
+
+// NCCL is used through dlopen (multi-GPU section): only its types are needed at build time
+#if __has_include(<nccl.h>) && !defined(DG_EMU)
+#include <nccl.h>
+#include <dlfcn.h>
+#define DG_HAVE_NCCL 1
+#else
+#define DG_HAVE_NCCL 0
 #endif
 
 #include "bvh_build.h"
@@ -85,6 +95,15 @@ int check_handle_device(int handle_device, const char* who)
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(DG_ERR_NO_DEVICE, "%s: no current CUDA device", who); }
     if (dev != handle_device) return fail(DG_ERR_INVALID, "%s: the handle lives on device %d but the current device is %d (dg_set_device)", who, handle_device, dev);
     return DG_OK;
+}
+
+// page-locked host memory (cudaMallocHost / cudaHostRegister, by any CUDA runtime instance of the process) can be DMA'd directly
+bool is_pinned_host(const void* p)
+{
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 
 // simple owning device buffer
@@ -605,6 +624,63 @@ static void fill_cells_host(const GridDev& g, uint64_t c0, uint64_t c1, uint32_t
     }
 }
 
+// Host side of addFunction while the GPU samples the nodes: worker threads pre-fault the coefficient array (content-preserving: the
+// D2H pipeline may already be writing there), then write the connectivity table (:833-886) and the identity cell map (:888-891)
+// straight into the caller's memory -- 4 MiB blocks dealt dynamically.
+namespace {
+struct HostTablesJob {
+    GridDev g; uint64_t n_nodes = 0, n_cells = 0;
+    double* nodes = nullptr; uint32_t* cells = nullptr; uint32_t* cell_map = nullptr;
+    std::atomic<uint64_t> next_task{0};
+    std::atomic<int> prefault_left{0};
+    uint64_t nb_nodes = 0, nb_cells = 0, nb_map = 0, n_tasks = 0;
+    static constexpr uint64_t blk = 4u << 20;
+    std::chrono::steady_clock::time_point t0;
+    double ms_prefault = 0.0;
+    unsigned n_workers = 0;
+    std::vector<std::thread> th;
+    void work()
+    {
+        for (;;) {
+            const uint64_t t = next_task.fetch_add(1);
+            if (t >= n_tasks) break;
+            if (t < nb_nodes) {
+                char* p = reinterpret_cast<char*>(nodes);
+                const uint64_t b = t * blk, e = std::min<uint64_t>(n_nodes * 8, b + blk);
+                prefault_preserving(p + b, e - b);
+                if (prefault_left.fetch_sub(1) == 1) ms_prefault = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            } else if (t < nb_nodes + nb_cells) {
+                const uint64_t per = blk / 128, c0 = (t - nb_nodes) * per, c1 = std::min<uint64_t>(n_cells, c0 + per);
+                fill_cells_host(g, c0, c1, cells + 32 * c0);
+            } else {
+                const uint64_t per = blk / 4, c0 = (t - nb_nodes - nb_cells) * per, c1 = std::min<uint64_t>(n_cells, c0 + per);
+                for (uint64_t c = c0; c < c1; c++) cell_map[c] = (uint32_t)c;
+            }
+        }
+    }
+    void start(const GridDev& g_, uint64_t n_nodes_, double* nodes_, uint32_t* cells_, uint32_t* cell_map_, unsigned reserve_threads)
+    {
+        g = g_; n_nodes = n_nodes_; n_cells = (uint64_t)g.n[0] * g.n[1] * g.n[2];
+        nodes = nodes_; cells = cells_; cell_map = cell_map_;
+        nb_nodes = (n_nodes * 8 + blk - 1) / blk;
+        nb_cells = cells ? (n_cells * 128 + blk - 1) / blk : 0;
+        nb_map = cell_map ? (n_cells * 4 + blk - 1) / blk : 0;
+        n_tasks = nb_nodes + nb_cells + nb_map;
+        prefault_left = (int)std::min<uint64_t>(nb_nodes, 0x7fffffff);
+        t0 = std::chrono::steady_clock::now();
+        const unsigned hw = host_threads();
+        n_workers = std::max(1u, std::min(hw > reserve_threads + 1 ? hw - reserve_threads - 1 : 1u, 24u));
+        try { for (unsigned k = 0; k < n_workers; k++) th.emplace_back([this]() { work(); }); } catch (...) { /* fewer workers: finish() does the rest */ }
+    }
+    void finish()
+    {
+        work();                                         // whatever is left
+        for (auto& t : th) t.join();
+        th.clear();
+    }
+};
+}  // namespace
+
 // The whole of CubicLagrangeDiscreteGrid::addFunction(GenerateSDF functor) into the caller's three arrays
 // (cubic_lagrange_discrete_grid.cpp:780-899): node loop on the GPU (K1 chunks on two streams, D2H through the pinned double
 // buffer), and -- while the GPU works -- the host threads write the 32-index connectivity table (:833-886) and the identity cell
@@ -620,53 +696,292 @@ int dg_add_function_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign,
     if (int rc = check_range(grid, 0, n_nodes, g, "dg_add_function_sdf")) return rc;
     if (!nodes_host) return fail(DG_ERR_INVALID, "dg_add_function_sdf: nodes output is NULL");
     if (int rc = check_handle_device(m->device, "dg_add_function_sdf")) return rc;
-    const uint64_t n_cells = (uint64_t)g.n[0] * g.n[1] * g.n[2];
     const auto t0 = std::chrono::steady_clock::now();
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
-    const unsigned hw = host_threads();
-    const unsigned n_workers = std::max(1u, std::min(hw > 2 ? hw - 2 : 1u, 24u));      // the calling thread drives the GPU pipeline
-    std::atomic<uint64_t> next_task{0};
-    double ms_prefault = 0.0, ms_cells = 0.0;
-    // tasks, in this order: pre-fault the coefficient array (one write per page: the pages are about to be overwritten by the
-    // pipeline's memcpy), then the cell table, then the cell map -- 4 MiB blocks dealt dynamically to the workers
-    const uint64_t blk = 4u << 20;
-    const uint64_t nb_nodes = (n_nodes * 8 + blk - 1) / blk;
-    const uint64_t nb_cells = cells_host ? (n_cells * 128 + blk - 1) / blk : 0;
-    const uint64_t nb_map = cell_map_host ? (n_cells * 4 + blk - 1) / blk : 0;
-    const uint64_t n_tasks = nb_nodes + nb_cells + nb_map;
-    std::atomic<int> prefault_left{(int)std::min<uint64_t>(nb_nodes, 0x7fffffff)};
-    auto worker = [&]() {
-        for (;;) {
-            const uint64_t t = next_task.fetch_add(1);
-            if (t >= n_tasks) break;
-            if (t < nb_nodes) {
-                // content-preserving (the pipeline's memcpy may already be writing here): MADV_POPULATE_WRITE, else a locked `or 0` per page
-                char* p = reinterpret_cast<char*>(nodes_host);
-                const uint64_t b = t * blk, e = std::min<uint64_t>(n_nodes * 8, b + blk);
-                prefault_preserving(p + b, e - b);
-                if (prefault_left.fetch_sub(1) == 1) ms_prefault = ms_since(t0);
-            } else if (t < nb_nodes + nb_cells) {
-                const uint64_t per = blk / 128, c0 = (t - nb_nodes) * per, c1 = std::min<uint64_t>(n_cells, c0 + per);
-                fill_cells_host(g, c0, c1, cells_host + 32 * c0);
-            } else {
-                const uint64_t per = blk / 4, c0 = (t - nb_nodes - nb_cells) * per, c1 = std::min<uint64_t>(n_cells, c0 + per);
-                for (uint64_t c = c0; c < c1; c++) cell_map_host[c] = (uint32_t)c;
-            }
-        }
-    };
-    std::vector<std::thread> th;
-    try { for (unsigned k = 0; k < n_workers; k++) th.emplace_back(worker); } catch (...) { /* fewer workers: the calling thread finishes the tasks below */ }
+    const unsigned copy_threads = std::min(4u, std::max(1u, host_threads() / 4));
+    HostTablesJob job;
+    job.start(g, n_nodes, nodes_host, cells_host, cell_map_host, copy_threads);
     int rc;
     {
         std::lock_guard<std::mutex> lock(g_pool.mu);
-        rc = sample_sdf_host_locked(m, g, sign, 0, n_nodes, nodes_host, std::min(4u, std::max(1u, hw / 4)));
+        rc = sample_sdf_host_locked(m, g, sign, 0, n_nodes, nodes_host, copy_threads);
     }
     const double ms_nodes = ms_since(t0);
-    worker();                                           // whatever is left
-    for (auto& t : th) t.join();
-    ms_cells = ms_since(t0);
-    if (timings_ms) { timings_ms[0] = ms_since(t0); timings_ms[1] = ms_nodes; timings_ms[2] = ms_cells; timings_ms[3] = ms_prefault; timings_ms[4] = (double)n_workers; timings_ms[5] = 0.0; }
+    job.finish();
+    if (timings_ms) { timings_ms[0] = ms_since(t0); timings_ms[1] = ms_nodes; timings_ms[2] = timings_ms[0]; timings_ms[3] = job.ms_prefault; timings_ms[4] = (double)job.n_workers; timings_ms[5] = 1.0; }
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU from ONE process
+// `dg_sample_sdf(..., n_gpus, ...)`.  A dg_mesh_group replicates a mesh's device records on further GPUs (peer
+// copies over NVLink from the first device, no second host build) and keeps per-device streams, buffers and -- for the device-resident
+// form -- one NCCL communicator per device (ncclCommInitAll; libnccl is loaded at first use, the library does not link it).
+// Work split: plane pairs of the four node arrays dealt round-robin (the interleaved layout of k1_sdf.cu), every part one launch.
+
+struct dg_mesh_group {
+    struct PerDev {
+        cudaStream_t st[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        double* d_buf = nullptr; size_t d_cap = 0;          // host form: 2 slots; device form: n exchange slots
+        double* h_stage = nullptr; size_t h_cap = 0;        // pinned staging (pageable destinations only)
+        void* comm = nullptr;                               // ncclComm_t
+    };
+    int n = 0;
+    std::vector<int> devices;
+    std::vector<dg_mesh*> parts;                            // parts[0] is the caller's mesh (not owned); the others are replicas
+    std::vector<PerDev> dev;
+    bool comms_ready = false;
+    std::mutex mu;
+};
+
+namespace {
+#if DG_HAVE_NCCL
+struct NcclApi {
+    void* so = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load()
+    {
+        if (so) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { so = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (so) break; }
+        if (!so) return false;
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(so, "ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(so, "ncclCommDestroy"));
+        AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(so, "ncclAllGather"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(so, "ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(so, "ncclGroupEnd"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(so, "ncclGetErrorString"));
+        return CommInitAll && CommDestroy && AllGather && GroupStart && GroupEnd && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+#endif
+
+struct DeviceGuard {                                  // restores the caller's current device
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int group_grow(dg_mesh_group::PerDev& d, size_t dev_elems, size_t host_elems)
+{
+    if (dev_elems > d.d_cap) {
+        if (d.d_buf) cudaFree(d.d_buf);
+        d.d_buf = nullptr; d.d_cap = 0;
+        DG_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.d_buf), dev_elems * sizeof(double)));
+        d.d_cap = dev_elems;
+    }
+    if (host_elems > d.h_cap) {
+        if (d.h_stage) cudaFreeHost(d.h_stage);
+        d.h_stage = nullptr; d.h_cap = 0;
+        DG_CUDA(cudaMallocHost(reinterpret_cast<void**>(&d.h_stage), host_elems * sizeof(double)));
+        d.h_cap = host_elems;
+    }
+    return DG_OK;
+}
+}  // namespace
+
+int dg_mesh_group_destroy(dg_mesh_group* grp)
+{
+    if (!grp) return DG_OK;
+    DeviceGuard guard;
+    for (int i = 0; i < grp->n; i++) {
+        if (cudaSetDevice(grp->devices[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+        auto& d = grp->dev[i];
+#if DG_HAVE_NCCL
+        if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(d.comm));
+#endif
+        for (int k = 0; k < 2; k++) { if (d.st[k]) cudaStreamDestroy(d.st[k]); if (d.ev[k]) cudaEventDestroy(d.ev[k]); }
+        if (d.d_buf) cudaFree(d.d_buf);
+        if (d.h_stage) cudaFreeHost(d.h_stage);
+        if (i > 0) delete grp->parts[i];
+    }
+    delete grp;
+    return DG_OK;
+}
+
+int dg_mesh_group_create(const dg_mesh* mesh, int n_gpus, const int* devices, dg_mesh_group** out)
+{
+    if (!out) return fail(DG_ERR_INVALID, "dg_mesh_group_create: out is NULL");
+    *out = nullptr;
+    if (!mesh) return fail(DG_ERR_INVALID, "dg_mesh_group_create: mesh is NULL (not constructed)");
+    if (int rc = require_device()) return rc;
+    const int have = dg_device_count();
+    if (n_gpus < 1 || n_gpus > 16 || n_gpus > have) return fail(DG_ERR_INVALID, "dg_mesh_group_create: n_gpus = %d, but 1..min(16, %d visible devices) are possible", n_gpus, have);
+    std::unique_ptr<dg_mesh_group, int (*)(dg_mesh_group*)> grp(new (std::nothrow) dg_mesh_group(), dg_mesh_group_destroy);
+    if (!grp) return fail(DG_ERR_NOMEM, "dg_mesh_group_create: out of host memory");
+    grp->devices.push_back(mesh->device);
+    for (int k = 0, next = 0; k < n_gpus - 1; k++) {
+        int dv;
+        if (devices) { dv = devices[k + 1]; if (devices[0] != mesh->device) return fail(DG_ERR_INVALID, "dg_mesh_group_create: devices[0] must be the mesh's device (%d)", mesh->device); }
+        else { while (next == mesh->device) next++; dv = next++; }
+        if (dv < 0 || dv >= have || std::find(grp->devices.begin(), grp->devices.end(), dv) != grp->devices.end())
+            return fail(DG_ERR_INVALID, "dg_mesh_group_create: bad or repeated device id %d", dv);
+        grp->devices.push_back(dv);
+    }
+    grp->dev.resize(n_gpus);
+    grp->parts.push_back(const_cast<dg_mesh*>(mesh));
+    DeviceGuard guard;
+    const size_t nT = mesh->host.n_triangles;
+    for (int i = 0; i < n_gpus; i++) {
+        DG_CUDA(cudaSetDevice(grp->devices[i]));
+        grp->n = i + 1;                                             // destroy() only visits initialised entries
+        auto& d = grp->dev[i];
+        for (int k = 0; k < 2; k++) { DG_CUDA(cudaStreamCreateWithFlags(&d.st[k], cudaStreamNonBlocking)); DG_CUDA(cudaEventCreateWithFlags(&d.ev[k], cudaEventDisableTiming)); }
+        if (i == 0) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, grp->devices[i], mesh->device) == cudaSuccess && can) { if (cudaDeviceEnablePeerAccess(mesh->device, 0) != cudaSuccess) cudaGetLastError(); }
+        dg_mesh* r = new (std::nothrow) dg_mesh();
+        if (!r) return fail(DG_ERR_NOMEM, "dg_mesh_group_create: out of host memory");
+        grp->parts.push_back(r);
+        r->device = grp->devices[i];
+        r->host.n_triangles = mesh->host.n_triangles; r->host.n_vertices = mesh->host.n_vertices; r->host.flags = mesh->host.flags;
+        DG_CUDA(r->d_spheres.alloc(nT)); DG_CUDA(r->d_leaves.alloc(nT)); DG_CUDA(r->d_normals.alloc(nT)); DG_CUDA(r->d_nodes_f.alloc(nT * K1_NODEF_STRIDE));
+        DG_CUDA(cudaMemcpyPeer(r->d_spheres.p, r->device, mesh->d_spheres.p, mesh->device, nT * sizeof(SpherePair)));
+        DG_CUDA(cudaMemcpyPeer(r->d_leaves.p, r->device, mesh->d_leaves.p, mesh->device, nT * sizeof(LeafRecord)));
+        DG_CUDA(cudaMemcpyPeer(r->d_normals.p, r->device, mesh->d_normals.p, mesh->device, nT * sizeof(PseudoNormals)));
+        DG_CUDA(cudaMemcpyPeer(r->d_nodes_f.p, r->device, mesh->d_nodes_f.p, mesh->device, nT * K1_NODEF_STRIDE * sizeof(float4)));
+        r->dev = mesh->dev;
+        r->dev.spheres = r->d_spheres.p; r->dev.leaves = r->d_leaves.p; r->dev.normals = r->d_normals.p; r->dev.nodes_f = r->d_nodes_f.p;
+#if K1_LEAF_FILTER
+        DG_CUDA(r->d_leaves_f.alloc(nT));
+        DG_CUDA(cudaMemcpyPeer(r->d_leaves_f.p, r->device, mesh->d_leaves_f.p, mesh->device, nT * sizeof(LeafF)));
+        r->dev.leaves_f = r->d_leaves_f.p;
+#endif
+#if K1_FAST_DIV
+        DG_CUDA(r->d_recips.alloc(nT));
+        DG_CUDA(cudaMemcpyPeer(r->d_recips.p, r->device, mesh->d_recips.p, mesh->device, nT * sizeof(LeafRecip)));
+        r->dev.recips = r->d_recips.p;
+#endif
+        DG_CUDA(k1_configure(r->dev.stack_depth));
+        DG_CUDA(cudaDeviceSynchronize());
+    }
+    *out = grp.release();
+    return DG_OK;
+}
+
+int dg_mesh_group_size(const dg_mesh_group* grp) { return grp ? grp->n : 0; }
+
+// addFunction across the group's GPUs, host arrays out.  n x 2 parts (two launches per GPU on two streams, so that the D2H of a
+// GPU's first part runs under its second launch); each GPU is driven by its own host thread and DMAs the contiguous plane-pair runs
+// of its parts to their final positions (directly when nodes_host is page-locked, else through pinned staging).  No collective is
+// needed: the exchange target is host memory.  cells_host / cell_map_host as in dg_add_function_sdf (nullable).
+int dg_add_function_sdf_multi(dg_mesh_group* grp, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host,
+                              uint32_t* cell_map_host, double* timings_ms)
+{
+    if (!grp) return fail(DG_ERR_INVALID, "dg_add_function_sdf_multi: group is NULL");
+    GridDev g;
+    uint64_t n_nodes = 0;
+    if (grid && dg_grid_num_nodes(grid->resolution, &n_nodes)) return DG_ERR_INVALID;
+    if (int rc = check_range(grid, 0, n_nodes, g, "dg_add_function_sdf_multi")) return rc;
+    if (!nodes_host) return fail(DG_ERR_INVALID, "dg_add_function_sdf_multi: nodes output is NULL");
+    std::lock_guard<std::mutex> lock(grp->mu);
+    const int n = grp->n;
+    const unsigned splits = (2 * n <= 16) ? 2u : 1u;
+    InterleavedLayout L;
+    if (!k1_interleaved_layout(g, (unsigned)n * splits, L)) return fail(DG_ERR_INVALID, "dg_add_function_sdf_multi: grid too large for the exchange layout");
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+    const bool direct = is_pinned_host(nodes_host);
+    HostTablesJob job;
+    job.start(g, n_nodes, nodes_host, cells_host, cell_map_host, (unsigned)n);
+    std::vector<int> rcs(n, DG_OK);
+    std::vector<std::string> errs(n);
+    std::vector<uint64_t> launches(n, 0);
+    auto drive = [&](int i) -> int {
+        DG_CUDA(cudaSetDevice(grp->devices[i]));
+        auto& d = grp->dev[i];
+        if (int rc = group_grow(d, (size_t)splits * L.slot_elems, direct ? 0 : (size_t)splits * L.slot_elems)) return rc;
+        std::vector<K1Run> runs[2];
+        for (unsigned sp = 0; sp < splits; sp++) {
+            const unsigned part = (unsigned)i + sp * (unsigned)n;
+            double* d_slot = d.d_buf + (size_t)sp * L.slot_elems;
+            DG_CUDA(k1_launch_sample_interleaved(grp->parts[i]->dev, g, sign, L, part, d_slot, d.st[sp]));
+            launches[i]++;
+            k1_interleaved_runs(g, L, part, runs[sp]);
+            uint64_t used = 0;
+            for (const auto& r : runs[sp]) used = std::max<uint64_t>(used, r.slot_pos + r.count);
+            if (direct) { for (const auto& r : runs[sp]) DG_CUDA(cudaMemcpyAsync(nodes_host + r.node_begin, d_slot + r.slot_pos, r.count * sizeof(double), cudaMemcpyDeviceToHost, d.st[sp])); }
+            else if (used) DG_CUDA(cudaMemcpyAsync(d.h_stage + (size_t)sp * L.slot_elems, d_slot, used * sizeof(double), cudaMemcpyDeviceToHost, d.st[sp]));
+            DG_CUDA(cudaEventRecord(d.ev[sp], d.st[sp]));
+        }
+        for (unsigned sp = 0; sp < splits; sp++) {
+            DG_CUDA(cudaEventSynchronize(d.ev[sp]));
+            if (!direct) for (const auto& r : runs[sp]) std::memcpy(nodes_host + r.node_begin, d.h_stage + (size_t)sp * L.slot_elems + r.slot_pos, r.count * sizeof(double));
+        }
+        return DG_OK;
+    };
+    {
+        DeviceGuard guard;
+        std::vector<std::thread> th;
+        for (int i = 1; i < n; i++) th.emplace_back([&, i]() { DeviceGuard tg; rcs[i] = drive(i); if (rcs[i] != DG_OK) errs[i] = g_err; });
+        rcs[0] = drive(0);
+        if (rcs[0] != DG_OK) errs[0] = g_err;
+        for (auto& t : th) t.join();
+    }
+    const double ms_nodes = ms_since(t0);
+    job.finish();
+    for (int i = 0; i < n; i++) g_launches.fetch_add(launches[i]);
+    if (timings_ms) { timings_ms[0] = ms_since(t0); timings_ms[1] = ms_nodes; timings_ms[2] = timings_ms[0]; timings_ms[3] = job.ms_prefault; timings_ms[4] = (double)job.n_workers; timings_ms[5] = (double)n; }
+    for (int i = 0; i < n; i++) if (rcs[i] != DG_OK) return fail(rcs[i], "dg_add_function_sdf_multi (device %d): %s", grp->devices[i], errs[i].c_str());
+    return DG_OK;
+}
+
+// Device-resident form (the coefficient array is needed on every GPU, e.g. for K2/K3 replicas): GPU i samples part i of n into its
+// slot of an n x slot_elems exchange buffer, ONE in-place ncclAllGather per device (grouped) moves the slots over NVLink, and an
+// unpack kernel scatters them into the reference's node order in d_out[i] (device i's memory, n_nodes doubles each).
+int dg_sample_sdf_multi_device(dg_mesh_group* grp, const dg_grid_desc* grid, double sign, double* const* d_out)
+{
+    if (!grp || !d_out) return fail(DG_ERR_INVALID, "dg_sample_sdf_multi_device: NULL argument");
+    GridDev g;
+    uint64_t n_nodes = 0;
+    if (grid && dg_grid_num_nodes(grid->resolution, &n_nodes)) return DG_ERR_INVALID;
+    if (int rc = check_range(grid, 0, n_nodes, g, "dg_sample_sdf_multi_device")) return rc;
+    std::lock_guard<std::mutex> lock(grp->mu);
+    const int n = grp->n;
+    for (int i = 0; i < n; i++) if (!d_out[i]) return fail(DG_ERR_INVALID, "dg_sample_sdf_multi_device: d_out[%d] is NULL", i);
+    InterleavedLayout L;
+    if (!k1_interleaved_layout(g, (unsigned)n, L)) return fail(DG_ERR_INVALID, "dg_sample_sdf_multi_device: grid too large for the exchange layout");
+    DeviceGuard guard;
+#if DG_HAVE_NCCL
+    if (n > 1 && !grp->comms_ready) {
+        if (!g_nccl.load()) return fail(DG_ERR_CUDA, "dg_sample_sdf_multi_device: libnccl.so.2 could not be loaded (%s)", dlerror() ? dlerror() : "missing symbol");
+        std::vector<ncclComm_t> comms(n);
+        const ncclResult_t r = g_nccl.CommInitAll(comms.data(), n, grp->devices.data());
+        if (r != ncclSuccess) return fail(DG_ERR_CUDA, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
+        for (int i = 0; i < n; i++) grp->dev[i].comm = comms[i];
+        grp->comms_ready = true;
+    }
+#else
+    if (n > 1) return fail(DG_ERR_CUDA, "dg_sample_sdf_multi_device: built without NCCL");
+#endif
+    for (int i = 0; i < n; i++) {
+        DG_CUDA(cudaSetDevice(grp->devices[i]));
+        if (int rc = group_grow(grp->dev[i], (size_t)n * L.slot_elems, 0)) return rc;
+        DG_LAUNCH(k1_launch_sample_interleaved(grp->parts[i]->dev, g, sign, L, (unsigned)i, grp->dev[i].d_buf + (size_t)i * L.slot_elems, grp->dev[i].st[0]));
+    }
+#if DG_HAVE_NCCL
+    if (n > 1) {
+        ncclResult_t r = g_nccl.GroupStart();
+        for (int i = 0; i < n && r == ncclSuccess; i++)
+            r = g_nccl.AllGather(grp->dev[i].d_buf + (size_t)i * L.slot_elems, grp->dev[i].d_buf, L.slot_elems, ncclDouble, static_cast<ncclComm_t>(grp->dev[i].comm), grp->dev[i].st[0]);
+        const ncclResult_t r2 = g_nccl.GroupEnd();
+        if (r != ncclSuccess || r2 != ncclSuccess) return fail(DG_ERR_CUDA, "ncclAllGather failed: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
+    }
+#endif
+    for (int i = 0; i < n; i++) {
+        DG_CUDA(cudaSetDevice(grp->devices[i]));
+        DG_LAUNCH(k1_launch_unpack_interleaved(g, L, grp->dev[i].d_buf, d_out[i], grp->dev[i].st[0]));
+    }
+    for (int i = 0; i < n; i++) {
+        DG_CUDA(cudaSetDevice(grp->devices[i]));
+        DG_CUDA(cudaStreamSynchronize(grp->dev[i].st[0]));
+    }
+    return DG_OK;
 }
 
 // plane ranges of part `part` of `n_parts`: boundaries fall on even plane indices (a brick spans K1_BRICK_S = 2 planes)
@@ -973,14 +1288,6 @@ struct InterpPool {
     }
 };
 InterpPool g_ipool;
-
-bool is_pinned_host(const void* p)
-{
-    if (!p) return true;
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
-}
 
 void threaded_copy(void* dst, const void* src, size_t bytes, unsigned nt)
 {

@@ -29,6 +29,8 @@
 
 #include <cfloat>
 #include <mutex>
+#include <vector>
+#include <algorithm>
 
 #include "dg_launch.h"       // DG_KERNEL_LAUNCH: <<<>>> on the device, fibers under tests/emu (DG_EMU)
 #if K1_BRICK_AUTO
@@ -1018,6 +1020,26 @@ void k1_interleaved_node_slots(const GridDev& g, const InterleavedLayout& L, uin
         const unsigned long long pos = interleaved_slot_of(g, L, l_begin + i, r);
         if (part_out) part_out[i] = r;
         if (pos_out) pos_out[i] = pos;
+    }
+}
+
+// The contiguous runs of part `part`: every plane group it owns is one run, contiguous both in the slot and in the node array.
+void k1_interleaved_runs(const GridDev& g, const InterleavedLayout& L, unsigned part, std::vector<K1Run>& runs)
+{
+    uint64_t base[4]; unsigned dims[4][3];
+    node_arrays(g, base, dims);
+    runs.clear();
+    for (int a = 0; a < 4; a++) {
+        const unsigned bs = LAY_BS(L, a);
+        for (unsigned pair = part; pair < L.pairs[a]; pair += L.n_parts) {
+            const unsigned s0 = pair * bs, s1 = std::min(dims[a][0], s0 + bs);
+            K1Run r;
+            r.node_begin = base[a] + (uint64_t)s0 * L.plane[a];
+            r.count = (uint64_t)(s1 - s0) * L.plane[a];
+            unsigned owner;
+            r.slot_pos = interleaved_slot_of(g, L, r.node_begin, owner);
+            runs.push_back(r);
+        }
     }
 }
 

@@ -1,6 +1,7 @@
 // Launch interface of the K1 kernels (k1_sdf.cu).  Host-callable, no kernel code here.
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 #include "bvh_build.h"
 #include "dg_device.cuh"
@@ -169,6 +170,8 @@ bool k1_interleaved_layout(const GridDev& g, unsigned n_parts, InterleavedLayout
 cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, double sign, const InterleavedLayout& L, unsigned part,
                                          double* d_slot, cudaStream_t stream);
 void k1_interleaved_node_slots(const GridDev& g, const InterleavedLayout& L, uint64_t l_begin, uint64_t count, uint32_t* part_out, uint64_t* pos_out);
+struct K1Run { uint64_t slot_pos, node_begin, count; };      // slot[slot_pos .. +count) == nodes[node_begin .. +count)
+void k1_interleaved_runs(const GridDev& g, const InterleavedLayout& L, unsigned part, std::vector<K1Run>& runs);
 cudaError_t k1_launch_unpack_interleaved(const GridDev& g, const InterleavedLayout& L, const double* d_slots, double* d_nodes, cudaStream_t stream);
 cudaError_t k1_launch_distance(const DeviceBvh& m, const double* d_pts, uint64_t count, int is_signed, double* d_dist,
                                double* d_near, int* d_ent, int* d_tri, cudaStream_t stream);

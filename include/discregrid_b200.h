@@ -151,6 +151,24 @@ DG_API int dg_sample_sdf_device(const dg_mesh* mesh, const dg_grid_desc* grid, d
  * This is what the C++ facade's addFunction(MeshSignedDistanceFunction) calls and what bench.py times as `e2e`. */
 DG_API int dg_add_function_sdf(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host,
                         uint32_t* cell_map_host, double* timings_ms);
+/* ---- multi-GPU from ONE process (`dg_sample_sdf(..., n_gpus, ...)`; 8e) -------------------------------------------
+ * A dg_mesh_group replicates the device records of `mesh` on n_gpus - 1 further GPUs (peer copies from the mesh's device; the host
+ * build is not repeated).  devices: NULL = the mesh's device first, then the lowest other ids; else n_gpus ids with devices[0] == the
+ * mesh's device.  The group borrows `mesh` (destroy the group first).  n_gpus = 1 is valid (same code path on one GPU).
+ *   dg_add_function_sdf_multi : dg_add_function_sdf across the group -- plane pairs of the four node arrays dealt round-robin to
+ *       2 x n_gpus parts, one host thread and two streams per GPU, every part DMA'd to its final place in nodes_host (directly if that
+ *       memory is page-locked, else through pinned staging); index tables by host threads meanwhile.  No collective: the exchange
+ *       target is host memory.  This is what `GenerateSDF --gpus N` calls.
+ *   dg_sample_sdf_multi_device: the coefficient array device-resident on EVERY GPU of the group (d_out[i] = n_nodes doubles in
+ *       device i's memory): one launch per GPU into its slot of an exchange buffer, ONE in-place ncclAllGather per device
+ *       (ncclCommInitAll, grouped calls; libnccl.so.2 is loaded at first use), one unpack kernel into the reference's node order. */
+typedef struct dg_mesh_group dg_mesh_group;
+DG_API int dg_mesh_group_create(const dg_mesh* mesh, int n_gpus, const int* devices, dg_mesh_group** out);
+DG_API int dg_mesh_group_destroy(dg_mesh_group* group);
+DG_API int dg_mesh_group_size(const dg_mesh_group* group);
+DG_API int dg_add_function_sdf_multi(dg_mesh_group* group, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host,
+                              uint32_t* cell_map_host, double* timings_ms);
+DG_API int dg_sample_sdf_multi_device(dg_mesh_group* group, const dg_grid_desc* grid, double sign, double* const* d_out);
 /* Slab sharding of the same loop for one-process-per-GPU jobs ("P1"): part `part` of `n_parts` samples, in ONE launch,
  * whole slow-plane PAIRS of each of the four row-major node arrays (vertex / x-edge nodes: z-slabs; y-edge nodes: x-slabs; z-edge
  * nodes: y-slabs), i.e. no partially filled bricks and a single launch tail per rank.  Results are written at their final positions

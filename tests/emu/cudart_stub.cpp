@@ -38,6 +38,9 @@ cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { std::memset(a, 0, sizeof *a); a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
+cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 0; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+cudaError_t cudaMemcpyPeer(void* dst, int, const void* src, int, size_t n) { if (n) std::memcpy(dst, src, n); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return cudaSuccess; }
 

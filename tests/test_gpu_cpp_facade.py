@@ -28,6 +28,19 @@ def test_generate_sdf_tool_reproduces_box_cdf(tmp_path):
     assert out.read_bytes() == open(os.path.join(GOLDEN, "box.cdf"), "rb").read()      # byte-identical to the reference's output
 
 
+@pytest.mark.parametrize("n_gpus", [2, 8])
+def test_generate_sdf_tool_multi_gpu_same_file(dg, tmp_path, n_gpus):
+    """GenerateSDF --gpus N (dg_add_function_sdf_multi through the facade) writes the same bytes as the single-GPU run"""
+    exe = _need("GenerateSDF")
+    if dg.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    a, b = tmp_path / "one.cdf", tmp_path / "many.cdf"
+    for out, extra in ((a, []), (b, ["--gpus", str(n_gpus)])):
+        r = subprocess.run([exe, "-r", "21 17 12", "-i", "-o", str(out)] + extra + [os.path.join(GOLDEN, "sphere.obj")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    assert a.read_bytes() == b.read_bytes()
+
+
 def test_facade_api_vs_oracle(dg, orc, tmp_path):
     exe = _need("facade_check")
     g = dg.CubicLagrangeDiscreteGrid(os.path.join(GOLDEN, "box.cdf"))
