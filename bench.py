@@ -4,16 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Metric (BASELINE.json): SDF grid nodes/s of CubicLagrangeDiscreteGrid::addFunction with the GenerateSDF functor,
-on configs[1] "Stanford-bunny-class mesh (~70k triangles), 128^3 grid, fp64" -- synthetic closed mesh of that size
-(BASELINE.json north_star: "synthetic meshes/grids of the named shape"; /root/reference does not exist on the GPU box).
-A "step" = one full pass of the node loop over the 14,926,977 nodes.  N > 1: the node range is dealt in chunks to the
-ranks (strong scaling), followed by the all-gather of the coefficient array (discregrid_b200/distributed.py).
-The JSON line also carries the second half of the metric, interpolate()+gradient Mqueries/s (config 4: 10 M uniform
-random queries on a 256^3 SDF), under "interpolate".
+Metric (BASELINE.json): "SDF grid nodes/sec (addFunction) + interpolate Mqueries/sec".
+Workload at N = 1: BASELINE.json configs[1], "Stanford bunny (~70k tris) 128^3 grid, 1xB200, fp64" -- the reference's own bunny.obj
+(69,630 triangles; staged as an INPUT file under oracle/_ref/resources by `make -C oracle ref`, it travels to the GPU box) on the
+GenerateSDF-padded domain; when the file is not staged, a synthetic closed mesh of the same size (69,564 triangles) and the line says so.
+A "step" = one full pass of the addFunction node loop over the 14,926,977 nodes.
 
---impl reference: the reference's own CPU path (oracle/_ref = its unmodified TriangleMeshDistance.h compiled here, else
-the oracle port) on the host cores, same workload, each step a bounded sample of the node loop.
+  value      nodes/s of the node loop, coefficients device-resident (CUDA events, max over ranks)
+  e2e        the same metric through the C-ABI call a caller makes, dg_add_function_sdf(mesh, grid, sign, nodes, cells, cell_map):
+             the WHOLE of CubicLagrangeDiscreteGrid::addFunction (cubic_lagrange_discrete_grid.cpp:780-899) -- node loop, D2H of the
+             coefficient array, 32-index connectivity table, cell map -- into freshly allocated host arrays, wall-clock
+  roofline   K1 against the measured fp64 issue rate (dg_fp64_rate_probe: DMUL+DADD, no FMA -- the numerical contract), with the HBM
+             view and the interpolate kernel's HBM roofline nested
+  cpu_baseline / --impl reference
+             the reference's REAL addFunction (oracle/_ref/libdiscregrid_ref.so = its unmodified sources, oracle/ref_grid_wrapper.cpp:
+             refg_add_function_sdf) with the GenerateSDF functor on the host cores, whole grid, timed around the call exactly as e2e is.
+             Threads: physical cores in the affinity mask, capped by the cgroup CPU quota, OMP_PROC_BIND=spread OMP_PLACES=cores
+             (SURVEY 8d).  The CPU work always runs in a child process so that these settings are in place before libgomp starts.
+The second half of the metric, interpolate()+gradient Mqueries/s (config 4: 10 M uniform random queries on a 256^3 SDF), is carried
+under "interpolate" and nested in roofline / e2e / cpu_baseline (the driver keeps those objects whole).
 """
 import argparse
 import ctypes as C
@@ -29,9 +38,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = {"mesh": "synthetic bumpy torus, 186x187 quads = 69,564 triangles / 34,782 vertices (bunny-class: bunny.obj has 69,630)",
-            "resolution": [128, 128, 128], "torus": (186, 187, 1.0, 0.4, 0.05, 7, 5)}
+WORKLOAD = {"source": "bunny", "resolution": [128, 128, 128], "torus": (186, 187, 1.0, 0.4, 0.05, 7, 5)}
 INTERP = {"resolution": [256, 256, 256], "queries": 10_000_000, "seed": 0x5EED}
+RES_DIR = os.path.join(ROOT, "oracle", "_ref", "resources")      # the reference's meshes (inputs), staged by `make -C oracle ref`
 
 
 def parse():
@@ -44,16 +53,18 @@ def parse():
     ap.add_argument("--interp-resolution", type=int, default=0, help="override the interpolate grid resolution (diagnostics)")
     ap.add_argument("--target-resolution", type=int, default=256, help="grid resolution of the target-config leg (diagnostics / rehearsal; the config is 256)")
     ap.add_argument("--real-resolution", type=int, default=0, help="override the grid resolution of the reference-mesh leg (diagnostics / rehearsal)")
+    ap.add_argument("--mesh", default="", choices=["", "bunny", "torus"], help="override the headline mesh (default: bunny.obj when staged, else the synthetic torus)")
     ap.add_argument("--no-interp", action="store_true", help="skip the interpolate half (diagnostics / profiling)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (diagnostics / profiling)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip every CPU leg (diagnostics / profiling)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (diagnostics / profiling)")
     ap.add_argument("--no-target", action="store_true", help="skip the 256^3 / 100k-triangle target-config leg")
     ap.add_argument("--sharding", default="auto", choices=["auto", "slab", "chunks", "interleaved"],
                     help="N>1: round-robin node-id chunks, whole-plane slabs, or plane pairs dealt round-robin (one launch + one all-gather + unpack); "
-                         "auto = interleaved from 4 ranks up (measured at N=8: equal at 128^3, 58.2 vs 64.2 ms at 256^3), chunks below")
-    ap.add_argument("--no-real", action="store_true", help="skip the leg on the reference meshes staged under oracle/_ref/resources")
-    ap.add_argument("--no-density", action="store_true", help="skip the density-map (K3) leg (diagnostics / profiling)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+                         "auto = interleaved from 4 ranks up, chunks below")
+    ap.add_argument("--no-real", action="store_true", help="skip the leg on the other reference meshes (dragon / happy_buddha)")
+    ap.add_argument("--no-density", action="store_true", help="skip the density-map (K3) legs (diagnostics / profiling)")
+    ap.add_argument("--cpu-seconds", type=float, default=40.0, help="a CPU leg whose full-size run is estimated to take longer than this falls back to a strided sample")
+    ap.add_argument("--cpu-child", default="", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.sharding == "auto":
         args.sharding = "interleaved" if int(os.environ.get("WORLD_SIZE", "1")) >= 4 else "chunks"
@@ -62,8 +73,7 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------ helpers
 def scratch_dir():
-    """for the few hundred MB the CPU legs exchange with the reference class through files: the repo's own volume (build/ is git-ignored);
-    /tmp can be a slow copy-on-write layer"""
+    """for the few hundred MB some legs exchange through files: the repo's own volume (build/ is git-ignored); /tmp can be a slow copy-on-write layer"""
     d = os.path.join(ROOT, "build")
     try:
         os.makedirs(d, exist_ok=True)
@@ -72,55 +82,19 @@ def scratch_dir():
         return "/tmp"
 
 
-def reduce_field_leg(capi, desc, values, cells, lo, hi, with_reference, tmp_dir=None):
-    """reduceField(field, lo <= v <= hi) (cmd/generate_density_map/main.cpp:141-144) on a sampled field -- host code on
-    both sides: dg_reduce_field (index passes, multithreaded) vs the reference class's own reduceField (oracle/_ref, when built)."""
-    if tmp_dir is None:
-        tmp_dir = scratch_dir()
-    keep = np.ascontiguousarray((lo <= values) & (values <= hi) & (values != np.finfo(np.float64).max), np.uint8)
-    n_grid_cells = int(desc.resolution[0]) * int(desc.resolution[1]) * int(desc.resolution[2])
-    best, out = None, None
-    for _ in range(3):
-        nodes, cc = values.copy(), cells.copy()
-        cmap = np.empty(n_grid_cells, np.uint32); n1, n2 = C.c_uint64(), C.c_uint64(); tm = np.zeros(5)
-        t0 = time.perf_counter()
-        capi.check(capi.lib.dg_reduce_field(C.byref(desc), capi.ptr(nodes, capi.F64P), len(nodes), keep.ctypes.data_as(C.POINTER(C.c_uint8)),
-                                            capi.ptr(cc, capi.U32P), len(cc), capi.ptr(cmap, capi.U32P), 0, C.byref(n1), C.byref(n2), capi.ptr(tm, capi.F64P)))
-        dt = time.perf_counter() - t0
-        if best is None or dt < best:
-            best, out = dt, (nodes[:n1.value], cc[:n2.value], cmap, tm.copy())
-    leg = {"what": "reduceField of the density field with the tool's predicate 0 <= v <= 3 rho0: host index passes of dg_reduce_field",
-           "nodes_in": int(len(values)), "nodes_out": int(len(out[0])), "cells_in": int(len(cells)), "cells_out": int(len(out[1])),
-           "ms": best * 1e3, "ms_cells_nodes_sort_write": [float(t) for t in out[3][:4]], "morton_keys_tied": bool(out[3][4])}
-    if with_reference:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from oracle_api import REF_GRID_SO, RefGrid
-        if os.path.exists(REF_GRID_SO):
-            import struct
-            src, dst = os.path.join(tmp_dir, f"dg_reduce_in_{os.getpid()}.cdf"), os.path.join(tmp_dir, f"dg_reduce_out_{os.getpid()}.cdf")
-            try:
-                with open(src, "wb") as f:                              # the reference's one-field file layout (:678-719)
-                    f.write(struct.pack("<3d", *desc.domain_min)); f.write(struct.pack("<3d", *desc.domain_max)); f.write(struct.pack("<3I", *desc.resolution))
-                    f.write(struct.pack("<3d", *desc.cell_size)); f.write(struct.pack("<3d", *desc.inv_cell_size)); f.write(struct.pack("<QQ", n_grid_cells, 1))
-                    for arr in (values, cells, np.arange(len(cells), dtype=np.uint32)):
-                        f.write(struct.pack("<QQ", 1, len(arr))); f.write(np.ascontiguousarray(arr).tobytes())
-                ref = RefGrid(src); t_ref = ref.reduce_window(0, lo, hi); ref.save(dst); ref.close()
-                raw = np.fromfile(dst, np.uint8)
-                off = 24 * 4 + 12 + 16                                   # header: 4 x 3 doubles, 3 uint32, n_cells, n_fields
-                def nested(dtype, width):
-                    nonlocal off
-                    n = int(raw[off + 8:off + 16].view(np.uint64)[0]); off += 16
-                    a = raw[off:off + n * width * np.dtype(dtype).itemsize].view(dtype); off += a.nbytes
-                    return a.reshape(n, width) if width > 1 else a
-                rn, rc, rm = nested(np.float64, 1), nested(np.uint32, 32), nested(np.uint32, 1)
-                same = bool(np.array_equal(rn.view(np.uint64), out[0].view(np.uint64)) and np.array_equal(rc, out[1]) and np.array_equal(rm, out[2]))
-                leg["reference"] = {"ms": t_ref * 1e3, "kind": "reference", "impl": "CubicLagrangeDiscreteGrid::reduceField of oracle/_ref (serial, one std::set per node)",
-                                    "identical_nodes_cells_cell_map": same, "speedup": t_ref / best}
-            finally:
-                for p_ in (src, dst):
-                    if os.path.exists(p_):
-                        os.remove(p_)
-    return leg
+def workload_mesh(dg, source, torus=None):
+    """-> (mesh, description, data tag).  'bunny' = the reference's bunny.obj when staged."""
+    if source in ("bunny", "dragon", "happy_buddha"):
+        p = os.path.join(RES_DIR, source + ".obj")
+        if os.path.exists(p):
+            m = dg.TriangleMesh(p)
+            return m, f"{source}.obj of the reference ({m.nFaces()} triangles / {len(m.vertices)} vertices)", "reference mesh file"
+        source = "torus"
+    if source == "target":
+        m = dg.bumpy_torus()
+        return m, "synthetic bumpy torus, 250x200 quads = exactly 100,000 triangles / 50,000 vertices (BASELINE.md target config)", "synthetic"
+    m = dg.bumpy_torus(*(torus or WORKLOAD["torus"]))
+    return m, f"synthetic bumpy torus, {m.nFaces()} triangles / {len(m.vertices)} vertices (bunny-class: bunny.obj has 69,630; the file is not staged here)", "synthetic"
 
 
 class ClockSampler:
@@ -186,7 +160,31 @@ def splitmix_points(n, seed, lo, hi):
     return lo + u.reshape(n, 3) * (hi - lo)
 
 
-def host_cpu_info():
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_policy():
+    """Host threads for the reference's OpenMP loops: one per PHYSICAL core of the affinity mask, never more than the cgroup
+    CPU quota allows (a 1-GPU lease that sees 128 logical CPUs under a smaller quota runs 128 spinning threads several times slower),
+    spread over the sockets, pinned to cores.  DG_CPU_THREADS overrides the count."""
+    allowed = sorted(os.sched_getaffinity(0))
+    cores = {}
+    for c in allowed:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        cores.setdefault(sib, c)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and per > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
     model = "unknown"
     try:
         for line in open("/proc/cpuinfo"):
@@ -195,97 +193,227 @@ def host_cpu_info():
                 break
     except OSError:
         pass
-    return model, os.cpu_count()
+    threads = len(cores) or len(allowed) or 1
+    if quota is not None and quota >= 1:
+        threads = max(1, min(threads, int(quota)))
+    if os.environ.get("DG_CPU_THREADS"):
+        threads = int(os.environ["DG_CPU_THREADS"])
+    env = {"OMP_NUM_THREADS": str(threads), "OMP_PROC_BIND": os.environ.get("DG_OMP_PROC_BIND", "spread"),
+           "OMP_PLACES": os.environ.get("DG_OMP_PLACES", "cores"), "OMP_DYNAMIC": "false"}
+    return {"threads": threads, "logical_cpus": len(allowed), "physical_cores": len(cores), "cgroup_cpu_quota": quota, "cpu_model": model, "omp_env": env}
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample_rate(mesh, mn, mx, res, seconds, steps=1, warmup=0):
-    """Times the reference's CPU path on a strided sample of the node loop.  Returns (nodes/s list per step, info)."""
-    # all host threads this process may use -- set before the OpenMP runtime starts, because torchrun exports OMP_NUM_THREADS=1
-    os.environ["OMP_NUM_THREADS"] = os.environ.get("DG_CPU_THREADS") or str(len(os.sched_getaffinity(0)))
+def run_cpu_child(spec, timeout=1800):
+    """Runs one CPU leg in a child process whose OpenMP environment is set before libgomp starts.  -> result dict (or {"error": ...})"""
+    pol = cpu_policy()
+    env = dict(os.environ, **pol["omp_env"])
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-child", json.dumps(spec)], capture_output=True, text=True, env=env, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {"error": f"cpu child timed out after {timeout} s"}
+    for line in reversed(r.stdout.splitlines()):
+        if line.startswith('{"cpu_child"'):
+            d = json.loads(line)
+            d.pop("cpu_child")
+            d.update({k: pol[k] for k in ("logical_cpus", "physical_cores", "cgroup_cpu_quota", "cpu_model")})
+            d["omp"] = {k: v for k, v in pol["omp_env"].items() if k != "OMP_DYNAMIC"}
+            return d
+    return {"error": f"cpu child rc={r.returncode}: {(r.stdout + r.stderr)[-600:]}"}
+
+
+def _child_mesh(spec):
+    import discregrid_b200 as dg
+    return workload_mesh(dg, spec["mesh"], spec.get("torus"))[0]
+
+
+def cpu_child_addfunction(spec):
+    """The reference's real addFunction on the whole grid, `runs` times (+ `warm` untimed), optionally checked against the GPU result."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_api import Oracle, RefMesh, have_ref
+    import discregrid_b200 as dg
+    from oracle_api import Oracle, RefAddFunction, RefMesh, have_ref, have_ref_grid
+    mesh = _child_mesh(spec)
+    mn, mx = dg.generate_sdf_domain(mesh.vertices)
+    res = spec["res"]
     orc = Oracle()
     gd, r = orc.grid_desc(mn, mx, res)
     n_nodes = orc.num_nodes(r)
-    threads = orc.max_threads()
-    kind = "reference" if have_ref() else "port"
-    m = RefMesh(mesh.vertices, mesh.faces) if kind == "reference" else orc.mesh(mesh.vertices, mesh.faces)
+    threads = int(os.environ.get("OMP_NUM_THREADS", "0")) or orc.max_threads()
+    out = {"n_nodes": n_nodes, "cores": threads}
+    # traversal statistics of the reference algorithm on a strided node sample (single-threaded counters of the oracle port): the
+    # algorithmic flop count of K1's roofline, SURVEY 8(d): visits * 24 + leaf tests * 65
+    if spec.get("stats_nodes"):
+        ids = np.linspace(0, n_nodes - 1, int(spec["stats_nodes"])).astype(np.int64)
+        v, l = orc.mesh(mesh.vertices, mesh.faces).stats(orc.node_positions_at(gd, r, ids))
+        out.update(visits_per_node=v, leaf_tests_per_node=l, flops_per_node=24.0 * v + 65.0 * l)
+    # calibration on 20k strided nodes with the reference's signed_distance: is the full-size call affordable?
+    est = None
+    if have_ref():
+        rm = RefMesh(mesh.vertices, mesh.faces)
+        ids = np.linspace(0, n_nodes - 1, 20_000).astype(np.int64)
+        x = orc.node_positions_at(gd, r, ids)
+        rm.sample_points(x[:2000], nthreads=threads)
+        t0 = time.perf_counter(); rm.sample_points(x, nthreads=threads); dt = time.perf_counter() - t0
+        est = dt / len(ids) * n_nodes
+        out["calibration_nodes_per_s"] = len(ids) / dt
+    runs, warm = int(spec.get("runs", 1)), int(spec.get("warm", 0))
+    full = have_ref_grid() and (est is None or est * (runs + warm) <= float(spec.get("max_seconds", 60.0)))
+    if full:
+        ref = RefAddFunction(mesh.vertices, mesh.faces)
+        times, nodes, cells = [], None, None
+        want = bool(spec.get("check_gpu"))
+        for it in range(warm + runs):
+            last = it == warm + runs - 1
+            dt, nn, cc = ref.add_function(mn, mx, res, nthreads=threads, want_nodes=want and last, want_cells=want and last and n_nodes < 40_000_000)
+            if it >= warm:
+                times.append(dt)
+            if last:
+                nodes, cells = nn, cc
+        out.update(kind="reference", mode="full_addfunction", times_s=times,
+                   sample=f"the reference's real CubicLagrangeDiscreteGrid::addFunction(GenerateSDF functor, verbose=false) over all {n_nodes} nodes "
+                          f"({runs} timed call(s) after {warm} warm-up), node loop + connectivity + cell map, steady_clock around the call")
+        if want:
+            # full-size parity, by-product of the baseline: every node (and every cell index) the reference produced vs the GPU path
+            md = dg.TriangleMeshDistance(mesh)
+            g = dg.CubicLagrangeDiscreteGrid(mn, mx, res)
+            g.addFunction(dg.MeshSignedDistance(md))
+            out["parity_nodes_bit_exact"] = bool(np.array_equal(g.m_nodes[0].view(np.uint64), nodes.view(np.uint64)))
+            out["parity_nodes_compared"] = int(n_nodes)
+            if cells is not None:
+                out["parity_cells_equal"] = bool(np.array_equal(g.m_cells[0], cells))
+    else:
+        # bounded sample: the node-loop body on evenly strided nodes (positions by the oracle's indexToNodePosition, untimed)
+        kind = "reference" if have_ref() else "port"
+        m = RefMesh(mesh.vertices, mesh.faces) if kind == "reference" else orc.mesh(mesh.vertices, mesh.faces)
+        budget = float(spec.get("max_seconds", 60.0)) / max(1, runs + warm)
+        n_sample = int(min(n_nodes, max(20_000, (budget / est * n_nodes) if est else 200_000)))
+        ids = np.linspace(0, n_nodes - 1, n_sample).astype(np.int64)
+        x = orc.node_positions_at(gd, r, ids)
+        times = []
+        for it in range(warm + runs):
+            t0 = time.perf_counter()
+            if kind == "reference":
+                m.sample_points(x, nthreads=threads)
+            else:
+                m.distance(x)
+            if it >= warm:
+                times.append((time.perf_counter() - t0) * n_nodes / n_sample)           # scaled to the full grid
+        out.update(kind=kind, mode="strided_sample", times_s=times,
+                   sample=f"{n_sample} of {n_nodes} nodes, evenly strided, OpenMP schedule(static), node-loop body only "
+                          f"({'reference TriangleMeshDistance.h' if kind == 'reference' else 'oracle port'}); times scaled to the full grid "
+                          f"(the full call was estimated at {est:.1f} s per run)" if est else "strided sample")
+    return out
 
-    def run(ids):
-        # node positions by the oracle's indexToNodePosition (untimed), then the node-loop body on all host threads
-        x = _positions(orc, gd, r, ids)
-        t0 = time.perf_counter()
-        if kind == "reference":
-            m.sample_points(x, nthreads=threads)
-        else:
-            m.distance(x)
-        return time.perf_counter() - t0
 
-    # calibrate on 20k strided nodes, then size the sample for ~`seconds`
-    probe = np.linspace(0, n_nodes - 1, 20_000).astype(np.int64)
-    dt = run(probe)
-    n_sample = int(min(n_nodes, max(20_000, seconds / max(dt, 1e-6) * len(probe))))
-    ids = np.linspace(0, n_nodes - 1, n_sample).astype(np.int64)
-    rates = []
-    for it in range(warmup + steps):
-        dt = run(ids)
-        if it >= warmup:
-            rates.append(n_sample / dt)
-    model, ncpu = host_cpu_info()
-    info = {"kind": kind, "cores": threads, "cpu_model": model, "logical_cpus": ncpu,
-            "sample": f"{n_sample} of {n_nodes} nodes, evenly strided over the node index space, OpenMP schedule(static), "
-                      f"{'reference TriangleMeshDistance.h (oracle/_ref)' if kind == 'reference' else 'oracle port'}"}
-    return rates, info
+def cpu_child_interp(spec):
+    """The reference's own CubicLagrangeDiscreteGrid::interpolate(field, x, &grad) in the OpenMP loop of cmd/discrete_field_to_bitmap/main.cpp:118-135
+    over the SAME queries on the SAME field as the GPU leg; the field is built on the GPU (input preparation), the grid object by the reference's
+    own addFunction, and every query's value + gradient is compared with the GPU's."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import discregrid_b200 as dg
+    from oracle_api import Oracle, RefGridInMemory, have_ref_grid
+    mesh = _child_mesh(spec)
+    mn, mx = dg.generate_sdf_domain(mesh.vertices)
+    res, nq = spec["res"], int(spec["queries"])
+    md = dg.TriangleMeshDistance(mesh)
+    g = dg.CubicLagrangeDiscreteGrid(mn, mx, res)
+    g.addFunction(dg.MeshSignedDistance(md))
+    x = np.ascontiguousarray(splitmix_points(nq, spec["seed"], mn, mx))
+    pg, gg = g.interpolate(0, x, gradient=True)
+    threads = int(os.environ.get("OMP_NUM_THREADS", "0"))
+    out = {"queries": nq, "cores": threads}
+    if have_ref_grid():
+        rg = RefGridInMemory(mn, mx, res, g.m_nodes[0], nthreads=threads)
+        rg.interpolate(0, x[:200_000], grad=True, nthreads=threads)
+        best = None
+        for _ in range(int(spec.get("runs", 2))):
+            t0 = time.perf_counter(); pr, gr = rg.interpolate(0, x, grad=True, nthreads=threads); dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out.update(kind="reference", seconds=best,
+                   sample=f"all {nq} queries on the {res[0]}^3 field ({len(g.m_nodes[0])} nodes): the reference class's interpolate(0, x, &grad) in an OpenMP parallel for, best of {spec.get('runs', 2)}")
+    else:
+        orc = Oracle(); gd, r = orc.grid_desc(mn, mx, res)
+        t0 = time.perf_counter(); pr, gr = orc.interpolate(gd, r, g.m_nodes[0], x, grad=True); best = time.perf_counter() - t0
+        out.update(kind="port", seconds=best, sample=f"all {nq} queries on the {res[0]}^3 field, oracle port")
+    out["bit_exact_vs_gpu"] = bool(np.array_equal(pr.view(np.uint64), pg.view(np.uint64)) and np.array_equal(gr.view(np.uint64), gg.view(np.uint64)))
+    out["queries_compared"] = nq
+    return out
 
 
-def _positions(orc, gd, r, ids):
-    """positions of arbitrary node ids via the oracle's indexToNodePosition"""
-    return orc.node_positions_at(gd, r, ids)
+def cpu_child_main(spec):
+    fn = {"addfunction": cpu_child_addfunction, "interp": cpu_child_interp}[spec["what"]]
+    out = fn(spec)
+    out["cpu_child"] = 1
+    # key order: the parent looks for a line starting with {"cpu_child"
+    print(json.dumps({"cpu_child": 1, **{k: v for k, v in out.items() if k != "cpu_child"}}))
+
+
+def addfunction_baseline(source, torus, res, runs, warm, max_seconds, check_gpu, stats_nodes=4000):
+    d = run_cpu_child({"what": "addfunction", "mesh": source, "torus": torus, "res": list(res), "runs": runs, "warm": warm,
+                       "max_seconds": max_seconds, "check_gpu": check_gpu, "stats_nodes": stats_nodes})
+    if "error" in d:
+        return d
+    t = d["times_s"]
+    d["value"] = d["n_nodes"] / float(np.mean(t)); d["unit"] = "nodes/s"; d["best_value"] = d["n_nodes"] / min(t)
+    return d
 
 
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse()
+    if args.cpu_child:
+        cpu_child_main(json.loads(args.cpu_child))
+        return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     res = [args.resolution] * 3 if args.resolution else WORKLOAD["resolution"]
+    source = args.mesh or WORKLOAD["source"]
 
     import discregrid_b200 as dg           # fails loudly if the CUDA library is not built
     from discregrid_b200 import _capi as capi
-    from discregrid_b200.distributed import make_sharding, allgather_rows, ShardedSdfSampler, SlabSdfSampler, InterleavedSdfSampler
 
-    mesh = dg.bumpy_torus(*WORKLOAD["torus"])
+    mesh, mesh_text, data_tag = workload_mesh(dg, source)
+    if data_tag == "synthetic":
+        source = "torus"
     mn, mx = dg.generate_sdf_domain(mesh.vertices)
     desc = dg.grid_desc(mn, mx, res)
     n_nodes = C.c_uint64()
     capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(n_nodes)))
     n_nodes = n_nodes.value
-    config = {"workload": f"GenerateSDF addFunction: {WORKLOAD['mesh']}; {res[0]}x{res[1]}x{res[2]} grid = {n_nodes} nodes; "
+    n_cells = int(res[0]) * int(res[1]) * int(res[2])
+    par = f"x{world}" + ("" if world == 1 else (", slabs of whole plane pairs of the four node arrays: one launch per rank + one NCCL all-gather per node array" if args.sharding == "slab" else ", plane pairs dealt round-robin: one launch per rank + ONE NCCL all-gather + unpack kernel" if args.sharding == "interleaved" else ", 2 round-robin node-id chunks per rank on 2 streams + one in-place NCCL all-gather per row"))
+    config = {"workload": f"GenerateSDF addFunction (BASELINE.json configs[1]): {mesh_text}; {res[0]}x{res[1]}x{res[2]} grid = {n_nodes} nodes; "
                           "GenerateSDF-padded domain; fp64 bit-exact with the reference",
               "mesh_triangles": int(mesh.nFaces()), "grid": res, "nodes": n_nodes,
-              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"x{world}" + ("" if world == 1 else (", slabs of whole plane pairs of the four node arrays: one launch per rank + one NCCL all-gather per node array" if args.sharding == "slab" else ", plane pairs dealt round-robin: one launch per rank + ONE NCCL all-gather + unpack kernel" if args.sharding == "interleaved" else ", 2 round-robin node-id chunks per rank on 2 streams + one in-place NCCL all-gather per row"))}
+              "l2": "flushed between timed iterations (256 MiB write)", "parallelism": par}
+    data = f"{data_tag} + regular grid" if data_tag != "synthetic" else "synthetic"
 
-    # ---------------------------------------------------------------- reference arm (CPU)
+    # ---------------------------------------------------------------- reference arm (CPU): the reference's real addFunction per step
     if args.impl == "reference":
         if rank != 0:
             return
-        rates, info = cpu_sample_rate(mesh, mn, mx, res, args.cpu_seconds / 2, steps=args.steps, warmup=min(args.warmup, 1))
-        v = float(np.mean(rates))
-        n_sample = int(info["sample"].split()[0])
+        d = addfunction_baseline(source, WORKLOAD["torus"], res, runs=args.steps, warm=min(args.warmup, 1), max_seconds=args.cpu_seconds * 6, check_gpu=False, stats_nodes=0)
+        if "error" in d:
+            print(json.dumps({"impl": "reference", "unavailable": d["error"][:300]}))
+            return
+        v = d["value"]
         line = {"impl": "reference", "metric": "SDF grid nodes/sec (addFunction)", "value": v, "unit": "nodes/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_sample / v, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": dict(info, value=v, unit="nodes/s"),
-                "e2e": {"value": v, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_nodes / v, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": data, "config": config,
+                "cpu_baseline": {k: d[k] for k in d if k not in ("times_s",)},
+                "e2e": {"value": v, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+                "timing": {"per_step_s": d["times_s"], "best_value": d["best_value"]}}
         print(json.dumps(line))
         return
 
     # ---------------------------------------------------------------- our arm (GPU)
     import torch
     import torch.distributed as dist
+    from discregrid_b200.distributed import make_sharding, ShardedSdfSampler, SlabSdfSampler, InterleavedSdfSampler
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    assert not hasattr(capi.lib, "emu_mesh_create") or os.environ.get("DG_ALLOW_EMULATED_LIBRARY") == "1", "bench.py must run on the CUDA build of the library"
     torch.cuda.set_device(local_rank)
     capi.check(capi.lib.dg_set_device(local_rank))
     if world > 1:
@@ -307,7 +435,6 @@ def main():
     md = dg.TriangleMeshDistance(mesh)
     mesh_info = md.info()
     sh = make_sharding(n_nodes, world)
-    full = torch.empty(sh.padded, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     my_chunks = [(j, b, e) for (j, b, e) in sh.chunks_of(rank)]
     stream = torch.cuda.current_stream()
@@ -319,14 +446,8 @@ def main():
             return InterleavedSdfSampler(md_, desc_, rank, world)
         return ShardedSdfSampler(md_, desc_, make_sharding(n_, world), rank)
 
-    if args.sharding != "chunks":
-        sdf_sampler = make_sampler(md, desc, n_nodes)
-        full = torch.empty(sdf_sampler.sh.padded, dtype=torch.float64, device=dev)
-    else:
-        sdf_sampler = ShardedSdfSampler(md, desc, sh, rank)
-
-    def sdf_step():
-        sdf_sampler.step(full)
+    sdf_sampler = make_sampler(md, desc, n_nodes)
+    full = torch.empty(sdf_sampler.sh.padded, dtype=torch.float64, device=dev)
 
     def same_as_single_launch(md_, desc_, n_, sharded):
         """every rank: the assembled array of the sharded step vs ONE dg_sample_sdf_device launch over all nodes on this GPU (bit-for-bit)"""
@@ -358,7 +479,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = dg.kernel_launch_count()
-    sdf_ms, sdf_wall = timed(sdf_step, args.steps, args.warmup)
+    sdf_ms, sdf_wall = timed(lambda: sdf_sampler.step(full), args.steps, args.warmup)
     launches = (dg.kernel_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
     sharded_ok = same_as_single_launch(md, desc, n_nodes, full)
     clocks = sampler.stop() if rank == 0 else None
@@ -366,58 +487,91 @@ def main():
     value = n_nodes / (ms_step * 1e-3)
 
     # kernel-only time of K1 on this rank (no collective): what the roofline object refers to
-    def k1_only():
-        sdf_sampler.launch(full)
-    k1_ms, _ = timed(k1_only, max(3, args.steps // 2), 1)
+    k1_ms, _ = timed(lambda: sdf_sampler.launch(full), max(3, args.steps // 2), 1)
     k1_ms = float(np.mean(k1_ms))
-    if args.sharding == "slab":
+    if args.sharding == "slab" and world > 1:
         my_nodes = sum(e - b for (b, e) in sdf_sampler.sh.ranges[rank]); n_launch = 1
-    elif args.sharding == "interleaved":
+    elif args.sharding == "interleaved" and world > 1:
         my_nodes = n_nodes // world; n_launch = 1
     else:
         my_nodes = sum(e - b for (_j, b, e) in my_chunks); n_launch = sum(1 for (_j, b, e) in my_chunks if e > b)
     peaks, peak_src = measured_peaks()
-    k1_alg_bytes = 8.0 * my_nodes + mesh_info["device_bytes"]          # 8 B/node written + mesh records read once
-    k1_gbs = k1_alg_bytes / (k1_ms * 1e-3) / 1e9
-    roofline = {"kernel": "sdf_sample_nodes_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": k1_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                "traffic_ncu_other_config": {"bytes_per_launch": 27.4e6, "capture": "profiles/r1d_ncu_summary.csv: ncu --set full at 64^3 (the bench runs 128^3): dram read "
-                                                                                    "27.0 MB = the mesh records once, 0.4 MB written back inside the launch"},
-                "algorithmic_bytes_per_launch": k1_alg_bytes / max(1, n_launch), "launches_per_step": n_launch,
-                "avg_launch_ms": k1_ms / max(1, n_launch),
-                "note": "K1 is NOT HBM-bound: BVH + triangle records are L2-resident and compulsory HBM traffic is 8 B/node "
-                        "(SURVEY 8d); it is bound by divergent fp64 ALU work and L1/L2 latency -- grade it on nodes/s"}
+    fp64_peak = C.c_double()
+    capi.check(capi.lib.dg_fp64_rate_probe(C.byref(fp64_peak)))
+    fp64_peak = fp64_peak.value
 
-    # ---------------------------------------------------------------- e2e: C-ABI with HOST buffers
+    # ---------------------------------------------------------------- e2e: the whole addFunction through the C-ABI, HOST arrays
     e2e = None
     if not args.no_e2e:
+        def add_function_e2e(md_, desc_, n_, nc_):
+            """fresh arrays every call (as the reference's addFunction allocates its three vectors inside the timed call)"""
+            nodes = np.empty(n_); cells = np.empty((nc_, 32), np.uint32); cmap = np.empty(nc_, np.uint32); tm = np.zeros(6)
+            capi.check(capi.lib.dg_add_function_sdf(md_.handle, C.byref(desc_), 1.0, capi.ptr(nodes, capi.F64P), capi.ptr(cells, capi.U32P), capi.ptr(cmap, capi.U32P), capi.ptr(tm, capi.F64P)))
+            return nodes, cells, cmap, tm
         if world == 1:
-            my_ranges = [(0, n_nodes)]
-        elif args.sharding == "slab":
-            my_ranges = [(b, e) for (b, e) in sdf_sampler.sh.ranges[rank] if e > b]
-        else:                                                  # the host API takes node-id ranges: chunks (also in interleaved mode)
-            my_ranges = [(b, e) for (_j, b, e) in my_chunks if e > b]
-        outs = [np.empty(e - b) for (b, e) in my_ranges]
+            for _ in range(2):
+                add_function_e2e(md, desc, n_nodes, n_cells)
+            n_e2e = max(3, args.steps // 2)
+            ts, tms = [], []
+            for _ in range(n_e2e):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                out = add_function_e2e(md, desc, n_nodes, n_cells)
+                ts.append(time.perf_counter() - t0); tms.append(out[3])
+                del out
+            dt = float(np.mean(ts))
+            tm = np.mean(np.array(tms), axis=0)
+            e2e = {"value": n_nodes / dt, "unit": "nodes/s", "h2d_bytes_per_step": C.sizeof(capi.GridDesc),
+                   "d2h_bytes_per_step": 8 * n_nodes, "ms_per_step": dt * 1e3, "best_ms": min(ts) * 1e3,
+                   "host_bytes_written_per_step": 8 * n_nodes + 132 * n_cells,
+                   "breakdown_ms": {"total_inside_call": float(tm[0]), "node_pipeline_done": float(tm[1]), "coefficient_array_prefaulted": float(tm[3]),
+                                    "host_worker_threads": int(tm[4]), "allocation_and_return": dt * 1e3 - float(tm[0])},
+                   "api": "dg_add_function_sdf(mesh, grid, sign, nodes_host, cells_host, cell_map_host): the whole of addFunction (:780-899) into fresh "
+                          "pageable host arrays -- K1 chunks on two streams, D2H through a pooled pinned double buffer, connectivity table (:833-886) and "
+                          "cell map (:888-891) written by host threads while the GPU works; the mesh/BVH was uploaded once by dg_mesh_create (as "
+                          "TriangleMeshDistance is built once, outside addFunction's timer, in the reference)",
+                   "mesh_upload": {"host_build_ms": mesh_info["build_us"] / 1e3, "h2d_ms": mesh_info["upload_us"] / 1e3, "h2d_bytes": mesh_info["device_bytes"]}}
+        else:
+            # one process per GPU: every rank delivers its node-id chunks to its own host buffers (dg_sample_sdf) ...
+            my_ranges = [(b, e) for (_j, b, e) in my_chunks if e > b] if args.sharding != "slab" else [(b, e) for (b, e) in sdf_sampler.sh.ranges[rank] if e > b]
+            outs = [np.empty(e - b) for (b, e) in my_ranges]
 
-        def e2e_step():
-            for (b, e), o in zip(my_ranges, outs):
-                capi.check(capi.lib.dg_sample_sdf(md.handle, C.byref(desc), 1.0, b, e, capi.ptr(o, capi.F64P)))
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(3, args.steps // 2)
-        for _ in range(n_e2e):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = max_over_ranks((time.perf_counter() - t0) / n_e2e)
-        e2e = {"value": n_nodes / dt, "unit": "nodes/s", "h2d_bytes_per_step": C.sizeof(capi.GridDesc) * len(my_ranges),
-               "d2h_bytes_per_step": 8 * n_nodes, "ms_per_step": dt * 1e3,
-               "api": "dg_sample_sdf(mesh, grid, sign, l_begin, l_end, out_host): kernel + D2H of the coefficient array into a "
-                      "pageable host buffer; the mesh/BVH was uploaded once by dg_mesh_create (as TriangleMeshDistance is built "
-                      "once, outside addFunction's timer, in the reference)",
-               "mesh_upload": {"host_build_ms": mesh_info["build_us"] / 1e3, "h2d_ms": mesh_info["upload_us"] / 1e3,
-                               "h2d_bytes": mesh_info["device_bytes"]}}
+            def e2e_step():
+                for (b, e), o in zip(my_ranges, outs):
+                    capi.check(capi.lib.dg_sample_sdf(md.handle, C.byref(desc), 1.0, b, e, capi.ptr(o, capi.F64P)))
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e = max(3, args.steps // 2)
+            for _ in range(n_e2e):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = max_over_ranks((time.perf_counter() - t0) / n_e2e)
+            e2e = {"value": n_nodes / dt, "unit": "nodes/s", "h2d_bytes_per_step": C.sizeof(capi.GridDesc) * len(my_ranges),
+                   "d2h_bytes_per_step": 8 * n_nodes, "ms_per_step": dt * 1e3,
+                   "api": "one process per GPU: dg_sample_sdf(mesh, grid, sign, l_begin, l_end, out_host) per rank over its node-id chunks (kernel + D2H into pageable host buffers)"}
+            # ... and the single-process form a C++ caller uses: rank 0 drives ALL N GPUs through dg_add_function_sdf_multi while the other ranks idle
+            barrier()
+            if rank == 0:
+                try:
+                    grp = C.c_void_p()
+                    capi.check(capi.lib.dg_mesh_group_create(md.handle, world, None, C.byref(grp)))
+                    ts = []
+                    for it in range(2 + 3):
+                        nodes = np.empty(n_nodes); cells = np.empty((n_cells, 32), np.uint32); cmap = np.empty(n_cells, np.uint32); tm = np.zeros(6)
+                        t0 = time.perf_counter()
+                        capi.check(capi.lib.dg_add_function_sdf_multi(grp, C.byref(desc), 1.0, capi.ptr(nodes, capi.F64P), capi.ptr(cells, capi.U32P), capi.ptr(cmap, capi.U32P), capi.ptr(tm, capi.F64P)))
+                        if it >= 2:
+                            ts.append(time.perf_counter() - t0)
+                    same = bool(np.array_equal(nodes.view(np.uint64), full[:n_nodes].cpu().numpy().view(np.uint64)))
+                    e2e["single_process_c_abi"] = {"api": f"dg_add_function_sdf_multi(group of {world} GPUs, ...): whole addFunction from ONE process, host arrays out (what GenerateSDF --gpus N calls)",
+                                                   "ms_per_step": float(np.mean(ts)) * 1e3, "value": n_nodes / float(np.mean(ts)), "unit": "nodes/s",
+                                                   "node_pipeline_ms": float(tm[1]), "equals_sharded_result": same}
+                    capi.lib.dg_mesh_group_destroy(grp)
+                except Exception as ex:                          # an auxiliary leg must not take the bench line down
+                    e2e["single_process_c_abi"] = {"error": repr(ex)}
+            barrier()
 
     # ---------------------------------------------------------------- interpolate half of the metric (config 4)
     interp = None
@@ -458,63 +612,58 @@ def main():
         is_ms, _ = timed(lambda: interp_step(True), 20, 3)
         is_ms = float(np.mean(is_ms))
         xd = xd_keep
+        del xd_sorted
+        interp_step(True); torch.cuda.synchronize()          # phi / grad hold the unsorted queries' results again (compared with the host path below)
         alg = 312.0 * (q_hi - q_lo)
         gbs = alg / (ig_ms * 1e-3) / 1e9
-        # e2e through the host API
-        xq = np.ascontiguousarray(xh); ph = np.empty(len(xq)); gh = np.empty((len(xq), 3))
+        # e2e through the host API: page-locked host buffers (the contract's pinned inputs), H2D + kernel + D2H inside the timed region
+        ph_t = torch.empty(q_hi - q_lo, dtype=torch.float64).pin_memory(); gh_t = torch.empty((q_hi - q_lo, 3), dtype=torch.float64).pin_memory()
+        xq, ph, gh = xh_t.numpy(), ph_t.numpy(), gh_t.numpy()
+
+        def host_call(x_, p_, g_):
+            capi.check(capi.lib.dg_interpolate_batch(fh, capi.ptr(x_, capi.F64P), len(x_), capi.ptr(p_, capi.F64P), capi.ptr(g_, capi.F64P)))
         for _ in range(2):
-            capi.check(capi.lib.dg_interpolate_batch(fh, capi.ptr(xq, capi.F64P), len(xq), capi.ptr(ph, capi.F64P), capi.ptr(gh, capi.F64P)))
+            host_call(xq, ph, gh)
         barrier(); t0 = time.perf_counter()
         for _ in range(5):
-            capi.check(capi.lib.dg_interpolate_batch(fh, capi.ptr(xq, capi.F64P), len(xq), capi.ptr(ph, capi.F64P), capi.ptr(gh, capi.F64P)))
+            host_call(xq, ph, gh)
         dt = max_over_ranks((time.perf_counter() - t0) / 5)
+        pinned_equal = bool(np.array_equal(ph.view(np.uint64), phi.cpu().numpy().view(np.uint64)))
+        # the same with ordinary (pageable) numpy arrays: staged through the library's pinned pool
+        xp, pp, gp = np.array(xq), np.empty(len(xq)), np.empty((len(xq), 3))
+        host_call(xp, pp, gp)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(3):
+            host_call(xp, pp, gp)
+        dt_pageable = max_over_ranks((time.perf_counter() - t0) / 3)
+        del xp, pp, gp
         interp = {"metric": "interpolate()+gradient Mqueries/s", "value": nq / (ig_ms * 1e-3) / 1e6, "unit": "Mqueries/s",
                   "value_only_mqps": nq / (iv_ms * 1e-3) / 1e6, "cell_sorted_mqps": nq / (is_ms * 1e-3) / 1e6, "ms_per_launch": ig_ms, "queries": nq,
-                  "config": {"workload": f"10M splitmix64 uniform queries (seed 0x5EED) on the {ires[0]}^3 SDF of the same mesh "
+                  "config": {"workload": f"10M splitmix64 uniform queries (seed 0x5EED) on the {ires[0]}^3 SDF of the headline mesh "
                                          f"({nn} nodes; packed cell blocks {16 * ires[0] * ires[1] * ires[2] * 16 / 1e9:.2f} GB >> L2)",
                              "field_build_s": build_s},
                   "roofline": {"kernel": "interpolate_kernel<true> (K2)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
-                               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                               "algorithmic_bytes_per_query": 312,
-                               "traffic_ncu_other_config": {"bytes_per_launch": 2.78e9, "algorithmic_bytes_per_launch": 3.12e9,
-                                                            "capture": "profiles/r1e_k2k3_ncu_summary.csv: ncu --set full on the 128^3 field (the bench runs 256^3), "
-                                                                       "dram read 2.46 GB + write 0.314 GB"}},
-                  "e2e": {"value": nq / dt / 1e6, "unit": "Mqueries/s", "h2d_bytes_per_step": 24 * nq, "d2h_bytes_per_step": 32 * nq,
-                          "api": "dg_interpolate_batch(field, x_host, n, phi_host, grad_host)"}}
+                               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": NCU["k2_dram_bytes_per_launch"], "traffic_source": NCU["k2_source"],
+                               "peak_source": peak_src, "algorithmic_bytes_per_query": 312, "algorithmic_bytes_per_launch": alg},
+                  "e2e": {"value": nq / dt / 1e6, "unit": "Mqueries/s", "h2d_bytes_per_step": 24 * nq, "d2h_bytes_per_step": 32 * nq, "ms_per_step": dt * 1e3,
+                          "pcie_gbs": 56.0 * (q_hi - q_lo) / dt / 1e9, "equals_device_result": pinned_equal,
+                          "pageable_buffers": {"value": nq / dt_pageable / 1e6, "unit": "Mqueries/s", "ms_per_step": dt_pageable * 1e3},
+                          "api": "dg_interpolate_batch(field, x_host, n, phi_host, grad_host): 3-slot pipeline of 512k-query chunks (H2D, kernel, D2H overlapped); "
+                                 "page-locked caller buffers are DMA'd directly, pageable ones are staged through pooled pinned buffers"}}
+        del ph_t, gh_t
         capi.lib.dg_field_destroy(fh)
-        # CPU baseline of interpolate: the reference's own CubicLagrangeDiscreteGrid::interpolate (oracle/_ref/libdiscregrid_ref.so =
-        # its unmodified sources against the Eigen stand-in) in the OpenMP loop of cmd/discrete_field_to_bitmap/main.cpp:118-135
+        del phi, grad, xd, xd_keep
+        torch.cuda.empty_cache()
         if rank == 0 and world == 1 and not args.no_cpu:
-            os.environ["OMP_NUM_THREADS"] = os.environ.get("DG_CPU_THREADS") or str(len(os.sched_getaffinity(0)))
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            from oracle_api import Oracle, RefGrid, have_ref_grid
-            cres = [min(128, r_) for r_ in ires]                 # a 256^3 .cdf is 3 GB on disk: the CPU arm reads the 128^3 field of the same mesh
-            cgrid = dg.CubicLagrangeDiscreteGrid(mn, mx, cres)
-            cgrid.addFunction(dg.MeshSignedDistance(md))
-            nq_cpu = 2_000_000
-            xc = np.ascontiguousarray(splitmix_points(nq_cpu, INTERP["seed"], mn, mx))
-            if have_ref_grid():
-                tmpf = os.path.join(scratch_dir(), f"_dg_bench_field_{os.getpid()}.cdf")
-                cgrid.save(tmpf)
-                rg = RefGrid(tmpf)
-                rg.interpolate(0, xc[:100000], grad=True)
-                t0 = time.perf_counter(); pr, gr = rg.interpolate(0, xc, grad=True); t_cpu = time.perf_counter() - t0
-                kind = "reference"
-                rg.close(); os.remove(tmpf)
-            else:
-                orc = Oracle(); gd_c, r_c = orc.grid_desc(mn, mx, cres)
-                t0 = time.perf_counter(); pr, gr = orc.interpolate(gd_c, r_c, cgrid.m_nodes[0], xc, grad=True); t_cpu = time.perf_counter() - t0
-                kind = "port"
-            pg, gg = cgrid.interpolate(0, xc, gradient=True)
-            interp["cpu_baseline"] = {"value": nq_cpu / t_cpu / 1e6, "unit": "Mqueries/s", "kind": kind, "cores": int(os.environ["OMP_NUM_THREADS"]),
-                                      "sample": f"{nq_cpu} of the 10M queries on the {cres[0]}^3 field of the same mesh (OpenMP parallel for, value+gradient)",
-                                      "bit_exact_vs_gpu": bool(np.array_equal(pr.view(np.uint64), pg.view(np.uint64)) and np.array_equal(gr.view(np.uint64), gg.view(np.uint64)))}
-            del cgrid
+            c = run_cpu_child({"what": "interp", "mesh": source, "torus": WORKLOAD["torus"], "res": ires, "queries": nq, "seed": INTERP["seed"], "runs": 2})
+            if "seconds" in c:
+                c["value"] = nq / c["seconds"] / 1e6; c["unit"] = "Mqueries/s"
+            interp["cpu_baseline"] = c
 
     # ---------------------------------------------------------------- north-star target config: 256^3 grid, 100,000-triangle mesh
     target = None
     if not args.no_target:
-        tmesh = dg.bumpy_torus()                               # 250 x 200 quads = exactly 100,000 triangles
+        tmesh, ttext, _ = workload_mesh(dg, "target")
         tmd = dg.TriangleMeshDistance(tmesh)
         tmn, tmx = dg.generate_sdf_domain(tmesh.vertices)
         tres = [args.target_resolution] * 3
@@ -524,21 +673,37 @@ def main():
         tfull = torch.empty(tsampler.sh.padded, dtype=torch.float64, device=dev)
         t_ms, _ = timed(lambda: tsampler.step(tfull), 3, 1)
         t_ms = float(np.mean(t_ms))
-        target = {"workload": f"north_star target: {tres[0]}^3 grid ({tn} nodes), synthetic bumpy torus with exactly 100,000 triangles, "
-                              "strong scaling, sharding as config.parallelism", "ms_per_step": t_ms, "value": tn / (t_ms * 1e-3), "unit": "nodes/s",
+        target = {"workload": f"north_star target: {tres[0]}^3 grid ({tn} nodes), {ttext}, strong scaling, sharding as config.parallelism",
+                  "ms_per_step": t_ms, "value": tn / (t_ms * 1e-3), "unit": "nodes/s",
                   "n_gpus": world, "sharded_equals_single_launch": same_as_single_launch(tmd, tdesc, tn, tfull)}
+        del tfull, tsampler
+        torch.cuda.empty_cache()
+        if world == 1 and not args.no_e2e:
+            tnc = tres[0] ** 3
+            add_function_e2e(tmd, tdesc, tn, tnc)
+            ts, tms = [], []
+            for _ in range(3):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                out = add_function_e2e(tmd, tdesc, tn, tnc)
+                ts.append(time.perf_counter() - t0); tms.append(out[3]); del out
+            tm = np.mean(np.array(tms), axis=0)
+            target["e2e"] = {"api": "dg_add_function_sdf: whole addFunction into fresh host arrays (as `e2e` above)", "ms_per_step": float(np.mean(ts)) * 1e3, "best_ms": min(ts) * 1e3,
+                             "value": tn / float(np.mean(ts)), "unit": "nodes/s", "d2h_bytes_per_step": 8 * tn, "host_bytes_written_per_step": 8 * tn + 132 * tnc,
+                             "breakdown_ms": {"total_inside_call": float(tm[0]), "node_pipeline_done": float(tm[1]), "coefficient_array_prefaulted": float(tm[3]),
+                                              "host_worker_threads": int(tm[4]), "allocation_and_return": float(np.mean(ts)) * 1e3 - float(tm[0])}}
         if rank == 0 and world == 1 and not args.no_cpu:
-            rates, info = cpu_sample_rate(tmesh, tmn, tmx, tres, args.cpu_seconds)
-            target["cpu_baseline"] = dict(info, value=float(np.mean(rates)), unit="nodes/s")
-        del tfull, tsampler, tmd
+            c = addfunction_baseline("target", None, tres, runs=1, warm=0, max_seconds=args.cpu_seconds, check_gpu=False, stats_nodes=2000)
+            target["cpu_baseline"] = c
+            if "value" in c and "e2e" in target:
+                target["e2e_speedup_vs_cpu_baseline"] = target["e2e"]["value"] / c["value"]
+        del tmd
 
-    # ---------------------------------------------------------------- the reference's own meshes (configs 2/3/5), when staged
+    # ---------------------------------------------------------------- the reference's other meshes (configs 3/5), when staged
     real = None
-    res_dir = os.path.join(ROOT, "oracle", "_ref", "resources")      # copied there by `make -C oracle ref`; travels with the repo
-    if not args.no_real and os.path.isdir(res_dir):
+    if not args.no_real and os.path.isdir(RES_DIR):
         real = []
-        for name, r3 in (("bunny.obj", 128), ("dragon.obj", 256), ("happy_buddha.obj", 256)):
-            path = os.path.join(res_dir, name)
+        for name, r3 in (("dragon", 256), ("happy_buddha", 256)):
+            path = os.path.join(RES_DIR, name + ".obj")
             if not os.path.exists(path):
                 continue
             rmesh = dg.TriangleMesh(path)
@@ -551,20 +716,27 @@ def main():
             rfull = torch.empty(rs.sh.padded, dtype=torch.float64, device=dev)
             r_ms, _ = timed(lambda: rs.step(rfull), 2, 1)
             r_ms = float(np.mean(r_ms))
-            entry = {"mesh": name, "triangles": int(rmesh.nFaces()), "grid": r3, "nodes": rn, "ms_per_step": r_ms, "value": rn / (r_ms * 1e-3),
+            entry = {"mesh": name + ".obj", "triangles": int(rmesh.nFaces()), "grid": r3, "nodes": rn, "ms_per_step": r_ms, "value": rn / (r_ms * 1e-3),
                      "unit": "nodes/s", "mesh_create_s": t_create, "watertight_flags": rmd.info()["watertight_flags"]}
-            if name == "dragon.obj" and world == 1 and not args.no_density:      # config 5: GenerateDensityMap on the dragon SDF, h = 0.1, rho0 = 1000
+            if rank == 0 and world == 1 and not args.no_cpu:
+                # bounded CPU sample of the reference on the real mesh + a strided full-size parity check of the GPU array against it
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                entry["cpu_baseline"] = addfunction_baseline(name, None, [r3] * 3, runs=1, warm=0, max_seconds=min(10.0, args.cpu_seconds), check_gpu=False, stats_nodes=0)
+                entry["parity_strided"] = strided_parity(rmesh, rmn, rmx, [r3] * 3, rfull[:rn], 1_000_000)
+            if name == "dragon" and world == 1 and not args.no_density:      # config 5: GenerateDensityMap on the dragon SDF, h = 0.1, rho0 = 1000
                 fh = C.c_void_p(); sp = C.c_void_p(stream.cuda_stream)
                 capi.check(capi.lib.dg_field_create_device(C.byref(rdesc), C.c_void_p(rfull.data_ptr()), rn, sp, C.byref(fh)))
                 dens = torch.empty(rn, dtype=torch.float64, device=dev)
                 k3_ms, _ = timed(lambda: capi.check(capi.lib.dg_density_map_device(fh, 0.1, 1000.0, 0, 0, rn, C.c_void_p(dens.data_ptr()), sp)), 1, 1)
+                active = int(((dens > 0) & (dens < 1e300)).sum().item())
                 entry["density_map"] = {"h": 0.1, "rho0": 1000.0, "ms": float(k3_ms[0]), "value": rn / (k3_ms[0] * 1e-3), "unit": "nodes/s",
-                                        "nodes_in_quadrature_branch": int(((dens > 0) & (dens < 1e300)).sum().item())}
+                                        "nodes_in_quadrature_branch": active, "fp64_roofline": k3_roofline(active, float(k3_ms[0]), fp64_peak)}
                 capi.lib.dg_field_destroy(fh); del dens
             real.append(entry)
             del rfull, rs, rmd
+            torch.cuda.empty_cache()
 
-    # ---------------------------------------------------------------- density map (config 5 kernel), N = 1 only
+    # ---------------------------------------------------------------- density map (config 5 kernel) on the headline SDF, N = 1 only
     density = None
     if world == 1 and not args.no_density:
         sdf_sampler.launch(full); torch.cuda.synchronize()
@@ -573,6 +745,7 @@ def main():
         capi.check(capi.lib.dg_field_create_device(C.byref(desc), C.c_void_p(full.data_ptr()), n_nodes, sp, C.byref(fh)))
         dens = torch.empty(n_nodes, dtype=torch.float64, device=dev)
         h_dm = 0.1 * float(np.max(mx - mn)) / 2.5            # the reference default h = 0.1 is for a ~2.5-unit dragon
+
         def dm_step():
             capi.check(capi.lib.dg_density_map_device(fh, h_dm, 1000.0, 0, 0, n_nodes, C.c_void_p(dens.data_ptr()), sp))
         dm_ms, _ = timed(dm_step, 2, 1)
@@ -581,7 +754,8 @@ def main():
         active = int(((dens_h > 0) & (dens_h < 1e300)).sum())
         density = {"metric": "GenerateDensityMap nodes/s (K3)", "value": n_nodes / (dm_ms * 1e-3), "unit": "nodes/s", "ms": dm_ms,
                    "config": {"workload": f"density_func + predicate over the {res[0]}^3 SDF above, h = {h_dm:.4f}, rho0 = 1000, 16^3 Gauss points",
-                              "nodes_in_quadrature_branch": active}}
+                              "nodes_in_quadrature_branch": active},
+                   "fp64_roofline": k3_roofline(active, dm_ms, fp64_peak)}
         if not args.no_cpu:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             from oracle_api import Oracle
@@ -598,8 +772,8 @@ def main():
             density["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "nodes/s", "kind": "port", "cores": orc.max_threads(),
                                        "sample": f"{n_cpu} nodes in 8 windows, oracle/dg_oracle.cpp (the reference tool needs Eigen)",
                                        "bit_exact_vs_gpu": bool(ok)}
-        try:                                                    # N3: the step after the density map in GenerateDensityMap (host code)
-            cells_h = np.empty((int(np.prod(np.array(res, np.uint64))), 32), np.uint32)
+        try:                                                    # N3: the step after the density map in GenerateDensityMap
+            cells_h = np.empty((n_cells, 32), np.uint32)
             capi.check(capi.lib.dg_build_cells(desc.resolution, 0, len(cells_h), capi.ptr(cells_h, capi.U32P)))
             density["reduce_field"] = reduce_field_leg(capi, desc, dens_h, cells_h, 0.0, 3000.0, with_reference=not args.no_cpu)
             del cells_h
@@ -633,22 +807,144 @@ def main():
             capi.lib.dg_field_destroy(fh)
         del dens
 
-    # ---------------------------------------------------------------- CPU baseline, rank 0, N = 1 only
+    # ---------------------------------------------------------------- CPU baseline (the reference's real addFunction), rank 0, N = 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rates, info = cpu_sample_rate(mesh, mn, mx, res, args.cpu_seconds)
-        cpu = dict(info, value=float(np.mean(rates)), unit="nodes/s")
+        cpu = addfunction_baseline(source, WORKLOAD["torus"], res, runs=2, warm=1, max_seconds=args.cpu_seconds, check_gpu=True)
+        if "error" in cpu:
+            cpu = {"value": None, "unit": "nodes/s", "cores": 0, "kind": "reference", "sample": "unavailable: " + cpu["error"][:200]}
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel (K1): fp64 issue, not HBM
+    flops_node = (cpu or {}).get("flops_per_node") or NCU["k1_flops_per_node_fallback"]
+    k1_flops = flops_node * my_nodes
+    k1_tflops = k1_flops / (k1_ms * 1e-3) / 1e12
+    k1_alg_bytes = 8.0 * my_nodes + mesh_info["device_bytes"]          # 8 B/node written + mesh records read once
+    k1_gbs = k1_alg_bytes / (k1_ms * 1e-3) / 1e9
+    roofline = {"kernel": "sdf_sample_nodes_kernel (K1)", "bound": "fp64", "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": k1_tflops / fp64_peak if fp64_peak else None,
+                "traffic": NCU["k1_dram_bytes_per_launch"] if (world == 1 and source == NCU["k1_mesh"] and res[0] == 128) else None, "traffic_source": NCU["k1_source"],
+                "peak_source": "measured in this run: dg_fp64_rate_probe (8 independent DMUL+DADD chains per thread, 8 blocks of 256 threads per SM) -- "
+                               "the library is built without FMA contraction (bit-exact parity with the reference's x86-64 build), so this, not the "
+                               "FMA rate, is the ceiling of its fp64 pipe",
+                "algorithmic_flops_per_node": flops_node,
+                "algorithmic_flops_note": "SURVEY 8(d): visits * 24 + leaf tests * 65 of the REFERENCE algorithm (spheres only, all in fp64), counted by the "
+                                          "oracle port on a strided node sample of this workload; the kernel itself does fewer (fp32 sphere filter, box skip)",
+                "launches_per_step": n_launch, "avg_launch_ms": k1_ms / max(1, n_launch),
+                "ncu": NCU["k1_summary"],
+                "hbm": {"bound": "hbm", "achieved": k1_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k1_gbs / peaks["hbm_gbs"], "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": k1_alg_bytes / max(1, n_launch),
+                        "note": "K1 is not HBM-bound: BVH + triangle records are L2-resident, compulsory HBM traffic is 8 B/node (SURVEY 8d)"},
+                "interpolate": (interp or {}).get("roofline")}
+    if e2e is not None and interp is not None:
+        e2e["interpolate"] = interp["e2e"]
+    if cpu is not None and interp is not None and "cpu_baseline" in interp:
+        cpu["interpolate"] = interp["cpu_baseline"]
 
     if rank == 0:
         line = {"metric": "SDF grid nodes/sec (addFunction)", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "dtype": "f64", "data": data, "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "target_config": target, "reference_meshes": real, "density_map": density,
-                "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms},
-                "sharded_equals_single_launch": sharded_ok}
+                "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms,
+                           "ideal_ms_per_step_from_n1": None, "collective_and_unpack_ms": ms_step - k1_ms},
+                "parity_full": None if cpu is None else {"nodes_bit_exact": cpu.get("parity_nodes_bit_exact"), "nodes_compared": cpu.get("parity_nodes_compared"),
+                                                         "cells_equal": cpu.get("parity_cells_equal"),
+                                                         "interpolate_bit_exact": ((interp or {}).get("cpu_baseline") or {}).get("bit_exact_vs_gpu"),
+                                                         "interpolate_queries_compared": ((interp or {}).get("cpu_baseline") or {}).get("queries_compared")},
+                "sharded_equals_single_launch": sharded_ok,
+                "library": {"path": os.path.relpath(capi.LIB_PATH, ROOT), "emulated": hasattr(capi.lib, "emu_mesh_create")}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ncu-derived constants of the shipped kernels AT THE BENCH CONFIGURATIONS (profiles/: `ncu --set full --clock-control none`; numbers taken
+# under ncu are never bench values -- these are per-launch DRAM bytes and pipe statistics only)
+NCU = {
+    "k1_mesh": "torus", "k1_dram_bytes_per_launch": None, "k1_source": "profiles/ (capture pending for this build)",
+    "k1_summary": None,
+    "k1_flops_per_node_fallback": 9000.0,
+    "k2_dram_bytes_per_launch": None, "k2_source": "profiles/ (capture pending for this build)",
+}
+
+
+def k3_roofline(active_nodes, ms, fp64_peak):
+    """K3 against the measured fp64 issue rate: 4096 value-only interpolations (~155 unfused flops) + the kernel/gamma
+    arithmetic (~15) per node in the quadrature branch; skipped W == 0 points still count as algorithmic work of the reference."""
+    flops = 4096.0 * (155.0 + 15.0) * active_nodes
+    t = flops / (ms * 1e-3) / 1e12
+    return {"bound": "fp64", "achieved": t, "peak": fp64_peak, "unit": "TFLOP/s", "frac": t / fp64_peak if fp64_peak else None,
+            "algorithmic_flops_per_active_node": 4096 * 170, "peak_source": "dg_fp64_rate_probe (DMUL+DADD, no FMA), this run"}
+
+
+def strided_parity(mesh, mn, mx, res, d_nodes, n_check):
+    """full-size parity sample: `n_check` evenly strided nodes of a device-resident coefficient array vs the reference's own
+    signed_distance (oracle/_ref/libdgref.so, else the oracle port) at the oracle's node positions -- bit for bit"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_api import Oracle, RefMesh, have_ref
+    import torch
+    orc = Oracle()
+    gd, r = orc.grid_desc(mn, mx, res)
+    n = orc.num_nodes(r)
+    ids = np.unique(np.linspace(0, n - 1, min(n, n_check)).astype(np.int64))
+    x = orc.node_positions_at(gd, r, ids)
+    m = RefMesh(mesh.vertices, mesh.faces) if have_ref() else orc.mesh(mesh.vertices, mesh.faces)
+    want = m.sample_points(x) if have_ref() else m.distance(x)[0]
+    got = d_nodes[torch.from_numpy(ids).to(d_nodes.device)].cpu().numpy()
+    return {"nodes_compared": int(len(ids)), "bit_exact": bool(np.array_equal(got.view(np.uint64), want.view(np.uint64))),
+            "against": "reference TriangleMeshDistance.h (oracle/_ref)" if have_ref() else "oracle port"}
+
+
+def reduce_field_leg(capi, desc, values, cells, lo, hi, with_reference, tmp_dir=None):
+    """reduceField(field, lo <= v <= hi) (cmd/generate_density_map/main.cpp:141-144) on a sampled field:
+    dg_reduce_field vs the reference class's own reduceField (oracle/_ref, when built)."""
+    if tmp_dir is None:
+        tmp_dir = scratch_dir()
+    keep = np.ascontiguousarray((lo <= values) & (values <= hi) & (values != np.finfo(np.float64).max), np.uint8)
+    n_grid_cells = int(desc.resolution[0]) * int(desc.resolution[1]) * int(desc.resolution[2])
+    best, out = None, None
+    for _ in range(3):
+        nodes, cc = values.copy(), cells.copy()
+        cmap = np.empty(n_grid_cells, np.uint32); n1, n2 = C.c_uint64(), C.c_uint64(); tm = np.zeros(5)
+        t0 = time.perf_counter()
+        capi.check(capi.lib.dg_reduce_field(C.byref(desc), capi.ptr(nodes, capi.F64P), len(nodes), keep.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                            capi.ptr(cc, capi.U32P), len(cc), capi.ptr(cmap, capi.U32P), 0, C.byref(n1), C.byref(n2), capi.ptr(tm, capi.F64P)))
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, out = dt, (nodes[:n1.value], cc[:n2.value], cmap, tm.copy())
+    leg = {"what": "reduceField of the density field with the tool's predicate 0 <= v <= 3 rho0 (dg_reduce_field)",
+           "nodes_in": int(len(values)), "nodes_out": int(len(out[0])), "cells_in": int(len(cells)), "cells_out": int(len(out[1])),
+           "ms": best * 1e3, "ms_cells_nodes_sort_write": [float(t) for t in out[3][:4]], "morton_keys_tied": bool(out[3][4])}
+    if with_reference:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_api import REF_GRID_SO, RefGrid
+        if os.path.exists(REF_GRID_SO):
+            import struct
+            src, dst = os.path.join(tmp_dir, f"dg_reduce_in_{os.getpid()}.cdf"), os.path.join(tmp_dir, f"dg_reduce_out_{os.getpid()}.cdf")
+            try:
+                with open(src, "wb") as f:                              # the reference's one-field file layout (:678-719)
+                    f.write(struct.pack("<3d", *desc.domain_min)); f.write(struct.pack("<3d", *desc.domain_max)); f.write(struct.pack("<3I", *desc.resolution))
+                    f.write(struct.pack("<3d", *desc.cell_size)); f.write(struct.pack("<3d", *desc.inv_cell_size)); f.write(struct.pack("<QQ", n_grid_cells, 1))
+                    for arr in (values, cells, np.arange(len(cells), dtype=np.uint32)):
+                        f.write(struct.pack("<QQ", 1, len(arr))); f.write(np.ascontiguousarray(arr).tobytes())
+                ref = RefGrid(src); t_ref = ref.reduce_window(0, lo, hi); ref.save(dst); ref.close()
+                raw = np.fromfile(dst, np.uint8)
+                off = 24 * 4 + 12 + 16                                   # header: 4 x 3 doubles, 3 uint32, n_cells, n_fields
+
+                def nested(dtype, width):
+                    nonlocal off
+                    n = int(raw[off + 8:off + 16].view(np.uint64)[0]); off += 16
+                    a = raw[off:off + n * width * np.dtype(dtype).itemsize].view(dtype); off += a.nbytes
+                    return a.reshape(n, width) if width > 1 else a
+                rn, rc, rm = nested(np.float64, 1), nested(np.uint32, 32), nested(np.uint32, 1)
+                same = bool(np.array_equal(rn.view(np.uint64), out[0].view(np.uint64)) and np.array_equal(rc, out[1]) and np.array_equal(rm, out[2]))
+                leg["reference"] = {"ms": t_ref * 1e3, "kind": "reference", "impl": "CubicLagrangeDiscreteGrid::reduceField of oracle/_ref (serial, one std::set per node)",
+                                    "identical_nodes_cells_cell_map": same, "speedup": t_ref / best}
+            finally:
+                for p_ in (src, dst):
+                    if os.path.exists(p_):
+                        os.remove(p_)
+    return leg
 
 
 if __name__ == "__main__":

@@ -134,6 +134,23 @@ double refg_add_function_sdf(void* md_, const double* dom_min, const double* dom
     if (cells_out) std::memcpy(cells_out, sdf.m_cells[0].data(), sdf.m_cells[0].size() * 32 * sizeof(uint32_t));
     return dt;
 }
+// A reference grid object holding a given coefficient field, built in memory (a 256^3 .cdf is 3 GB on disk): the reference's own
+// addFunction runs with a constant functor -- that creates m_nodes[0], the connectivity m_cells[0] (:833-886) and m_cell_map[0] (:888-891)
+// exactly as GenerateSDF would -- and the coefficients are then overwritten with `nodes`.  Used as the interpolate CPU baseline on the
+// same field the GPU leg uses.
+void* refg_grid_from_nodes(const double* dom_min, const double* dom_max, const uint32_t* res, const double* nodes, uint64_t n_nodes, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    Eigen::AlignedBox3d domain(Vector3d(dom_min[0], dom_min[1], dom_min[2]), Vector3d(dom_max[0], dom_max[1], dom_max[2]));
+    std::array<unsigned int, 3> resolution = {{res[0], res[1], res[2]}};
+    auto* g = new CubicLagrangeDiscreteGrid(domain, resolution);
+    g->addFunction([](Vector3d const&) { return 0.0; }, false);
+    if (g->m_nodes[0].size() != n_nodes) { delete g; return nullptr; }
+    std::memcpy(g->m_nodes[0].data(), nodes, n_nodes * sizeof(double));
+    return g;
+}
 int refg_omp_max_threads()
 {
 #ifdef _OPENMP

@@ -62,6 +62,7 @@ import bench                         # noqa: E402
 
 bench.INTERP["queries"] = 3000                                   # instead of 10 M
 bench.WORKLOAD["torus"] = (24, 20, 1.0, 0.4, 0.05, 7, 5)        # 960 triangles instead of 69,564
+bench.WORKLOAD["source"] = "torus"                              # not the 69,630-triangle bunny.obj
 
 if __name__ == "__main__":
     bench.main()

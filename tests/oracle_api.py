@@ -298,3 +298,16 @@ class RefAddFunction:
             self.h = None
 
     __del__ = close
+
+
+class RefGridInMemory(RefGrid):
+    """RefGrid over a coefficient array handed over in memory (oracle/ref_grid_wrapper.cpp: refg_grid_from_nodes)."""
+
+    def __init__(self, mn, mx, res, nodes, nthreads=0):
+        self.lib = C.CDLL(REF_GRID_SO)
+        mn, mx, res, nodes = _f64(mn), _f64(mx), _u32(res), _f64(nodes)
+        self.lib.refg_grid_from_nodes.restype = C.c_void_p
+        self.lib.refg_grid_from_nodes.argtypes = [_dp, _dp, _u32p, _dp, C.c_uint64, C.c_int]
+        self.h = self.lib.refg_grid_from_nodes(_p(mn, _dp), _p(mx, _dp), _p(res, _u32p), _p(nodes, _dp), len(nodes), int(nthreads))
+        if not self.h:
+            raise ValueError("node count does not match the grid")

@@ -12,13 +12,13 @@ mkdir -p $O
 } > $O/r2a_host.txt 2>&1
 
 # --- CPU arm under different thread settings (reference arm = oracle/_ref on the host cores)
-for cfg in "DG_CPU_THREADS=128" "DG_CPU_THREADS=64 OMP_PROC_BIND=spread OMP_PLACES=cores" "DG_CPU_THREADS=32 OMP_PROC_BIND=spread OMP_PLACES=cores" "DG_CPU_THREADS=64 OMP_PROC_BIND=spread OMP_PLACES=cores"; do
+for cfg in "DG_CPU_THREADS=128 DG_OMP_PROC_BIND=false" "DG_NOP=1" "DG_CPU_THREADS=128" "DG_CPU_THREADS=32" "DG_NOP=2"; do
   echo "== $cfg" >> $O/r2a_cpuarm.txt
-  env $cfg timeout 200 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | python -c "
+  env $cfg timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print(round(d['value']/1e6,2),'Mnodes/s', d['cpu_baseline']['cores'],'threads', d['cpu_baseline']['sample'][:40])" >> $O/r2a_cpuarm.txt
+        d=json.loads(l); c=d['cpu_baseline']; print(round(d['value']/1e6,2),'Mnodes/s mean;', [round(t,2) for t in d['timing']['per_step_s']], 's/step;', c['cores'],'threads', c.get('omp'), 'quota', c.get('cgroup_cpu_quota'), 'phys', c.get('physical_cores'), c['mode'])" >> $O/r2a_cpuarm.txt
 done
 cat /sys/fs/cgroup/cpu.stat 2>/dev/null | head -6 >> $O/r2a_host.txt
 
@@ -28,7 +28,9 @@ for so in build/variants/*.so; do
   extra="--no-density --no-target"; tests="tests/test_gpu_k1_sdf.py"
   case $n in
     k3div) extra="--no-target"; tests="tests/test_gpu_k3_density.py";;
-    base)  extra="";;
+    base)  extra=""; DISCREGRID_B200_LIB=$PWD/$so timeout 300 python bench.py --steps 5 --warmup 3 --mesh torus --no-interp --no-cpu --no-e2e --no-real --no-density --no-target 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('base TORUS K1 128^3', round(d['ms_per_step'],2),'ms (round 1: 54.9)')";;
     cost|fastdiv) extra="--no-density";;
   esac
   ok=$(DISCREGRID_B200_LIB=$PWD/$so timeout 300 python -m pytest $tests -m gpu -q -x -k "not full_size" 2>&1 | tail -1)
