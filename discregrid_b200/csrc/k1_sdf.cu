@@ -46,9 +46,11 @@
 #endif
 #ifdef DG_EMU
 #define DG_EMU_COUNT(i) (dg_emu::g_counters[(i)]++)        // event counters of the emulation (tests/emu, tools): nothing on the device
+#define DG_EMU_ADD(i, v) (dg_emu::g_counters[(i)] += (unsigned long long)(v))
 #define DG_EMU_TRACE_BLOCK(b) do { if (threadIdx.x == 0) dg_emu::g_block_trace.push_back(b); } while (0)
 #else
 #define DG_EMU_COUNT(i)
+#define DG_EMU_ADD(i, v)
 #define DG_EMU_TRACE_BLOCK(b)
 #endif
 
@@ -619,6 +621,310 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
     out[out_idx] = (sign == 1.0) ? dist : sign * dist;           // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
 }
 
+#if K1_WAVE
+// =====================================================================================================================================
+// WAVEFRONT VARIANT OF THE NODE-LOOP KERNEL (K1_WAVE): persistent warps, queries decoupled from lanes, warp-ballot compaction.
+//
+// The per-lane kernel above keeps one query per lane for its whole walk; every iteration only the lanes whose query sits in the voted
+// phase do work (measured: 14.6 of 32 lanes per instruction -- unequal walk lengths x phases out of step).  Here a WARP owns a pool of
+// K1_WAVE_SLOTS query slots in shared memory; every iteration it counts the slots per phase (one redux.sync), picks the fullest phase,
+// COMPACTS the slots of that phase onto lanes 0..n-1 (two ballots, a rank, a 32-entry work list in shared memory) and runs that phase's
+// straight-line block with (nearly) all lanes busy.  Slots whose query finished are refilled from the next brick of grid nodes (a
+// global atomic hands out bricks), so warps are persistent and there is no per-brick tail.  Each query still walks the tree in the
+// reference's own order with its own stack (shared memory, [depth][slot]) and its own running best: the arithmetic that reaches the
+// output is exactly that of the per-lane kernel -- only WHICH lane executes a step changes.  Stack entries are the packed range only
+// (4 bytes): the deferred sibling's fp32 sphere distance is recomputed from its parent's record when it is popped (the box test reads
+// that record anyway).
+// Slot state (SoA, per warp): A = {b, e, meta, pos} | Q = {qx, qy, qz, E} | B = {best_lo, best_hi, skip_sq, tiny_best} | best | p | s, t | out
+// =====================================================================================================================================
+enum { WP_NODE = 0, WP_LEAF = 1, WP_POP = 2, WP_FIN = 3, WP_EMPTY = 4 };
+constexpr int WS = K1_WAVE_SLOTS;
+static_assert(WS == 64, "two home slots per lane");
+
+struct WaveSmem {
+    int4* A; float4* Q; float4* B; double* best; double* px; double* py; double* pz; double* s; double* t; unsigned* out; unsigned* stack; unsigned* wl;
+};
+__host__ __device__ inline size_t wave_bytes_per_warp(int stack_depth) { return (size_t)WS * (16 + 16 + 16 + 8 + 24 + 16 + 4 + 4 * (size_t)stack_depth) + 64 * sizeof(unsigned); }
+
+__device__ __forceinline__ WaveSmem wave_carve(unsigned char* base, int stack_depth)
+{
+    WaveSmem w;
+    w.A = reinterpret_cast<int4*>(base); base += WS * 16;
+    w.Q = reinterpret_cast<float4*>(base); base += WS * 16;
+    w.B = reinterpret_cast<float4*>(base); base += WS * 16;
+    w.best = reinterpret_cast<double*>(base); base += WS * 8;
+    w.px = reinterpret_cast<double*>(base); base += WS * 8;
+    w.py = reinterpret_cast<double*>(base); base += WS * 8;
+    w.pz = reinterpret_cast<double*>(base); base += WS * 8;
+    w.s = reinterpret_cast<double*>(base); base += WS * 8;
+    w.t = reinterpret_cast<double*>(base); base += WS * 8;
+    w.out = reinterpret_cast<unsigned*>(base); base += WS * 4;
+    w.stack = reinterpret_cast<unsigned*>(base); base += (size_t)WS * 4 * stack_depth;
+    w.wl = reinterpret_cast<unsigned*>(base);
+    return w;
+}
+
+#ifdef DG_EMU
+inline void dg_syncwarp() { dg_emu::collective_wait(0u); }
+#else
+__device__ __forceinline__ void dg_syncwarp() { __syncwarp(); }
+#endif
+
+__device__ __forceinline__ int wave_meta(int depth, int sp, int phase, int ent) { return depth | (sp << 8) | (phase << 16) | (ent << 20); }
+
+// grid node of lane `ln` of brick unit `unit` (= 2 * block + warp of the per-lane kernel's launch geometry): position, output index
+__device__ __forceinline__ bool wave_brick_node(const GridDev& g, const K1Work& w, unsigned unit, unsigned ln, double& px, double& py, double& pz, unsigned& out_idx)
+{
+    const unsigned this_block = unit / (unsigned)(K1_THREADS / 32), warp = unit % (unsigned)(K1_THREADS / 32);
+    int sg = 0;
+#pragma unroll
+    for (int k = 1; k < 4; k++) if (k < w.nseg && this_block >= w.seg[k].block_begin) sg = k;
+    const K1Segment& S = w.seg[sg];
+    unsigned t = this_block - S.block_begin;
+    const unsigned tf = t % S.tiles_f; t /= S.tiles_f;
+    const unsigned tm = t % S.tiles_m; const unsigned ts = t / S.tiles_m;
+#if K1_BRICK_AUTO
+    const unsigned f = tf * (SEG_BF(S) * (unsigned)(K1_THREADS / 32)) + warp * SEG_BF(S) + (ln & (SEG_BF(S) - 1u));
+    const unsigned m = tm * SEG_BM(S) + ((ln >> S.lf) & (SEG_BM(S) - 1u));
+    const unsigned lane_s = ln >> (S.lf + S.lm);
+    const unsigned sl = S.s0 + ts * S.pl_stride * SEG_BS(S) + lane_s;
+#else
+    const unsigned f = tf * (unsigned)(K1_BRICK_F * (K1_THREADS / 32)) + warp * (unsigned)K1_BRICK_F + (ln % K1_BRICK_F);
+    const unsigned m = tm * (unsigned)K1_BRICK_M + ((ln / K1_BRICK_F) % K1_BRICK_M);
+    const unsigned lane_s = ln / (K1_BRICK_F * K1_BRICK_M);
+    const unsigned sl = S.s0 + ts * S.pl_stride * (unsigned)K1_BRICK_S + lane_s;
+#endif
+    const unsigned l = S.l_base + (sl * S.Dm + m) * S.Df + f;
+    const bool alive = (f < S.Df) && (m < S.Dm) && (sl < S.s1) && (l >= w.l_begin) && (l < w.l_end);
+    unsigned i, j, k;
+    const unsigned par = f & 1u, fh = f >> 1;
+    if (S.kind == 0) { i = f; j = m; k = sl; }
+    else if (S.kind == 1) { i = fh; j = m; k = sl; }
+    else if (S.kind == 2) { i = sl; k = m; j = fh; }
+    else { j = sl; i = m; k = fh; }
+    px = g.mn[0] + g.cell[0] * (double)i;                 // indexToNodePosition (cubic_lagrange_discrete_grid.cpp:604-665)
+    py = g.mn[1] + g.cell[1] * (double)j;
+    pz = g.mn[2] + g.cell[2] * (double)k;
+    const double fr = (1.0 + (double)par) / 3.0;
+    if (S.kind == 1) px = px + fr * g.cell[0];
+    else if (S.kind == 2) py = py + fr * g.cell[1];
+    else if (S.kind == 3) pz = pz + fr * g.cell[2];
+    out_idx = w.compact ? S.out_base + ((ts * SEG_BS(S) + lane_s) * S.Dm + m) * S.Df + f : l - w.l_begin;
+    return alive;
+}
+
+__global__ void __launch_bounds__(K1_THREADS, K1_WAVE_MIN_BLOCKS)
+sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normals, int stack_depth, GridDev g, K1Work w, unsigned n_units, double sign,
+                             double* __restrict__ out, unsigned* __restrict__ unit_counter)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const WaveSmem W = wave_carve(k1_smem + (size_t)(threadIdx.x >> 5) * wave_bytes_per_warp(stack_depth), stack_depth);
+    const int n_tri = M.n_tri;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float F_INF = __int_as_float(0x7f800000);
+    W.A[lane] = make_int4(0, 0, wave_meta(0, 0, WP_EMPTY, 0), -1);
+    W.A[lane + 32] = make_int4(0, 0, wave_meta(0, 0, WP_EMPTY, 0), -1);
+    unsigned cur_unit = 0, cur_off = 32;          // warp-uniform: the brick being handed out and how many of its 32 nodes are already in slots
+    bool more = n_units > 0;
+    dg_syncwarp();
+    for (;;) {
+        const int ph0 = (W.A[lane].z >> 16) & 15, ph1 = (W.A[lane + 32].z >> 16) & 15;
+        // one warp-wide sum carries the four live-phase counts (8 bits each; empty slots add nothing)
+        const unsigned tally = __reduce_add_sync(0xffffffffu, ((ph0 < WP_EMPTY) ? (1u << (8 * ph0)) : 0u) + ((ph1 < WP_EMPTY) ? (1u << (8 * ph1)) : 0u));
+        const int c_node = (int)(tally & 0xffu), c_leaf = (int)((tally >> 8) & 0xffu), c_pop = (int)((tally >> 16) & 0xffu), c_fin = (int)(tally >> 24);
+        const int c_live = c_node + c_leaf + c_pop + c_fin, c_empty = WS - c_live;
+        DG_EMU_COUNT(0);
+        int chosen;
+        if (more && c_empty >= K1_WAVE_REFILL) chosen = WP_EMPTY;                       // refill
+        else if (c_live == 0) break;                                                    // nothing left and no more bricks
+        else {
+            // the fullest phase runs (ties: leaf > node > pop > finish); a finished query only needs its result written, which is cheap,
+            // so FIN waits until it fills most of a warp or nothing else is ready
+            chosen = WP_LEAF; int c_best = c_leaf;
+            if (c_node > c_best) { chosen = WP_NODE; c_best = c_node; }
+            if (c_pop > c_best) { chosen = WP_POP; c_best = c_pop; }
+            if (c_fin > c_best || c_best == 0) { chosen = WP_FIN; c_best = c_fin; }
+        }
+        // compaction: slots in the chosen phase -> lanes 0..n-1
+        const bool in0 = (ph0 == chosen), in1 = (ph1 == chosen);
+        const unsigned b0 = __ballot_sync(0xffffffffu, in0), b1 = __ballot_sync(0xffffffffu, in1);
+        const int r0 = __popc(b0 & lt_mask), r1 = __popc(b0) + __popc(b1 & lt_mask);
+        if (in0 && r0 < 32) W.wl[r0] = lane;
+        if (in1 && r1 < 32) W.wl[r1] = lane + 32u;
+        int n_work = __popc(b0) + __popc(b1); if (n_work > 32) n_work = 32;
+        if (lane == 0) { DG_EMU_ADD(10 + chosen, 1); DG_EMU_ADD(16 + chosen, n_work); }     // emulation only: phase executions and lanes used
+        if (chosen == WP_EMPTY) {
+            // ---- REFILL: next nodes of the current brick into free slots
+            if (cur_off >= 32u) {
+                if (lane == 0) W.wl[32] = atomicAdd(unit_counter, 1u);
+                dg_syncwarp();
+                cur_unit = W.wl[32]; cur_off = 0;
+                if (cur_unit >= n_units) { more = false; dg_syncwarp(); continue; }
+            } else dg_syncwarp();
+            unsigned take = 32u - cur_off; if (take > (unsigned)n_work) take = (unsigned)n_work;
+            if (lane < take) {
+                const int slot = (int)W.wl[lane];
+                double px, py, pz; unsigned oi;
+                if (wave_brick_node(g, w, cur_unit, cur_off + lane, px, py, pz, oi)) {
+                    const float qx = (float)(px - M.cx), qy = (float)(py - M.cy), qz = (float)(pz - M.cz);
+                    const float Mq = fmaxf(fmaxf(M.half_extent, fabsf(qx)), fmaxf(fabsf(qy), fabsf(qz)));
+                    const float E = (Mq < 1.0e18f) ? __fmul_ru(Mq, 3.814697265625e-06f) : F_INF;     // 64 * 2^-24 * Mq
+                    W.px[slot] = px; W.py[slot] = py; W.pz[slot] = pz; W.out[slot] = oi;
+                    W.Q[slot] = make_float4(qx, qy, qz, E);
+                    W.best[slot] = DBL_MAX; W.s[slot] = 0.0; W.t[slot] = 0.0;
+                    W.B[slot] = make_float4(__double2float_rd(DBL_MAX), __double2float_ru(DBL_MAX), F_INF, 1.0e-6f * Mq);
+                    W.A[slot] = make_int4(0, n_tri, wave_meta(0, 0, (n_tri == 1) ? WP_LEAF : WP_NODE, 0), -1);
+                }
+            }
+            cur_off += take;
+            dg_syncwarp();
+            continue;
+        }
+        dg_syncwarp();
+        const int slot = ((int)lane < n_work) ? (int)W.wl[lane] : -1;
+        if (slot >= 0) {
+            int4 a = W.A[slot];
+            int b = a.x, e = a.y, depth = a.z & 255, sp = (a.z >> 8) & 255, ent = (a.z >> 20) & 7, phase = chosen;
+            if (chosen == WP_NODE) {
+                // ---- internal node (:537-561): identical decisions to the per-lane kernel
+                DG_EMU_COUNT(1);
+                const float4 q = W.Q[slot], bb = W.B[slot];
+                const float qx = q.x, qy = q.y, qz = q.z, E = q.w, E2 = E + E, best_lo = bb.x, best_hi = bb.y, skip_sq = bb.z;
+                const int m = (b + e) >> 1;
+                bool left_first, go_first, go_second = false, defer = true, decided;
+                {
+                    const float4* f4 = M.nodes_f + (size_t)m * K1_NODEF_STRIDE;
+                    const float4 l4 = __ldg(f4), r4 = __ldg(f4 + 1);
+                    const float4 b0f = __ldg(f4 + 2), b1f = __ldg(f4 + 3), b2f = __ldg(f4 + 4);
+                    const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
+                    const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
+                    const float dl = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) - l4.w;
+                    const float dr = sqrt_approx(fmaf(rz, rz, fmaf(ry, ry, rx * rx))) - r4.w;
+                    left_first = dl < dr;
+                    const float d_first_f = left_first ? dl : dr, d_second_f = left_first ? dr : dl;
+                    const bool order_sure = (d_first_f + E2 < d_second_f);
+                    go_first = (d_first_f + E < best_lo);
+                    const bool skip_first = (d_first_f - E >= best_hi);
+                    decided = order_sure && (go_first || skip_first);
+                    defer = !(d_second_f - E >= best_hi);
+                    if (decided && go_first) {
+                        const float lgx = fmaxf(fmaxf(b0f.x - qx, qx - b0f.w), 0.f), lgy = fmaxf(fmaxf(b0f.y - qy, qy - b1f.x), 0.f), lgz = fmaxf(fmaxf(b0f.z - qz, qz - b1f.y), 0.f);
+                        const float rgx = fmaxf(fmaxf(b1f.z - qx, qx - b2f.y), 0.f), rgy = fmaxf(fmaxf(b1f.w - qy, qy - b2f.z), 0.f), rgz = fmaxf(fmaxf(b2f.x - qz, qz - b2f.w), 0.f);
+                        const float l2 = __fmaf_rd(lgz, lgz, __fmaf_rd(lgy, lgy, __fmul_rd(lgx, lgx)));
+                        const float r2 = __fmaf_rd(rgz, rgz, __fmaf_rd(rgy, rgy, __fmul_rd(rgx, rgx)));
+                        const bool hopeless_first = (left_first ? l2 : r2) > skip_sq, hopeless_second = (left_first ? r2 : l2) > skip_sq;
+                        if (hopeless_second) defer = false;
+                        if (hopeless_first) {
+                            const bool second_yes = (d_second_f + E < best_lo), second_no = (d_second_f - E >= best_hi);
+                            if (second_yes || second_no) { go_first = false; go_second = second_yes && !hopeless_second; }
+                        }
+                    }
+                }
+                if (!decided) {                                                 // fp64, exactly the reference
+                    DG_EMU_COUNT(2);
+                    const double px = W.px[slot], py = W.py[slot], pz = W.pz[slot], best = W.best[slot];
+                    const double* sp8 = reinterpret_cast<const double*>(M.spheres + m);
+                    const double2 a0 = ldg2(sp8), a1 = ldg2(sp8 + 2), a2 = ldg2(sp8 + 4), a3 = ldg2(sp8 + 6);
+                    const double d_left = sphere_dist(px, py, pz, a0.x, a0.y, a1.x, a1.y);      // :539
+                    const double d_right = sphere_dist(px, py, pz, a2.x, a2.y, a3.x, a3.y);     // :540
+                    left_first = d_left < d_right;                                            // :542
+                    const double d_first = left_first ? d_left : d_right, d_second = left_first ? d_right : d_left;
+                    go_first = d_first < best;                                                // :545 / :554
+                    go_second = !go_first && (d_second < best);
+                    defer = (d_second < best);
+                }
+                depth++;
+                if (go_first) {
+                    if (defer) {
+                        DG_EMU_COUNT(9);
+                        W.stack[sp * WS + slot] = left_first ? pack_range(m, e, depth, n_tri, false) : pack_range(b, m, depth, n_tri, true);
+                        sp++;
+                    }
+                    if (left_first) e = m; else b = m;
+                    phase = (e - b == 1) ? WP_LEAF : WP_NODE;
+                } else if (go_second) {
+                    if (left_first) b = m; else e = m;
+                    phase = (e - b == 1) ? WP_LEAF : WP_NODE;
+                } else phase = WP_POP;
+            } else if (chosen == WP_LEAF) {
+                // ---- leaf (:517-534)
+                DG_EMU_COUNT(3);
+                const double px = W.px[slot], py = W.py[slot], pz = W.pz[slot], best = W.best[slot];
+                const double best_sq = best * best;                            // result.distance * result.distance (+inf initially), :528
+                double s, t; int en;
+#if K1_FAST_DIV
+                const double d2 = tri_dist2(M.leaves + b, M.recips + b, px, py, pz, s, t, en);
+#else
+                const double d2 = tri_dist2(M.leaves + b, px, py, pz, s, t, en);
+#endif
+                if (d2 < best_sq) {
+                    DG_EMU_COUNT(4);
+                    const double nb = sqrt(d2);
+                    const float4 q = W.Q[slot];
+                    const float tiny_best = W.B[slot].w, E2 = q.w + q.w;
+                    const float best_lo = __double2float_rd(nb), best_hi = __double2float_ru(nb);
+                    const float th = __fadd_ru(best_hi, E2);
+                    const float skip_sq = (K1_BOX_SKIP && best_lo >= tiny_best) ? __fmul_ru(th, th) : F_INF;
+                    W.best[slot] = nb; W.s[slot] = s; W.t[slot] = t;
+                    W.B[slot] = make_float4(best_lo, best_hi, skip_sq, tiny_best);
+                    a.w = b; ent = en;
+                }
+                phase = WP_POP;
+            } else if (chosen == WP_POP) {
+                // ---- deferred siblings: the reference's second `if (d < result.distance)` (:549, :557) with the updated best
+                const float4 q = W.Q[slot], bb = W.B[slot];
+                const float qx = q.x, qy = q.y, qz = q.z, E = q.w, best_lo = bb.x, best_hi = bb.y, skip_sq = bb.z;
+#pragma unroll 1
+                for (int attempt = 0; attempt < K1_POP_TRIES; attempt++) {
+                    if (sp == 0) { phase = WP_FIN; break; }
+                    sp--;
+                    DG_EMU_COUNT(5);
+                    const unsigned r = W.stack[sp * WS + slot];
+                    const int rb = (int)(r & 0x01ffffffu), rd = (int)((r >> 25) & 31u);
+                    const int re = rb + (n_tri >> rd) + (int)((r >> 30) & 1u);
+                    const bool is_left = (r >> 31) != 0u;
+                    const int pm = is_left ? re : rb;                          // the parent's split position: its record holds this child's sphere and box
+                    const float4* f4 = M.nodes_f + (size_t)pm * K1_NODEF_STRIDE;
+                    const float4 c4 = __ldg(f4 + (is_left ? 0 : 1));
+                    const float cx = qx - c4.x, cy = qy - c4.y, cz = qz - c4.z;
+                    const float df = sqrt_approx(fmaf(cz, cz, fmaf(cy, cy, cx * cx))) - c4.w;
+                    bool visit = (df + E < best_lo);                           // certainly d < best
+                    const bool skip = (df - E >= best_hi);                     // certainly d >= best
+                    if (!(visit || skip)) {                                    // undecided in fp32: the reference's fp64 value
+                        DG_EMU_COUNT(6);
+                        const double* s8 = reinterpret_cast<const double*>(M.spheres + pm) + (is_left ? 0 : 4);
+                        const double2 c0 = ldg2(s8), c1 = ldg2(s8 + 2);
+                        visit = sphere_dist(W.px[slot], W.py[slot], W.pz[slot], c0.x, c0.y, c1.x, c1.y) < W.best[slot];
+                    }
+                    if (visit) {
+#if K1_BOX_SKIP
+                        const float* bx = reinterpret_cast<const float*>(f4 + 2) + (is_left ? 0 : 6);
+                        const float gx = fmaxf(fmaxf(__ldg(bx) - qx, qx - __ldg(bx + 3)), 0.f), gy = fmaxf(fmaxf(__ldg(bx + 1) - qy, qy - __ldg(bx + 4)), 0.f),
+                                    gz = fmaxf(fmaxf(__ldg(bx + 2) - qz, qz - __ldg(bx + 5)), 0.f);
+                        if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
+#endif
+                        b = rb; depth = rd; e = re;
+                        phase = (e - b == 1) ? WP_LEAF : WP_NODE;
+                        break;
+                    }
+                }
+            } else {
+                // ---- finished: nearest point + pseudonormal sign, coefficient out, slot free
+                QueryResult r;
+                r.dist = W.best[slot]; r.s = W.s[slot]; r.t = W.t[slot]; r.pos = a.w; r.entity = ent;
+                const double px = W.px[slot], py = W.py[slot], pz = W.pz[slot];
+                double dist, qx, qy, qz; int tri;
+                finish_query(M.leaves, normals, r, px, py, pz, true, dist, qx, qy, qz, tri);
+                out[W.out[slot]] = (sign == 1.0) ? dist : sign * dist;           // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
+                phase = WP_EMPTY;
+            }
+            W.A[slot] = make_int4(b, e, wave_meta(depth, sp, phase, ent), a.w);
+        }
+        dg_syncwarp();
+    }
+}
+#endif  // K1_WAVE
+
 // batched TriangleMeshDistance::{signed,unsigned}_distance on arbitrary points (a warp = 32 consecutive points)
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 mesh_distance_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals, int stack_depth,
@@ -793,7 +1099,59 @@ cudaError_t k1_configure(int stack_depth)
 #endif
 }
 
-#if K1_COST_ORDER
+#if K1_WAVE
+// persistent launch of the wavefront kernel: one resident wave of blocks, bricks handed out by a global counter
+static cudaError_t launch_sampling_wave(const DeviceBvh& m, const GridDev& g, const K1Work& w, unsigned blocks, double sign, double* d_out, cudaStream_t stream)
+{
+    const unsigned n_units = blocks * (unsigned)(K1_THREADS / 32);
+    const size_t smem = (size_t)(K1_THREADS / 32) * wave_bytes_per_warp(m.stack_depth);
+#ifdef DG_EMU
+    static unsigned counter;
+    counter = 0;
+    const unsigned grid = blocks < 3u ? blocks : 3u;
+    DG_KERNEL_LAUNCH(sdf_sample_nodes_wave_kernel, grid, K1_THREADS, smem, stream, mesh_dev(m), m.normals, m.stack_depth, g, w, n_units, sign, d_out, &counter);
+    return cudaSuccess;
+#else
+    // per device: a ring of brick counters (a launch zeroes its own on its stream, so launches on different streams never share one)
+    // and the resident-block count of the kernel for this shared-memory size
+    struct PerDev { unsigned* counters = nullptr; unsigned next = 0; int sm = 0; int resident[64] = {0}; };
+    static std::mutex mu;
+    static PerDev per[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    unsigned* counter; int resident, sm;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        PerDev& P = per[dev];
+        if (!P.counters) {
+            e = cudaMalloc(reinterpret_cast<void**>(&P.counters), 256 * sizeof(unsigned));
+            if (e != cudaSuccess) return e;
+            e = cudaDeviceGetAttribute(&P.sm, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+        }
+        const int dkey = m.stack_depth < 64 ? m.stack_depth : 63;
+        if (!P.resident[dkey]) {
+            if (smem > 48 * 1024) { e = cudaFuncSetAttribute(sdf_sample_nodes_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+            int nb = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sdf_sample_nodes_wave_kernel, K1_THREADS, smem);
+            if (e != cudaSuccess) return e;
+            P.resident[dkey] = nb > 0 ? nb : 1;
+        }
+        counter = P.counters + (P.next++ & 255u);
+        resident = P.resident[dkey]; sm = P.sm;
+    }
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    const unsigned full = (unsigned)(resident * sm);
+    const unsigned grid = blocks < full ? blocks : full;
+    DG_KERNEL_LAUNCH(sdf_sample_nodes_wave_kernel, grid, K1_THREADS, smem, stream, mesh_dev(m), m.normals, m.stack_depth, g, w, n_units, sign, d_out, counter);
+    return DG_AFTER_LAUNCH();
+#endif
+}
+#define DG_LAUNCH_SAMPLING(m, g, w, blocks, sign, out, stream) return launch_sampling_wave((m), (g), (w), (blocks), (sign), (out), (stream))
+#elif K1_COST_ORDER
 #ifdef DG_EMU
 #define DG_SCRATCH_ALLOC(ptr, bytes, stream) ((*(void**)(ptr) = std::malloc(bytes)) ? cudaSuccess : cudaErrorMemoryAllocation)
 #define DG_SCRATCH_FREE(p, stream) std::free(p)

@@ -75,6 +75,21 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 #define K1_MIN_BLOCKS (1024 / K1_THREADS_PER_BLOCK)   // blocks per SM the register allocation must allow (32 warps)
 #endif
 
+// K1_WAVE 1: the node-loop kernel is the WAVEFRONT variant (k1_sdf.cu): persistent warps, a pool of K1_WAVE_SLOTS query slots per warp in
+// shared memory, per iteration the fullest phase is compacted onto the lanes by ballot.  0: the per-lane kernel (one query per lane).
+#ifndef K1_WAVE
+#define K1_WAVE 0
+#endif
+#ifndef K1_WAVE_SLOTS
+#define K1_WAVE_SLOTS 64           // query slots per warp (two home slots per lane)
+#endif
+#ifndef K1_WAVE_REFILL
+#define K1_WAVE_REFILL 16          // refill from the next brick as soon as this many slots are free
+#endif
+#ifndef K1_WAVE_MIN_BLOCKS
+#define K1_WAVE_MIN_BLOCKS 10      // blocks of K1_THREADS per SM the register allocation must allow (shared memory allows about as many)
+#endif
+
 // One of the four row-major 3-D node arrays of the grid (vertex nodes, x-/y-/z-edge nodes), restricted to the
 // slow-planes [s0, s1) that a node range touches.  l = l_base + (s*Dm + m)*Df + f.
 // K1_BRICK_AUTO 1: the warp's brick is chosen per node array at launch time -- the power-of-two shape (f x m x s, 32 nodes) whose PHYSICAL

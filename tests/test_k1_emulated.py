@@ -12,7 +12,7 @@ from conftest import GOLDEN, ROOT, bits_equal, grid_for
 from test_oracle_golden import read_cdf, read_obj
 
 # default knobs, and the prepared-but-off knob variants (K1_FAST_DIV + K1_VOTE_REDUX); DG_K1_EMU_LIB adds any other build of tests/emu/k1_emu.cpp
-LIBS = [os.path.join(ROOT, "build", "bin", "libk1emu.so"), os.path.join(ROOT, "build", "bin", "libk1emu_knobs.so")] + \
+LIBS = [os.path.join(ROOT, "build", "bin", n) for n in ("libk1emu.so", "libk1emu_knobs.so", "libk1emu_wave.so", "libk1emu_perlane.so")] + \
        ([os.environ["DG_K1_EMU_LIB"]] if os.environ.get("DG_K1_EMU_LIB") else [])
 _dp, _u32p, _i32p, _u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
 
@@ -198,6 +198,8 @@ def test_emulated_launch_order(emu, orc):
     """the order in which the sampling kernel takes its blocks: launch order in the default build; with K1_COST_ORDER (knobs build) a
     permutation of the same blocks that starts far from the surface (heavy) and ends near it (light)"""
     import discregrid_b200 as dg
+    if "wave" in emu.lib._name:
+        pytest.skip("the wavefront kernel hands out bricks through a counter: there is no block order")
     emu.lib.emu_block_trace.restype = C.c_uint64
     emu.lib.emu_block_trace.argtypes = [_u32p, C.c_uint64]
     t = dg.bumpy_torus(24, 20, 1.0, 0.4, 0.05, 7, 5)
