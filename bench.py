@@ -19,8 +19,10 @@ A "step" = one full pass of the addFunction node loop over the 14,926,977 nodes.
   cpu_baseline / --impl reference
              the reference's REAL addFunction (oracle/_ref/libdiscregrid_ref.so = its unmodified sources, oracle/ref_grid_wrapper.cpp:
              refg_add_function_sdf) with the GenerateSDF functor on the host cores, whole grid, timed around the call exactly as e2e is.
-             Threads: physical cores in the affinity mask, capped by the cgroup CPU quota, OMP_PROC_BIND=spread OMP_PLACES=cores
-             (SURVEY 8d).  The CPU work always runs in a child process so that these settings are in place before libgomp starts.
+             Threads: all logical CPUs of the affinity mask, or 2 x the cgroup CPU quota when one is in force (the measured optimum on
+             both kinds of box), OMP_PROC_BIND=spread OMP_PLACES=threads.  The CPU work always runs in a child process so that these
+             settings are in place before libgomp starts; the line reports cores, quota and the per-thread rate so that runs on
+             differently provisioned hosts can be compared.
 The second half of the metric, interpolate()+gradient Mqueries/s (config 4: 10 M uniform random queries on a 256^3 SDF), is carried
 under "interpolate" and nested in roofline / e2e / cpu_baseline (the driver keeps those objects whole).
 """
@@ -162,9 +164,11 @@ def splitmix_points(n, seed, lo, hi):
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_policy():
-    """Host threads for the reference's OpenMP loops: one per PHYSICAL core of the affinity mask, never more than the cgroup
-    CPU quota allows (a 1-GPU lease that sees 128 logical CPUs under a smaller quota runs 128 spinning threads several times slower),
-    spread over the sockets, pinned to cores.  DG_CPU_THREADS overrides the count."""
+    """Host threads for the reference's OpenMP loops: every logical CPU of the affinity mask -- the BVH walk is latency-bound and gains from
+    SMT (measured on the B200 hosts: 128 threads on 64 cores 13.0 vs 9.8 Mnodes/s with 64) -- unless a cgroup CPU quota is in force: a 1-GPU
+    lease of this pool sees 128 logical CPUs under `cpu.max = 16 CPUs`, where 128 busy threads are SLOWER than 32 (1.85 vs 2.09 Mnodes/s,
+    profiles/r2a_cpuarm.txt); then 2 x quota threads.  Threads are spread and pinned (OMP_PROC_BIND=spread, OMP_PLACES=threads).
+    DG_CPU_THREADS overrides the count."""
     allowed = sorted(os.sched_getaffinity(0))
     cores = {}
     for c in allowed:
@@ -193,13 +197,13 @@ def cpu_policy():
                 break
     except OSError:
         pass
-    threads = len(cores) or len(allowed) or 1
+    threads = len(allowed) or 1
     if quota is not None and quota >= 1:
-        threads = max(1, min(threads, int(quota)))
+        threads = max(1, min(threads, int(2 * quota)))
     if os.environ.get("DG_CPU_THREADS"):
         threads = int(os.environ["DG_CPU_THREADS"])
     env = {"OMP_NUM_THREADS": str(threads), "OMP_PROC_BIND": os.environ.get("DG_OMP_PROC_BIND", "spread"),
-           "OMP_PLACES": os.environ.get("DG_OMP_PLACES", "cores"), "OMP_DYNAMIC": "false"}
+           "OMP_PLACES": os.environ.get("DG_OMP_PLACES", "threads"), "OMP_DYNAMIC": "false"}
     return {"threads": threads, "logical_cpus": len(allowed), "physical_cores": len(cores), "cgroup_cpu_quota": quota, "cpu_model": model, "omp_env": env}
 
 
@@ -356,6 +360,7 @@ def addfunction_baseline(source, torus, res, runs, warm, max_seconds, check_gpu,
         return d
     t = d["times_s"]
     d["value"] = d["n_nodes"] / float(np.mean(t)); d["unit"] = "nodes/s"; d["best_value"] = d["n_nodes"] / min(t)
+    d["value_per_thread"] = d["value"] / max(1, d["cores"])          # hosts of this pool differ in the CPUs a lease may use (16-CPU quota vs 128)
     return d
 
 

@@ -118,3 +118,23 @@ def test_real_meshes_through_reference_tool(orc, mesh, fixture, sign):
     assert bits_equal(mn, g["mn"]) and bits_equal(mx, g["mx"])          # non-cubic bounding box: padding arithmetic incl. the norm order of the stand-in
     gd, res = orc.grid_desc(mn, mx, g["res"])
     assert bits_equal(orc.mesh(V, F).sample_sdf(gd, res, sign=sign), g["nodes"][0])
+
+
+def test_oracle_equals_the_references_real_addfunction(orc):
+    """refg_add_function_sdf drives the reference's own CubicLagrangeDiscreteGrid::addFunction with the GenerateSDF functor
+    (cubic_lagrange_discrete_grid.cpp:780-899; cmd/generate_sdf/main.cpp:92-105): node coefficients, connectivity table and node count
+    equal the oracle's restatement bit for bit -- also inverted and on an anisotropic resolution"""
+    from oracle_api import RefAddFunction, have_ref_grid
+    if not have_ref_grid():
+        pytest.skip("oracle/_ref/libdiscregrid_ref.so not built")
+    import discregrid_b200 as dg
+    t = dg.bumpy_torus(30, 24, 1.0, 0.4, 0.05, 7, 5)
+    ref = RefAddFunction(t.vertices, t.faces)
+    mesh = orc.mesh(t.vertices, t.faces)
+    mn, mx = orc.generate_sdf_domain(t.vertices)
+    for res, invert in (((9, 7, 5), False), ((6, 6, 6), True)):
+        dt, nodes, cells = ref.add_function(mn, mx, res, invert=invert, want_nodes=True, want_cells=True)
+        gd, r = orc.grid_desc(mn, mx, res)
+        want = mesh.sample_sdf(gd, r, sign=-1.0 if invert else 1.0)
+        assert dt > 0 and np.array_equal(nodes.view(np.uint64), want.view(np.uint64))
+        assert np.array_equal(cells, orc.build_cells(r))
