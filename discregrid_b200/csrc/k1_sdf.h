@@ -130,24 +130,6 @@ struct K1Work {
 #define K1_VOTE_REDUX 0
 #endif
 
-// K1_COST_ORDER 1: blocks are launched heaviest first.  A query's cost grows about linearly with its distance to the surface (x9 from the
-// nearest to the farthest decile), and a launch ends with a ~2 ms tail because the last-scheduled blocks include slow ones.  Five tiny
-// launches on the same stream build the order: unsigned distances on a coarse lattice (the query kernel itself), their maximum, a cost
-// class per block from the lattice value at the block's centre, a counting sort of the blocks by class (heaviest class first), and the
-// sampling kernel then takes its block id from that table.  Results do not depend on the order.  Off until measured on the GPU.
-#ifndef K1_COST_ORDER
-#define K1_COST_ORDER 0
-#endif
-#ifndef K1_COST_LATTICE
-#define K1_COST_LATTICE 16         // lattice points per axis
-#endif
-#ifndef K1_COST_CLASSES
-#define K1_COST_CLASSES 32
-#endif
-#ifndef K1_COST_MIN_BLOCKS
-#define K1_COST_MIN_BLOCKS 4096     // smaller launches keep the plain order (the emulated test build sets 1)
-#endif
-
 struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once by dg_mesh_create
     const SpherePair* spheres = nullptr;
     const LeafRecord* leaves = nullptr;

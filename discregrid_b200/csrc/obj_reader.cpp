@@ -29,6 +29,9 @@ inline bool take_double(const char*& p, const char* end, double& v)
         p = r.ptr; return false;
     }
     p = r.ptr;
+    // num_get accumulates "1e" / "1.5e+" as part of the number and then fails the conversion (value 0, failbit): from_chars stopped in
+    // front of the malformed exponent instead
+    if (p < end && (*p == 'e' || *p == 'E')) { v = 0.0; return false; }
     return true;
 }
 
@@ -61,10 +64,11 @@ void parse_chunk(const char* b, const char* e, Chunk& c)
                 if (!te) te = q;                                               // buf.substr(0, buf.find_first_of('/'))
                 // std::stoi: optional sign, digits; throws when there is no digit or the value leaves int
                 const char* d = t;
-                if (d < te && *d == '+') d++;
+                bool two_signs = false;
+                if (d < te && *d == '+') { d++; two_signs = (d < te && (*d == '-' || *d == '+')); }     // strtol takes ONE sign: "+-5" throws in std::stoi
                 long long val = 0;
                 const auto r = std::from_chars(d, te, val, 10);
-                if (r.ec != std::errc() || val < INT_MIN || val > INT_MAX) {
+                if (two_signs || r.ec != std::errc() || val < INT_MIN || val > INT_MAX) {
                     if (c.err_line < 0) { c.err_line = c.lines; c.err = "face index is not an integer (std::stoi would throw)"; }
                     val = 1;
                 }

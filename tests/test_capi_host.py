@@ -135,6 +135,15 @@ def test_obj_reader_records_and_errors(dg, tmp_path):
     assert ei.value.code == capi.DG_ERR_INVALID and "bad.obj:4" in str(ei.value)
     with pytest.raises(FileNotFoundError):
         dg.TriangleMesh(str(tmp_path / "missing.obj"))
+    # malformed exponents: num_get swallows "1e" / "1.5e+" as part of the number and fails the extraction (value 0, the following
+    # extractions fail too); a face index with two signs makes std::stoi throw
+    mal = tmp_path / "mal.obj"
+    mal.write_text("v 1e 2 3\nv 4 1.5e+ 6\nv 7 8 9\nf 1 2 3\n")
+    assert np.array_equal(dg.TriangleMesh(str(mal)).vertices, [[0, 0, 0], [4, 0, 0], [7, 8, 9]])
+    two = tmp_path / "two.obj"
+    two.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf +-1 2 3\n")
+    with pytest.raises(dg.DiscregridError):
+        dg.TriangleMesh(str(two))
 
 
 def test_obj_reader_parallel_chunks_and_reference_loader(dg, tmp_path):
