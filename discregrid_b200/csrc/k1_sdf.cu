@@ -399,10 +399,14 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                         const int re = rb + (n_tri >> rd) + (int)((r >> 30) & 1u);
 #if K1_BOX_SKIP
                         {   // the best has usually shrunk since this sibling was deferred: box test against the current best
+                            // the child's box sits in two of the record's three box quads (l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz): two
+                            // 16-byte loads instead of six scalar ones (the six were 29 % of the kernel's L1 tag requests, profiles/r2a)
                             const bool is_left = (r >> 31) != 0u;
-                            const float* bx = reinterpret_cast<const float*>(M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE + 2) + (is_left ? 0 : 6);
-                            const float gx = fmaxf(fmaxf(__ldg(bx) - qx, qx - __ldg(bx + 3)), 0.f), gy = fmaxf(fmaxf(__ldg(bx + 1) - qy, qy - __ldg(bx + 4)), 0.f),
-                                        gz = fmaxf(fmaxf(__ldg(bx + 2) - qz, qz - __ldg(bx + 5)), 0.f);
+                            const float4* bq = M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE + (is_left ? 2 : 3);
+                            const float4 u = __ldg(bq), v = __ldg(bq + 1);
+                            const float lox = is_left ? u.x : u.z, loy = is_left ? u.y : u.w, loz = is_left ? u.z : v.x;
+                            const float hix = is_left ? u.w : v.y, hiy = is_left ? v.x : v.z, hiz = is_left ? v.y : v.w;
+                            const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
                             if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
                         }
 #endif
@@ -627,21 +631,21 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
 // output is exactly that of the per-lane kernel -- only WHICH lane executes a step changes.  Stack entries are the packed range only
 // (4 bytes): the deferred sibling's fp32 sphere distance is recomputed from its parent's record when it is popped (the box test reads
 // that record anyway).
-// Slot state (SoA, per warp): A = {b, e, meta, pos} | Q = {qx, qy, qz, E} | B = {best_lo, best_hi, skip_sq, tiny_best} | best | p | s, t | out
+// Slot state (SoA, per warp): meta (depth | sp | phase | entity, 4-byte stride: the home lanes' phase reads are conflict-free) | BE = {b, e} |
+// pos | Q = {qx, qy, qz, E} | B = {best_lo, best_hi, skip_sq, tiny_best} | best | p | s, t | out
 // =====================================================================================================================================
 enum { WP_NODE = 0, WP_LEAF = 1, WP_POP = 2, WP_FIN = 3, WP_EMPTY = 4 };
 constexpr int WS = K1_WAVE_SLOTS;
 static_assert(WS == 64, "two home slots per lane");
 
 struct WaveSmem {
-    int4* A; float4* Q; float4* B; double* best; double* px; double* py; double* pz; double* s; double* t; unsigned* out; unsigned* stack; unsigned* wl;
+    int* meta; int2* BE; int* pos; float4* Q; float4* B; double* best; double* px; double* py; double* pz; double* s; double* t; unsigned* out; unsigned* stack; unsigned* wl;
 };
 __host__ __device__ inline size_t wave_bytes_per_warp(int stack_depth) { return (size_t)WS * (16 + 16 + 16 + 8 + 24 + 16 + 4 + 4 * (size_t)stack_depth) + 64 * sizeof(unsigned); }
 
 __device__ __forceinline__ WaveSmem wave_carve(unsigned char* base, int stack_depth)
 {
     WaveSmem w;
-    w.A = reinterpret_cast<int4*>(base); base += WS * 16;
     w.Q = reinterpret_cast<float4*>(base); base += WS * 16;
     w.B = reinterpret_cast<float4*>(base); base += WS * 16;
     w.best = reinterpret_cast<double*>(base); base += WS * 8;
@@ -650,6 +654,9 @@ __device__ __forceinline__ WaveSmem wave_carve(unsigned char* base, int stack_de
     w.pz = reinterpret_cast<double*>(base); base += WS * 8;
     w.s = reinterpret_cast<double*>(base); base += WS * 8;
     w.t = reinterpret_cast<double*>(base); base += WS * 8;
+    w.BE = reinterpret_cast<int2*>(base); base += WS * 8;
+    w.meta = reinterpret_cast<int*>(base); base += WS * 4;
+    w.pos = reinterpret_cast<int*>(base); base += WS * 4;
     w.out = reinterpret_cast<unsigned*>(base); base += WS * 4;
     w.stack = reinterpret_cast<unsigned*>(base); base += (size_t)WS * 4 * stack_depth;
     w.wl = reinterpret_cast<unsigned*>(base);
@@ -714,13 +721,13 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
     const int n_tri = M.n_tri;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float F_INF = __int_as_float(0x7f800000);
-    W.A[lane] = make_int4(0, 0, wave_meta(0, 0, WP_EMPTY, 0), -1);
-    W.A[lane + 32] = make_int4(0, 0, wave_meta(0, 0, WP_EMPTY, 0), -1);
+    W.meta[lane] = wave_meta(0, 0, WP_EMPTY, 0);
+    W.meta[lane + 32] = wave_meta(0, 0, WP_EMPTY, 0);
     unsigned cur_unit = 0, cur_off = 32;          // warp-uniform: the brick being handed out and how many of its 32 nodes are already in slots
     bool more = n_units > 0;
     dg_syncwarp();
     for (;;) {
-        const int ph0 = (W.A[lane].z >> 16) & 15, ph1 = (W.A[lane + 32].z >> 16) & 15;
+        const int ph0 = (W.meta[lane] >> 16) & 15, ph1 = (W.meta[lane + 32] >> 16) & 15;
         // one warp-wide sum carries the four live-phase counts (8 bits each; empty slots add nothing)
         const unsigned tally = __reduce_add_sync(0xffffffffu, ((ph0 < WP_EMPTY) ? (1u << (8 * ph0)) : 0u) + ((ph1 < WP_EMPTY) ? (1u << (8 * ph1)) : 0u));
         const int c_node = (int)(tally & 0xffu), c_leaf = (int)((tally >> 8) & 0xffu), c_pop = (int)((tally >> 16) & 0xffu), c_fin = (int)(tally >> 24);
@@ -744,6 +751,12 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
         if (in0 && r0 < 32) W.wl[r0] = lane;
         if (in1 && r1 < 32) W.wl[r1] = lane + 32u;
         int n_work = __popc(b0) + __popc(b1); if (n_work > 32) n_work = 32;
+#if K1_WAVE_HOME
+        // home-slot assignment: lane i only ever touches slots i and i + 32 (bank == lane for every state array: no shared-memory bank
+        // conflicts, no work list); a lane is busy when either of its two slots is in the chosen phase
+        const int home_slot = in0 ? (int)lane : (in1 ? (int)lane + 32 : -1);
+        if (chosen != WP_EMPTY) n_work = __popc(b0 | b1);
+#endif
         if (lane == 0) { DG_EMU_ADD(10 + chosen, 1); DG_EMU_ADD(16 + chosen, n_work); }     // emulation only: phase executions and lanes used
         if (chosen == WP_EMPTY) {
             // ---- REFILL: next nodes of the current brick into free slots
@@ -765,7 +778,8 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     W.Q[slot] = make_float4(qx, qy, qz, E);
                     W.best[slot] = DBL_MAX; W.s[slot] = 0.0; W.t[slot] = 0.0;
                     W.B[slot] = make_float4(__double2float_rd(DBL_MAX), __double2float_ru(DBL_MAX), F_INF, 1.0e-6f * Mq);
-                    W.A[slot] = make_int4(0, n_tri, wave_meta(0, 0, (n_tri == 1) ? WP_LEAF : WP_NODE, 0), -1);
+                    W.BE[slot] = make_int2(0, n_tri); W.pos[slot] = -1;
+                    W.meta[slot] = wave_meta(0, 0, (n_tri == 1) ? WP_LEAF : WP_NODE, 0);
                 }
             }
             cur_off += take;
@@ -773,10 +787,15 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
             continue;
         }
         dg_syncwarp();
+#if K1_WAVE_HOME
+        const int slot = home_slot;
+#else
         const int slot = ((int)lane < n_work) ? (int)W.wl[lane] : -1;
+#endif
         if (slot >= 0) {
-            int4 a = W.A[slot];
-            int b = a.x, e = a.y, depth = a.z & 255, sp = (a.z >> 8) & 255, ent = (a.z >> 20) & 7, phase = chosen;
+            const int2 be = W.BE[slot];
+            const int mt = W.meta[slot];
+            int b = be.x, e = be.y, depth = mt & 255, sp = (mt >> 8) & 255, ent = (mt >> 20) & 7, phase = chosen;
             if (chosen == WP_NODE) {
                 // ---- internal node (:537-561): identical decisions to the per-lane kernel
                 DG_EMU_COUNT(1);
@@ -859,7 +878,7 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     const float skip_sq = (K1_BOX_SKIP && best_lo >= tiny_best) ? __fmul_ru(th, th) : F_INF;
                     W.best[slot] = nb; W.s[slot] = s; W.t[slot] = t;
                     W.B[slot] = make_float4(best_lo, best_hi, skip_sq, tiny_best);
-                    a.w = b; ent = en;
+                    W.pos[slot] = b; ent = en;
                 }
                 phase = WP_POP;
             } else if (chosen == WP_POP) {
@@ -890,9 +909,11 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     }
                     if (visit) {
 #if K1_BOX_SKIP
-                        const float* bx = reinterpret_cast<const float*>(f4 + 2) + (is_left ? 0 : 6);
-                        const float gx = fmaxf(fmaxf(__ldg(bx) - qx, qx - __ldg(bx + 3)), 0.f), gy = fmaxf(fmaxf(__ldg(bx + 1) - qy, qy - __ldg(bx + 4)), 0.f),
-                                    gz = fmaxf(fmaxf(__ldg(bx + 2) - qz, qz - __ldg(bx + 5)), 0.f);
+                        const float4* bq = f4 + (is_left ? 2 : 3);            // the child's box: two of the record's three box quads
+                        const float4 u = __ldg(bq), v = __ldg(bq + 1);
+                        const float lox = is_left ? u.x : u.z, loy = is_left ? u.y : u.w, loz = is_left ? u.z : v.x;
+                        const float hix = is_left ? u.w : v.y, hiy = is_left ? v.x : v.z, hiz = is_left ? v.y : v.w;
+                        const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
                         if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
 #endif
                         b = rb; depth = rd; e = re;
@@ -903,14 +924,15 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
             } else {
                 // ---- finished: nearest point + pseudonormal sign, coefficient out, slot free
                 QueryResult r;
-                r.dist = W.best[slot]; r.s = W.s[slot]; r.t = W.t[slot]; r.pos = a.w; r.entity = ent;
+                r.dist = W.best[slot]; r.s = W.s[slot]; r.t = W.t[slot]; r.pos = W.pos[slot]; r.entity = ent;
                 const double px = W.px[slot], py = W.py[slot], pz = W.pz[slot];
                 double dist, qx, qy, qz; int tri;
                 finish_query(M.leaves, normals, r, px, py, pz, true, dist, qx, qy, qz, tri);
                 out[W.out[slot]] = (sign == 1.0) ? dist : sign * dist;           // cmd/generate_sdf/main.cpp:97 (-1.0 * d) / :101
                 phase = WP_EMPTY;
             }
-            W.A[slot] = make_int4(b, e, wave_meta(depth, sp, phase, ent), a.w);
+            if (chosen == WP_NODE || chosen == WP_POP) W.BE[slot] = make_int2(b, e);
+            W.meta[slot] = wave_meta(depth, sp, phase, ent);
         }
         dg_syncwarp();
     }

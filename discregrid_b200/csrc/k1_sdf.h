@@ -83,6 +83,9 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 #ifndef K1_WAVE_SLOTS
 #define K1_WAVE_SLOTS 64           // query slots per warp (two home slots per lane)
 #endif
+#ifndef K1_WAVE_HOME
+#define K1_WAVE_HOME 0             // 1: no compaction across lanes -- a lane serves only its two home slots (conflict-free shared memory)
+#endif
 #ifndef K1_WAVE_REFILL
 #define K1_WAVE_REFILL 16          // refill from the next brick as soon as this many slots are free
 #endif

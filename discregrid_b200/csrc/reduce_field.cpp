@@ -122,6 +122,60 @@ void replay_std_sort(KeyPos* a, uint64_t n, unsigned nt)
 bool replay_std_sort_matches() { return sort_replay_matches_std_sort(); }
 uint64_t replay_std_sort_heap_fallbacks() { return g_replay_heap_sorts.load(); }
 
+// The reference compacts the surviving nodes by "swap the dead node with the last live slot, walking from the back" (:1135-1156):
+// replayed on a permutation array.  Returns the number of survivors m; perm[0..m) = original ids of the survivors in that order.
+uint64_t reduce_swap_walk(const uint8_t* used, uint64_t n_nodes, std::vector<uint32_t>& perm)
+{
+    perm.resize(n_nodes);
+    std::iota(perm.begin(), perm.end(), 0u);
+    uint32_t last = (uint32_t)(n_nodes - 1);
+    for (int64_t i = (int64_t)n_nodes - 1; i >= 0; --i) {
+        if (used[i]) continue;                                   // position i still holds node i when the walk reaches it
+        std::swap(perm[i], perm[last]);
+        last--;                                                  // wraps to 0xffffffff when nothing survives: last + 1 == 0 below
+    }
+    return (uint64_t)(uint32_t)(last + 1u);
+}
+
+// Order of the survivors: positions 0..m-1 sorted by the Morton key of the node sitting there (:1160-1165), equal keys in the order
+// libstdc++'s std::sort leaves them (see reduce_field.h).  kp[i] = {key of the node at position i, i}; kp is consumed.
+void reduce_order_survivors(std::vector<KeyPos>& kp, bool force_std_sort, std::vector<uint32_t>& order, int& tie_path)
+{
+    const uint64_t m = kp.size();
+    const unsigned nt = n_threads();
+    order.resize(m);
+    tie_path = 0;
+    auto has_ties = [&](const std::vector<KeyPos>& sorted) {
+        std::atomic<int> dup{0};
+        parallel_chunks(m, nt, [&](unsigned, uint64_t b, uint64_t e) {
+            for (uint64_t i = std::max<uint64_t>(b, 1); i < e; i++) if (sorted[i].key == sorted[i - 1].key) { dup.store(1); break; }
+        });
+        return dup.load() != 0;
+    };
+    if (replay_std_sort_matches() && !force_std_sort) {
+        // the reference's own sort on the reference's own input sequence, replayed on all threads (reduce_field.h): right with and
+        // without ties
+        replay_std_sort(kp.data(), m, nt);
+        tie_path = has_ties(kp) ? 1 : 0;
+        parallel_chunks(m, nt, [&](unsigned, uint64_t b, uint64_t e) { for (uint64_t i = b; i < e; i++) order[i] = kp[i].pos; });
+    } else {
+        // another standard library (or force_std_sort): any correct sort will do while the keys are distinct; with ties only the
+        // reference's very call reproduces its order
+        bool ties = force_std_sort;
+        if (!ties) {
+            std::vector<KeyPos> sorted(kp);
+            sample_sort(sorted, nt);
+            ties = has_ties(sorted);
+            if (!ties) parallel_chunks(m, nt, [&](unsigned, uint64_t b, uint64_t e) { for (uint64_t i = b; i < e; i++) order[i] = sorted[i].pos; });
+        }
+        if (ties) {
+            std::iota(order.begin(), order.end(), 0u);
+            std::sort(order.begin(), order.end(), [&](unsigned int i, unsigned int j) { return kp[i].key < kp[j].key; });
+            tie_path = 1;
+        }
+    }
+}
+
 bool reduce_field_host(const GridDev& g, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
                        uint32_t* cell_map, uint64_t n_cells_grid, bool force_std_sort, ReduceStats& st, const char** err)
 {
@@ -164,15 +218,8 @@ bool reduce_field_host(const GridDev& g, double* nodes, uint64_t n_nodes, const 
     parallel_chunks(kept_cells * 32, nt, [&](unsigned, uint64_t b, uint64_t e) {
         for (uint64_t k = b; k < e; k++) __atomic_store_n(&used[cells[k]], (uint8_t)1, __ATOMIC_RELAXED);
     });
-    std::vector<uint32_t> perm(n_nodes);                         // perm[position] = original node id
-    std::iota(perm.begin(), perm.end(), 0u);
-    uint32_t last = (uint32_t)(n_nodes - 1);
-    for (int64_t i = (int64_t)n_nodes - 1; i >= 0; --i) {
-        if (used[i]) continue;                                   // position i still holds node i when the walk reaches it
-        std::swap(perm[i], perm[last]);
-        last--;                                                  // wraps to 0xffffffff when nothing survives: last + 1 == 0 below
-    }
-    const uint64_t m = (uint64_t)(uint32_t)(last + 1u);
+    std::vector<uint32_t> perm;                                  // perm[position] = original node id
+    const uint64_t m = reduce_swap_walk(used.data(), n_nodes, perm);
     st.nodes_out = m;
     st.ms_nodes = ms_since(t0); t0 = std::chrono::steady_clock::now();
 
@@ -181,36 +228,8 @@ bool reduce_field_host(const GridDev& g, double* nodes, uint64_t n_nodes, const 
     parallel_chunks(m, nt, [&](unsigned, uint64_t b, uint64_t e) {
         for (uint64_t i = b; i < e; i++) { kp[i].key = reduce_field_morton_key(g, perm[i]); kp[i].pos = (uint32_t)i; }
     });
-    std::vector<uint32_t> order(m);                              // sort_pattern
-    auto has_ties = [&](const std::vector<KeyPos>& sorted) {
-        std::atomic<int> dup{0};
-        parallel_chunks(m, nt, [&](unsigned, uint64_t b, uint64_t e) {
-            for (uint64_t i = std::max<uint64_t>(b, 1); i < e; i++) if (sorted[i].key == sorted[i - 1].key) { dup.store(1); break; }
-        });
-        return dup.load() != 0;
-    };
-    if (replay_std_sort_matches() && !force_std_sort) {
-        // the reference's own sort on the reference's own input sequence, replayed on all threads (reduce_field.h): right with and
-        // without ties
-        replay_std_sort(kp.data(), m, nt);
-        st.tie_path = has_ties(kp) ? 1 : 0;
-        parallel_chunks(m, nt, [&](unsigned, uint64_t b, uint64_t e) { for (uint64_t i = b; i < e; i++) order[i] = kp[i].pos; });
-    } else {
-        // another standard library (or force_std_sort): any correct sort will do while the keys are distinct; with ties only the
-        // reference's very call reproduces its order
-        bool ties = force_std_sort;
-        if (!ties) {
-            std::vector<KeyPos> sorted(kp);
-            sample_sort(sorted, nt);
-            ties = has_ties(sorted);
-            if (!ties) parallel_chunks(m, nt, [&](unsigned, uint64_t b, uint64_t e) { for (uint64_t i = b; i < e; i++) order[i] = sorted[i].pos; });
-        }
-        if (ties) {
-            std::iota(order.begin(), order.end(), 0u);
-            std::sort(order.begin(), order.end(), [&](unsigned int i, unsigned int j) { return kp[i].key < kp[j].key; });
-            st.tie_path = 1;
-        }
-    }
+    std::vector<uint32_t> order;                                 // sort_pattern
+    reduce_order_survivors(kp, force_std_sort, order, st.tie_path);
     st.ms_sort = ms_since(t0); t0 = std::chrono::steady_clock::now();
 
     // ---- 4. write back: new id of an original node = rank of its position; coefficients in rank order (:1167-1173)

@@ -13,6 +13,7 @@
 // Host code: the reference's reduceField is host bookkeeping around the sampled fields; nothing here is a kernel's fallback.
 #pragma once
 #include <cstdint>
+#include <vector>
 #include "dg_device.cuh"
 
 namespace dgb {
@@ -34,6 +35,11 @@ struct KeyPos { uint64_t key; uint32_t pos; };
 void replay_std_sort(KeyPos* a, uint64_t n, unsigned n_threads);
 bool replay_std_sort_matches();
 uint64_t replay_std_sort_heap_fallbacks();      // number of depth-exhausted ranges so far (tests)
+
+// the two stages that stay on the host when the index passes run on the GPU (k4_reduce.cu / dg_reduce_field): the reference's
+// back-to-front swap compaction replayed on a permutation, and the (tie-order-preserving) sort of the survivors
+uint64_t reduce_swap_walk(const uint8_t* used, uint64_t n_nodes, std::vector<uint32_t>& perm);
+void reduce_order_survivors(std::vector<KeyPos>& kp, bool force_std_sort, std::vector<uint32_t>& order, int& tie_path);
 
 // zValue(indexToNodePosition(l), 4 * min(inv_cell_size)) for one node (exposed for tests)
 uint64_t reduce_field_morton_key(const GridDev& g, uint32_t l);
