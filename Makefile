@@ -11,7 +11,7 @@ CXXFLAGS := -std=c++17 -O3 -fPIC -ffp-contract=off -fvisibility=hidden
 SRC      := discregrid_b200/csrc
 OBJ      := build/obj
 LIB      := discregrid_b200/lib/libdiscregrid_b200.so
-CU       := k1_sdf k2_interp k3_density dg_api
+CU       := k1_sdf k2_interp k3_density k4_reduce dg_api
 HDRS     := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/discregrid_b200.h
 
 all: lib cpp oracle
@@ -59,7 +59,7 @@ $(CPPBIN)/libk23emu_knobs.so: $(K23EMU_DEP)
 	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DK3_FAST_DIV=0 -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K23EMU_SRC) -o $@ -lpthread
 # test library: the WHOLE product library with every kernel emulated and the CUDA runtime stubbed on host memory -- lets the Python-level
 # and tool-level `-m gpu` tests be rehearsed on the CPU (tests/test_gpu_rehearsal.py); never loaded by the product
-DGEMU_SRC := tests/emu/dgapi_emu.cpp tests/emu/k1_emu.cpp tests/emu/k2_emu.cpp tests/emu/k3_emu.cpp tests/emu/cudart_stub.cpp \
+DGEMU_SRC := tests/emu/dgapi_emu.cpp tests/emu/k1_emu.cpp tests/emu/k2_emu.cpp tests/emu/k3_emu.cpp tests/emu/k4_emu.cpp tests/emu/cudart_stub.cpp \
              $(SRC)/bvh_build.cpp $(SRC)/host_threads.cpp $(SRC)/reduce_field.cpp $(SRC)/obj_reader.cpp $(SRC)/sort_replay.cpp
 $(CPPBIN)/libdgemu.so: $(DGEMU_SRC) tests/emu/cuda_emu.h $(wildcard $(SRC)/*.cu) $(HDRS)
 	@mkdir -p $(CPPBIN)

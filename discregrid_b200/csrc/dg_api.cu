@@ -37,6 +37,7 @@
 #include "k1_sdf.h"
 #include "k2_interp.h"
 #include "k3_density.h"
+#include "k4_reduce.h"
 #include "reduce_field.h"
 #include "obj_reader.h"
 
@@ -1390,6 +1391,69 @@ int dg_density_map(const dg_field* f, double h, double rho0, int no_reduction, u
     return DG_OK;
 }
 
+// reduceField with its index passes on the GPU (k4_reduce.cu); the swap-walk compaction and the tie-order-preserving sort stay on the host
+static int reduce_field_gpu(const GridDev& g, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
+                            uint32_t* cell_map, uint64_t n_cells_grid, bool force_std_sort, ReduceStats& st)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&]() { const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); t0 = std::chrono::steady_clock::now(); return ms; };
+    const uint64_t tile = k4_tile(), n_tiles = (n_cells_in + tile - 1) / tile;
+    DevBuf<double> d_nodes, d_nodes_out;
+    DevBuf<unsigned char> d_keep, d_cell_keep, d_used;
+    DevBuf<unsigned> d_cells, d_cells_out, d_cell_map, d_tile, d_bad, d_perm, d_order, d_new_id;
+    DevBuf<unsigned long long> d_key;
+    // ---- 1. surviving cells, cell map, compacted rows (:1076-1098)
+    DG_CUDA(d_nodes.alloc(n_nodes)); DG_CUDA(d_keep.alloc(n_nodes)); DG_CUDA(d_cells.alloc(32 * n_cells_in)); DG_CUDA(d_cells_out.alloc(32 * n_cells_in));
+    DG_CUDA(d_cell_keep.alloc(n_cells_in)); DG_CUDA(d_cell_map.alloc(n_cells_in)); DG_CUDA(d_tile.alloc(n_tiles)); DG_CUDA(d_bad.alloc(1)); DG_CUDA(d_used.alloc(n_nodes));
+    DG_CUDA(cudaMemcpyAsync(d_keep.p, keep_node, n_nodes, cudaMemcpyHostToDevice, nullptr));
+    DG_CUDA(cudaMemcpyAsync(d_cells.p, cells, 32 * n_cells_in * sizeof(unsigned), cudaMemcpyHostToDevice, nullptr));
+    DG_CUDA(cudaMemcpyAsync(d_nodes.p, nodes, n_nodes * sizeof(double), cudaMemcpyHostToDevice, nullptr));
+    DG_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(unsigned), nullptr));
+    DG_CUDA(cudaMemsetAsync(d_used.p, 0, n_nodes, nullptr));
+    DG_LAUNCH(k4_launch_cell_keep(d_cells.p, n_cells_in, d_keep.p, (unsigned)n_nodes, d_cell_keep.p, d_bad.p, nullptr));
+    DG_LAUNCH(k4_launch_tile_count(d_cell_keep.p, n_cells_in, d_tile.p, nullptr));
+    std::vector<unsigned> tile_cnt(n_tiles);
+    unsigned bad = 0;
+    if (n_tiles) DG_CUDA(cudaMemcpy(tile_cnt.data(), d_tile.p, n_tiles * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    DG_CUDA(cudaMemcpy(&bad, d_bad.p, sizeof bad, cudaMemcpyDeviceToHost));
+    if (bad) return fail(DG_ERR_INVALID, "dg_reduce_field: a cell refers to a node id >= n_nodes");
+    uint64_t kept_cells = 0;
+    for (uint64_t t = 0; t < n_tiles; t++) { const unsigned c = tile_cnt[t]; tile_cnt[t] = (unsigned)kept_cells; kept_cells += c; }     // exclusive scan of ~n/1024 counts
+    if (n_tiles) DG_CUDA(cudaMemcpyAsync(d_tile.p, tile_cnt.data(), n_tiles * sizeof(unsigned), cudaMemcpyHostToDevice, nullptr));
+    DG_LAUNCH(k4_launch_cell_compact(d_cells.p, n_cells_in, d_cell_keep.p, d_tile.p, d_cells_out.p, d_cell_map.p, nullptr));
+    DG_LAUNCH(k4_launch_mark_used(d_cells_out.p, 32 * kept_cells, d_used.p, nullptr));
+    if (n_cells_in) DG_CUDA(cudaMemcpyAsync(cell_map, d_cell_map.p, n_cells_in * sizeof(unsigned), cudaMemcpyDeviceToHost, nullptr));
+    std::vector<uint8_t> used(n_nodes);
+    DG_CUDA(cudaMemcpy(used.data(), d_used.p, n_nodes, cudaMemcpyDeviceToHost));
+    for (uint64_t i = n_cells_in; i < n_cells_grid; i++) cell_map[i] = (uint32_t)i;                     // resize + iota (:1076-1078) for cells the field never had
+    st.cells_out = kept_cells;
+    st.ms_cells = lap();
+    // ---- 2. surviving nodes: the reference's swap walk on a permutation (host, serial by nature)
+    std::vector<uint32_t> perm;
+    const uint64_t m = reduce_swap_walk(used.data(), n_nodes, perm);
+    st.nodes_out = m;
+    st.ms_nodes = lap();
+    // ---- 3. Z-curve keys on the GPU, the order among them on the host (std::sort's tie order)
+    DG_CUDA(d_perm.alloc(m)); DG_CUDA(d_key.alloc(m)); DG_CUDA(d_order.alloc(m)); DG_CUDA(d_new_id.alloc(n_nodes)); DG_CUDA(d_nodes_out.alloc(m));
+    if (m) DG_CUDA(cudaMemcpyAsync(d_perm.p, perm.data(), m * sizeof(unsigned), cudaMemcpyHostToDevice, nullptr));
+    DG_LAUNCH(k4_launch_morton_keys(g, d_perm.p, m, d_key.p, nullptr));
+    std::vector<unsigned long long> key(m);
+    if (m) DG_CUDA(cudaMemcpy(key.data(), d_key.p, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    std::vector<KeyPos> kp(m);
+    parallel_for(m, [&](uint64_t b0, uint64_t e0) { for (uint64_t i = b0; i < e0; i++) { kp[i].key = key[i]; kp[i].pos = (uint32_t)i; } });
+    std::vector<uint32_t> order;
+    reduce_order_survivors(kp, force_std_sort, order, st.tie_path);
+    st.ms_sort = lap();
+    // ---- 4. new ids, renumbered rows, gathered coefficients (:1158-1173)
+    if (m) DG_CUDA(cudaMemcpyAsync(d_order.p, order.data(), m * sizeof(unsigned), cudaMemcpyHostToDevice, nullptr));
+    DG_LAUNCH(k4_launch_renumber(d_perm.p, d_order.p, m, d_nodes.p, d_new_id.p, d_nodes_out.p, d_cells_out.p, 32 * kept_cells, nullptr));
+    if (kept_cells) DG_CUDA(cudaMemcpyAsync(cells, d_cells_out.p, 32 * kept_cells * sizeof(unsigned), cudaMemcpyDeviceToHost, nullptr));
+    if (m) DG_CUDA(cudaMemcpyAsync(nodes, d_nodes_out.p, m * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    DG_CUDA(cudaDeviceSynchronize());
+    st.ms_write = lap();
+    return DG_OK;
+}
+
 int dg_reduce_field(const dg_grid_desc* grid, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
                     uint32_t* cell_map, uint32_t flags, uint64_t* n_nodes_out, uint64_t* n_cells_out, double* timings_ms)
 {
@@ -1402,9 +1466,17 @@ int dg_reduce_field(const dg_grid_desc* grid, double* nodes, uint64_t n_nodes, c
     if (n_nodes != n_grid_nodes)          // node ids must be the grid's own numbering: their positions feed the Z-curve key (:1113)
         return fail(DG_ERR_INVALID, "dg_reduce_field: the field has %llu nodes, the grid %llu (already reduced?)", (unsigned long long)n_nodes,
                     (unsigned long long)n_grid_nodes);
+    if (n_cells_in > n_grid_cells) return fail(DG_ERR_INVALID, "dg_reduce_field: more cells than the grid has");
     ReduceStats st; const char* err = "";
-    if (!reduce_field_host(g, nodes, n_nodes, keep_node, cells, n_cells_in, cell_map, n_grid_cells, (flags & DG_REDUCE_REFERENCE_SORT) != 0, st, &err))
-        return fail(DG_ERR_INVALID, "dg_reduce_field: %s", err);
+    const char* env = std::getenv("DG_REDUCE_FIELD_HOST");
+    const bool host_passes = (flags & DG_REDUCE_HOST_PASSES) != 0 || (env && env[0] == '1');
+    if (host_passes) {
+        if (!reduce_field_host(g, nodes, n_nodes, keep_node, cells, n_cells_in, cell_map, n_grid_cells, (flags & DG_REDUCE_REFERENCE_SORT) != 0, st, &err))
+            return fail(DG_ERR_INVALID, "dg_reduce_field: %s", err);
+    } else {
+        if (int rc = require_device()) return rc;
+        if (int rc = reduce_field_gpu(g, nodes, n_nodes, keep_node, cells, n_cells_in, cell_map, n_grid_cells, (flags & DG_REDUCE_REFERENCE_SORT) != 0, st)) return rc;
+    }
     *n_nodes_out = st.nodes_out; *n_cells_out = st.cells_out;
     if (timings_ms) { timings_ms[0] = st.ms_cells; timings_ms[1] = st.ms_nodes; timings_ms[2] = st.ms_sort; timings_ms[3] = st.ms_write; timings_ms[4] = (double)st.tie_path; }
     return DG_OK;

@@ -234,11 +234,16 @@ DG_API int dg_density_map_device(const dg_field* sdf, double h, double rho0, int
  * been evaluated: keep_node[l] != 0 <=> pred(x_l, c_l) && c_l != DBL_MAX (:1069-1074).  Rewrites IN PLACE, exactly as the
  * reference leaves its members: cells (n_cells_in x 32; first *n_cells_out rows = surviving cells, renumbered), nodes (first
  * *n_nodes_out coefficients = surviving nodes in the reference's Z-curve order) and cell_map (resolution product entries; 0xffffffff
- * for removed cells).  Host bookkeeping like the reference's (multithreaded, no per-node std::set); needs no GPU.
+ * for removed cells).
  * flags: DG_REDUCE_REFERENCE_SORT makes the plain single-threaded std::sort call instead of its multithreaded replay (same result).
  * timings_ms: NULL or 5 doubles (ms spent on cells, node compaction, sort, write-back; 1.0 if surviving nodes shared Morton keys,
  * i.e. the node order depended on how std::sort leaves equal keys). */
 #define DG_REDUCE_REFERENCE_SORT 1u
+/* DG_REDUCE_HOST_PASSES (or the environment variable DG_REDUCE_FIELD_HOST=1): every pass on the host threads.  Default: the index passes run
+ * on the GPU (k4_reduce.cu: cell flags, cell map + row compaction, node marks, Z-curve keys, renumbering and coefficient gather); the host
+ * keeps the reference's serial swap-walk compaction and the sort whose order among equal keys is std::sort's.  Without a CUDA device the
+ * default fails with DG_ERR_NO_DEVICE -- nothing switches silently. */
+#define DG_REDUCE_HOST_PASSES 2u
 DG_API int dg_reduce_field(const dg_grid_desc* grid, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells,
                     uint64_t n_cells_in, uint32_t* cell_map, uint32_t flags, uint64_t* n_nodes_out, uint64_t* n_cells_out,
                     double* timings_ms);

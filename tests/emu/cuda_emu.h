@@ -151,6 +151,7 @@ inline void launch(unsigned grid, unsigned block, size_t /*smem*/, const std::fu
 inline unsigned __ballot_sync(unsigned, int pred) { dg_emu::collective_wait(pred ? 1u : 0u); return dg_emu::g_warp->result_ballot; }
 inline unsigned __reduce_add_sync(unsigned, unsigned v) { dg_emu::collective_wait(v); return dg_emu::g_warp->result_sum; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, 8); return r; }

@@ -14,8 +14,12 @@ DBL_MAX = np.finfo(np.float64).max
 H, RHO0 = 0.15, 1000.0                                   # make_golden.py: GenerateDensityMap -s 0.15 -r 1000
 
 
+HOST = 2                                                 # DG_REDUCE_HOST_PASSES: this file runs without a GPU (the GPU passes: tests/test_gpu_reduce_field.py)
+
+
 def reduce_field(dg, g, nodes, keep, cells, flags=0):
     from discregrid_b200 import _capi as capi
+    flags |= HOST
     desc = dg.grid_desc(g["mn"], g["mx"], g["res"], g["cell"], g["inv"])
     nodes = np.ascontiguousarray(nodes, np.float64).copy(); cells = np.ascontiguousarray(cells, np.uint32).copy()
     keep = np.ascontiguousarray(keep, np.uint8)
@@ -100,7 +104,7 @@ def test_facade_reduce_field_glue_without_gpu(dg, tmp_path):
         pytest.skip("build/bin/reduce_facade_check not built (make cpp)")
     src_path = os.path.join(GOLDEN, "ref_sphere_noreduction.cdm")
     out = str(tmp_path / "red.cdm")
-    r = subprocess.run([exe, src_path, str(H), str(RHO0), out], capture_output=True, text=True)
+    r = subprocess.run([exe, src_path, str(H), str(RHO0), out], capture_output=True, text=True, env=dict(os.environ, DG_REDUCE_FIELD_HOST="1"))
     assert r.returncode == 0, r.stdout + r.stderr
     got, src, red = read_cdf(out), read_cdf(src_path), read_cdf(os.path.join(GOLDEN, "ref_sphere_reduced.cdm"))
     assert bits_equal(got["nodes"][0], red["nodes"][0]) and np.array_equal(got["cells"][0], red["cells"][0]) and np.array_equal(got["cmap"][0], red["cmap"][0])

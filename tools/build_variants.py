@@ -11,7 +11,7 @@ procs = []
 for spec in sys.argv[1:]:
     name, _, defs = spec.partition(":")
     defs = [d for d in defs.split(",") if d]
-    srcs = [os.path.join(SRC, f) for f in ("k1_sdf.cu", "k2_interp.cu", "k3_density.cu", "dg_api.cu", "bvh_build.cpp", "host_threads.cpp", "reduce_field.cpp", "obj_reader.cpp", "sort_replay.cpp")]
+    srcs = [os.path.join(SRC, f) for f in ("k1_sdf.cu", "k2_interp.cu", "k3_density.cu", "k4_reduce.cu", "dg_api.cu", "bvh_build.cpp", "host_threads.cpp", "reduce_field.cpp", "obj_reader.cpp", "sort_replay.cpp")]
     cmd = NV + defs + ["-shared", "-o", os.path.join(out_dir, name + ".so")] + srcs
     procs.append((name, subprocess.Popen(cmd)))
 for name, p in procs:
