@@ -866,20 +866,32 @@ def main():
 # ncu-derived constants of the shipped kernels AT THE BENCH CONFIGURATIONS (profiles/: `ncu --set full --clock-control none`; numbers taken
 # under ncu are never bench values -- these are per-launch DRAM bytes and pipe statistics only)
 NCU = {
-    "k1_mesh": "torus", "k1_dram_bytes_per_launch": None, "k1_source": "profiles/ (capture pending for this build)",
-    "k1_summary": None,
-    "k1_flops_per_node_fallback": 9000.0,
-    "k2_dram_bytes_per_launch": None, "k2_source": "profiles/ (capture pending for this build)",
+    "k1_mesh": "bunny", "k1_dram_bytes_per_launch": 39.58e6 + 79.56e6,
+    "k1_source": "profiles/r2a_ncu_summary.csv: ncu --set full of sdf_sample_nodes_kernel at this configuration (bunny.obj, 128^3): dram read 39.6 MB (mesh records once) "
+                 "+ write 79.6 MB (8 B/node; the rest of the 119 MB drains after the launch)",
+    "k1_summary": {"capture": "profiles/r2a_ncu_summary.csv (bunny.obj 128^3, 76.9 ms under ncu)", "lanes_active_per_instruction": 15.44, "issue_active_pct": 67.5,
+                   "fp64_pipe_pct": 15.7, "alu_pipe_pct": 45.7, "l1_lsu_wavefronts_pct_of_peak": 67.2, "warps_active_pct": 43.6, "l1_hit_pct": 74.3, "l2_hit_pct": 98.1,
+                   "top_stalls": "long scoreboard 31 %, fixed-latency wait 25 %, branch resolving 10 %",
+                   "reading": "bound jointly by instruction issue (67 %) and L1 data-pipe wavefronts (67 %) at 15.4 of 32 lanes; neither HBM (0.02 %) nor the fp64 pipe (16 %)"},
+    "k1_flops_per_node_fallback": 15800.0,
+    "k2_dram_bytes_per_launch": 2757.4e6 + 312.9e6,
+    "k2_source": "profiles/r2a_ncu_summary.csv: ncu --set full of interpolate_kernel<true>, 10 M queries on the 256^3 field: dram read 2.757 GB + write 0.313 GB = 3.07 GB "
+                 "against 3.12 GB algorithmic (no re-reads); fp64 pipe 59 %, 32 of 32 lanes",
 }
 
 
 def k3_roofline(active_nodes, ms, fp64_peak):
-    """K3 against the measured fp64 issue rate: 4096 value-only interpolations (~155 unfused flops) + the kernel/gamma
-    arithmetic (~15) per node in the quadrature branch; skipped W == 0 points still count as algorithmic work of the reference."""
-    flops = 4096.0 * (155.0 + 15.0) * active_nodes
+    """K3 against the measured fp64 issue rate.  Work counted per node in the quadrature branch: one value-only interpolation (~155 unfused
+    flops) + the kernel/gamma arithmetic (~15) for every Gauss point INSIDE the kernel support |xi| <= h -- the points outside
+    contribute exactly +0 and the kernel skips them (the reference evaluates all 4096)."""
+    x, _w = np.polynomial.legendre.leggauss(16)
+    inside = int((x[:, None, None] ** 2 + x[None, :, None] ** 2 + x[None, None, :] ** 2 <= 1.0).sum())
+    flops = float(inside) * (155.0 + 15.0) * active_nodes
     t = flops / (ms * 1e-3) / 1e12
     return {"bound": "fp64", "achieved": t, "peak": fp64_peak, "unit": "TFLOP/s", "frac": t / fp64_peak if fp64_peak else None,
-            "algorithmic_flops_per_active_node": 4096 * 170, "peak_source": "dg_fp64_rate_probe (DMUL+DADD, no FMA), this run"}
+            "algorithmic_flops_per_active_node": inside * 170, "gauss_points_inside_support": inside, "gauss_points": 4096,
+            "peak_source": "dg_fp64_rate_probe (DMUL+DADD, no FMA), this run",
+            "ncu": "profiles/r2a_ncu_summary.csv (128^3 bunny field, before K3_FAST_DIV): fp64 pipe 29.5 %, issue active 26.6 %, 26.8 of 32 lanes, long-scoreboard bound"}
 
 
 def strided_parity(mesh, mn, mx, res, d_nodes, n_check):
