@@ -283,6 +283,51 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
     return true;
 }
 
+void pack_node_records(const HostBvh& h, int stride, bool qbox, float* out)
+{
+    const uint64_t nT = h.n_triangles;
+    parallel_for(nT, [&](uint64_t m0, uint64_t m1) {
+        for (uint64_t m = m0; m < m1; m++) {
+            float* rec = out + m * (uint64_t)stride * 4;
+            std::memset(rec, 0, (size_t)stride * 16);
+            std::memcpy(rec, &h.spheres_f[m], sizeof(SpherePairF));
+            if (!qbox) { std::memcpy(rec + 8, &h.boxes_f[m], sizeof(BoxPairF)); continue; }
+            const SpherePairF& sp = h.spheres_f[m];
+            const BoxPairF& bx = h.boxes_f[m];
+            uint8_t code[12]; uint32_t flags = 0;
+            for (int child = 0; child < 2; child++) {
+                const float* c = child ? sp.rc : sp.lc;
+                const float r = child ? sp.rr : sp.lr;
+                const float* lo = child ? bx.r_lo : bx.l_lo;
+                const float* hi = child ? bx.r_hi : bx.l_hi;
+                const float step = r * K1_QBOX_STEP;
+                bool ok = (m != 0);
+                for (int d = 0; d < 3 && ok; d++) {
+                    const float t = (c[d] - r) - step;
+                    auto dec = [&](int q) { return std::fmaf((float)q, step, t); };
+                    // lower face: the largest code that does not exceed lo
+                    int q = (step > 0.f) ? (int)std::floor(((double)lo[d] - (double)t) / (double)step) : 0;
+                    q = std::min(255, std::max(0, q));
+                    while (q < 255 && dec(q + 1) <= lo[d]) q++;
+                    while (q >= 0 && !(dec(q) <= lo[d])) q--;
+                    if (q < 0) { ok = false; break; }
+                    code[6 * child + d] = (uint8_t)q;
+                    // upper face: the smallest code that is not below hi
+                    q = (step > 0.f) ? (int)std::ceil(((double)hi[d] - (double)t) / (double)step) : 255;
+                    q = std::min(255, std::max(0, q));
+                    while (q > 0 && dec(q - 1) >= hi[d]) q--;
+                    while (q <= 255 && !(dec(q) >= hi[d])) q++;
+                    if (q > 255) { ok = false; break; }
+                    code[6 * child + 3 + d] = (uint8_t)q;
+                }
+                if (!ok) { flags |= 1u << child; for (int k = 0; k < 6; k++) code[6 * child + k] = (k < 3) ? 0 : 255; }
+            }
+            std::memcpy(rec + 8, code, 12);
+            std::memcpy(rec + 11, &flags, 4);
+        }
+    });
+}
+
 namespace {
 int export_rec(const HostBvh& bvh, int b, int e, int& next, double* spheres, int32_t* kids)
 {

@@ -132,6 +132,17 @@ struct HostBvh {
     RawVec<double> pn_tri, pn_edge, pn_vert;
 };
 
+// The fp32 record of every internal node as the traversal kernels read it (index = split position m, `stride` float4s each):
+//   qbox == false: [sphere pair, 32 B][box pair, 48 B] (+ padding)                                    -- 5 x 16-byte loads per node step
+//   qbox == true : [sphere pair, 32 B][both child boxes as 8-bit offsets in their sphere's frame, 12 B][flags, 4 B]   -- 3 loads
+// Quantised boxes (K1_QBOX): value = fmaf(float(q), s, t) with s = r * K1_QBOX_STEP, t = (c - r) - s per child and axis -- the very fp32
+// operations the kernel decodes with -- and q chosen on the host as the largest (lower faces) / smallest (upper faces) code whose
+// DECODED value still encloses the outward-rounded fp32 box; a child whose box cannot be enclosed (degenerate sphere) is flagged and the
+// kernel then never skips it.  Boxes only ever SKIP subtrees that provably cannot change the result, so a looser box changes nothing
+// but the amount of work.
+#define K1_QBOX_STEP 0.007905138f            /* ~ 2 / 253: codes 1 .. 254 span the sphere's diameter, one code of margin either side */
+void pack_node_records(const HostBvh& h, int stride, bool qbox, float* out /* n_triangles * stride * 4 floats */);
+
 // Returns false (and leaves *err) on invalid input.
 bool build_host_bvh(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err,
                     bool with_leaf_shadow = false, bool with_recips = false);

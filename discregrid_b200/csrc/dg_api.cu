@@ -344,16 +344,10 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     DG_CUDA_M(cudaMemcpy(m->d_spheres.p, m->host.spheres.data(), nT * sizeof(SpherePair), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_leaves.p, m->host.leaves.data(), nT * sizeof(LeafRecord), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_normals.p, m->host.normals.data(), nT * sizeof(PseudoNormals), cudaMemcpyHostToDevice));
-    {   // interleave the fp32 sphere pair and box pair of every internal node into one record
-        static_assert(K1_NODEF_STRIDE * sizeof(float4) >= sizeof(SpherePairF) + sizeof(BoxPairF), "node record too small");
+    {   // the fp32 record of every internal node: sphere pair + child boxes (quantised when K1_QBOX), bvh_build.h
+        static_assert(K1_QBOX || K1_NODEF_STRIDE * sizeof(float4) >= sizeof(SpherePairF) + sizeof(BoxPairF), "node record too small");
         RawVec<float4> rec(nT * K1_NODEF_STRIDE);
-        parallel_for(nT, [&](uint64_t i0, uint64_t i1) {
-            for (uint64_t i = i0; i < i1; i++) {
-                std::memset(&rec[i * K1_NODEF_STRIDE], 0, K1_NODEF_STRIDE * sizeof(float4));
-                std::memcpy(&rec[i * K1_NODEF_STRIDE], &m->host.spheres_f[i], sizeof(SpherePairF));
-                std::memcpy(&rec[i * K1_NODEF_STRIDE + 2], &m->host.boxes_f[i], sizeof(BoxPairF));
-            }
-        });
+        pack_node_records(m->host, K1_NODEF_STRIDE, K1_QBOX != 0, reinterpret_cast<float*>(rec.data()));
         DG_CUDA_M(cudaMemcpy(m->d_nodes_f.p, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice));
     }
     m->dev.nodes_f = m->d_nodes_f.p;
@@ -669,8 +663,12 @@ struct HostTablesJob {
         n_tasks = nb_nodes + nb_cells + nb_map;
         prefault_left = (int)std::min<uint64_t>(nb_nodes, 0x7fffffff);
         t0 = std::chrono::steady_clock::now();
+        // a quarter of the usable CPUs, at most 24.  Measured (profiles/r2d_e2e_probe.txt, 1-GPU lease with a 16-CPU cgroup quota, 256^3):
+        // 2 workers -> the call ends 8 ms after the last kernel; 11 workers + 4 copy threads (= every CPU of the quota busy) -> 95 ms
+        // later, because the bandwidth controller then throttles the thread that drives the GPU pipeline along with the rest.
         const unsigned hw = host_threads();
-        n_workers = std::max(1u, std::min(hw > reserve_threads + 1 ? hw - reserve_threads - 1 : 1u, 24u));
+        (void)reserve_threads;
+        n_workers = std::max(1u, std::min(hw / 4u, 24u));
         try { for (unsigned k = 0; k < n_workers; k++) th.emplace_back([this]() { work(); }); } catch (...) { /* fewer workers: finish() does the rest */ }
     }
     void finish()
@@ -699,7 +697,7 @@ int dg_add_function_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign,
     if (int rc = check_handle_device(m->device, "dg_add_function_sdf")) return rc;
     const auto t0 = std::chrono::steady_clock::now();
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
-    const unsigned copy_threads = std::min(4u, std::max(1u, host_threads() / 4));
+    const unsigned copy_threads = 1;                   // the pages are pre-faulted by the workers: one thread copies a 32 MiB piece in ~3 ms
     HostTablesJob job;
     job.start(g, n_nodes, nodes_host, cells_host, cell_map_host, copy_threads);
     int rc;

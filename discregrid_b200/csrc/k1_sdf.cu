@@ -262,6 +262,49 @@ __device__ __forceinline__ float sqrt_approx(float x)
 #endif
 }
 
+#if K1_QBOX
+// byte K of w as a float, exactly (0x4b000000 | q is the float 2^23 + q)
+template <int K>
+__device__ __forceinline__ float qbyte(unsigned w)
+{
+#ifdef DG_EMU
+    return (float)((w >> (8 * K)) & 255u);
+#else
+    return __int_as_float((int)__byte_perm(w, 0x4b000000u, 0x7650u + K)) - 8388608.0f;
+#endif
+}
+// squared distance (rounded down) from the query to a child's quantised box: w0 = codes lo.x lo.y lo.z hi.x, w1 = hi.y hi.z (low bytes);
+// decoded with exactly the operations pack_node_records chose the codes with
+__device__ __forceinline__ float qbox_gap2(const float4 sph, unsigned w0, unsigned w1, float qx, float qy, float qz)
+{
+    const float step = __fmul_rn(sph.w, K1_QBOX_STEP);
+    const float tx = __fsub_rn(__fsub_rn(sph.x, sph.w), step), ty = __fsub_rn(__fsub_rn(sph.y, sph.w), step), tz = __fsub_rn(__fsub_rn(sph.z, sph.w), step);
+    const float lox = fmaf(qbyte<0>(w0), step, tx), loy = fmaf(qbyte<1>(w0), step, ty), loz = fmaf(qbyte<2>(w0), step, tz);
+    const float hix = fmaf(qbyte<3>(w0), step, tx), hiy = fmaf(qbyte<0>(w1), step, ty), hiz = fmaf(qbyte<1>(w1), step, tz);
+    const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
+    return __fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx)));
+}
+// the two children's squared box distances from the record's third quad (0 for a flagged child: never skipped)
+__device__ __forceinline__ void qbox_pair_gap2(const float4 l4, const float4 r4, const float4 pk, float qx, float qy, float qz, float& l2, float& r2)
+{
+    const unsigned px = __float_as_uint(pk.x), py = __float_as_uint(pk.y), pz = __float_as_uint(pk.z), fl = __float_as_uint(pk.w);
+#ifdef DG_EMU
+    const unsigned rw0 = (py >> 16) | (pz << 16);
+#else
+    const unsigned rw0 = __byte_perm(py, pz, 0x5432u);
+#endif
+    l2 = (fl & 1u) ? 0.f : qbox_gap2(l4, px, py, qx, qy, qz);
+    r2 = (fl & 2u) ? 0.f : qbox_gap2(r4, rw0, pz >> 16, qx, qy, qz);
+}
+// one child's (popped sibling)
+__device__ __forceinline__ float qbox_child_gap2(const float4 c4, const float4 pk, bool is_left, float qx, float qy, float qz)
+{
+    const unsigned px = __float_as_uint(pk.x), py = __float_as_uint(pk.y), pz = __float_as_uint(pk.z), fl = __float_as_uint(pk.w);
+    const unsigned w0 = is_left ? px : ((py >> 16) | (pz << 16)), w1 = is_left ? py : (pz >> 16);
+    return ((fl >> (is_left ? 0 : 1)) & 1u) ? 0.f : qbox_gap2(c4, w0, w1, qx, qy, qz);
+}
+#endif
+
 // LEAF FILTER (K1_LEAF_FILTER): certified fp32 LOWER bound of the distance from the query to a triangle.
 //   * distance to each of the three closed edges (clamped parameter => an actual point of the edge, so each value is an upper
 //     bound of that edge's true distance up to rounding; their minimum is the true distance whenever the closest point is on the
@@ -402,12 +445,17 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                             // the child's box sits in two of the record's three box quads (l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz): two
                             // 16-byte loads instead of six scalar ones (the six were 29 % of the kernel's L1 tag requests, profiles/r2a)
                             const bool is_left = (r >> 31) != 0u;
+#if K1_QBOX
+                            const float4* rq = M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE;
+                            if (qbox_child_gap2(__ldg(rq + (is_left ? 0 : 1)), __ldg(rq + 2), is_left, qx, qy, qz) > skip_sq) { DG_EMU_COUNT(7); continue; }
+#else
                             const float4* bq = M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE + (is_left ? 2 : 3);
                             const float4 u = __ldg(bq), v = __ldg(bq + 1);
                             const float lox = is_left ? u.x : u.z, loy = is_left ? u.y : u.w, loz = is_left ? u.z : v.x;
                             const float hix = is_left ? u.w : v.y, hiy = is_left ? v.x : v.z, hiz = is_left ? v.y : v.w;
                             const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
                             if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
+#endif
                         }
 #endif
                         b = rb; depth = rd; e = re;
@@ -439,7 +487,11 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     if (e - m == 1) prefetch_l1(M.leaves + m); else prefetch_l1(M.nodes_f + (size_t)((m + e) >> 1) * K1_NODEF_STRIDE);
 #endif
 #if K1_BOX_SKIP && K1_EARLY_BOX
+#if K1_QBOX
+                    const float4 b0 = __ldg(f4 + 2);                                           // both boxes, quantised (12 bytes) + flags
+#else
                     const float4 b0 = __ldg(f4 + 2), b1 = __ldg(f4 + 3), b2 = __ldg(f4 + 4);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
+#endif
 #endif
                     const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
                     const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
@@ -457,6 +509,13 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     defer = !(d_second_f - E >= best_hi);
 #if K1_BOX_SKIP
                     if (decided && go_first) {
+#if K1_QBOX
+#if !K1_EARLY_BOX
+                        const float4 b0 = __ldg(f4 + 2);
+#endif
+                        float l2, r2;
+                        qbox_pair_gap2(l4, r4, b0, qx, qy, qz, l2, r2);
+#else
 #if !K1_EARLY_BOX
                         const float4 b0 = __ldg(f4 + 2), b1 = __ldg(f4 + 3), b2 = __ldg(f4 + 4);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
 #endif
@@ -467,6 +526,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                         // squared box distances rounded DOWN (a smaller value only skips less)
                         const float l2 = __fmaf_rd(lgz, lgz, __fmaf_rd(lgy, lgy, __fmul_rd(lgx, lgx)));
                         const float r2 = __fmaf_rd(rgz, rgz, __fmaf_rd(rgy, rgy, __fmul_rd(rgx, rgx)));
+#endif
                         const bool hopeless_first = (left_first ? l2 : r2) > skip_sq;
                         const bool hopeless_second = (left_first ? r2 : l2) > skip_sq;
                         if (hopeless_second) defer = false;
@@ -634,7 +694,7 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
 // Slot state (SoA, per warp): meta (depth | sp | phase | entity, 4-byte stride: the home lanes' phase reads are conflict-free) | BE = {b, e} |
 // pos | Q = {qx, qy, qz, E} | B = {best_lo, best_hi, skip_sq, tiny_best} | best | p | s, t | out
 // =====================================================================================================================================
-enum { WP_NODE = 0, WP_LEAF = 1, WP_POP = 2, WP_FIN = 3, WP_EMPTY = 4 };
+enum { WP_NODE = 0, WP_LEAF = 1, WP_POP = 2, WP_FIN = 3, WP_EMPTY = 4, WP_LEAFX = 5 };     // K1_LEAF_FILTER: LEAF = fp32 filter pending, LEAFX = exact test due
 constexpr int WS = K1_WAVE_SLOTS;
 static_assert(WS == 64, "two home slots per lane");
 
@@ -731,7 +791,12 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
         // one warp-wide sum carries the four live-phase counts (8 bits each; empty slots add nothing)
         const unsigned tally = __reduce_add_sync(0xffffffffu, ((ph0 < WP_EMPTY) ? (1u << (8 * ph0)) : 0u) + ((ph1 < WP_EMPTY) ? (1u << (8 * ph1)) : 0u));
         const int c_node = (int)(tally & 0xffu), c_leaf = (int)((tally >> 8) & 0xffu), c_pop = (int)((tally >> 16) & 0xffu), c_fin = (int)(tally >> 24);
-        const int c_live = c_node + c_leaf + c_pop + c_fin, c_empty = WS - c_live;
+#if K1_LEAF_FILTER
+        const int c_leafx = __popc(__ballot_sync(0xffffffffu, ph0 == WP_LEAFX)) + __popc(__ballot_sync(0xffffffffu, ph1 == WP_LEAFX));
+#else
+        const int c_leafx = 0;
+#endif
+        const int c_live = c_node + c_leaf + c_pop + c_fin + c_leafx, c_empty = WS - c_live;
         DG_EMU_COUNT(0);
         int chosen;
         if (more && c_empty >= K1_WAVE_REFILL) chosen = WP_EMPTY;                       // refill
@@ -742,6 +807,7 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
             chosen = WP_LEAF; int c_best = c_leaf;
             if (c_node > c_best) { chosen = WP_NODE; c_best = c_node; }
             if (c_pop > c_best) { chosen = WP_POP; c_best = c_pop; }
+            if (c_leafx > c_best) { chosen = WP_LEAFX; c_best = c_leafx; }
             if (c_fin > c_best || c_best == 0) { chosen = WP_FIN; c_best = c_fin; }
         }
         // compaction: slots in the chosen phase -> lanes 0..n-1
@@ -777,7 +843,7 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     W.px[slot] = px; W.py[slot] = py; W.pz[slot] = pz; W.out[slot] = oi;
                     W.Q[slot] = make_float4(qx, qy, qz, E);
                     W.best[slot] = DBL_MAX; W.s[slot] = 0.0; W.t[slot] = 0.0;
-                    W.B[slot] = make_float4(__double2float_rd(DBL_MAX), __double2float_ru(DBL_MAX), F_INF, 1.0e-6f * Mq);
+                    W.B[slot] = make_float4(__double2float_rd(DBL_MAX), __double2float_ru(DBL_MAX), F_INF, F_INF);       // best_lo, best_hi, skip_sq, skip_lin
                     W.BE[slot] = make_int2(0, n_tri); W.pos[slot] = -1;
                     W.meta[slot] = wave_meta(0, 0, (n_tri == 1) ? WP_LEAF : WP_NODE, 0);
                 }
@@ -806,7 +872,11 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                 {
                     const float4* f4 = M.nodes_f + (size_t)m * K1_NODEF_STRIDE;
                     const float4 l4 = __ldg(f4), r4 = __ldg(f4 + 1);
+#if K1_QBOX
+                    const float4 b0f = __ldg(f4 + 2);
+#else
                     const float4 b0f = __ldg(f4 + 2), b1f = __ldg(f4 + 3), b2f = __ldg(f4 + 4);
+#endif
                     const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
                     const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
                     const float dl = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) - l4.w;
@@ -819,10 +889,15 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     decided = order_sure && (go_first || skip_first);
                     defer = !(d_second_f - E >= best_hi);
                     if (decided && go_first) {
+#if K1_QBOX
+                        float l2, r2;
+                        qbox_pair_gap2(l4, r4, b0f, qx, qy, qz, l2, r2);
+#else
                         const float lgx = fmaxf(fmaxf(b0f.x - qx, qx - b0f.w), 0.f), lgy = fmaxf(fmaxf(b0f.y - qy, qy - b1f.x), 0.f), lgz = fmaxf(fmaxf(b0f.z - qz, qz - b1f.y), 0.f);
                         const float rgx = fmaxf(fmaxf(b1f.z - qx, qx - b2f.y), 0.f), rgy = fmaxf(fmaxf(b1f.w - qy, qy - b2f.z), 0.f), rgz = fmaxf(fmaxf(b2f.x - qz, qz - b2f.w), 0.f);
                         const float l2 = __fmaf_rd(lgz, lgz, __fmaf_rd(lgy, lgy, __fmul_rd(lgx, lgx)));
                         const float r2 = __fmaf_rd(rgz, rgz, __fmaf_rd(rgy, rgy, __fmul_rd(rgx, rgx)));
+#endif
                         const bool hopeless_first = (left_first ? l2 : r2) > skip_sq, hopeless_second = (left_first ? r2 : l2) > skip_sq;
                         if (hopeless_second) defer = false;
                         if (hopeless_first) {
@@ -857,7 +932,17 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     if (left_first) b = m; else e = m;
                     phase = (e - b == 1) ? WP_LEAF : WP_NODE;
                 } else phase = WP_POP;
+#if K1_LEAF_FILTER
             } else if (chosen == WP_LEAF) {
+                // ---- leaf, fp32 filter: a certified lower bound of the point-triangle distance above best + slack means the reference's
+                // test would fail (nothing changes): straight to POP.  Everything else takes the exact test in the LEAFX phase.
+                const float4 q = W.Q[slot];
+                const float lb = leaf_lower_bound(M.leaves_f + b, q.x, q.y, q.z, q.w);
+                phase = (lb > W.B[slot].w) ? WP_POP : WP_LEAFX;
+            } else if (chosen == WP_LEAFX) {
+#else
+            } else if (chosen == WP_LEAF) {
+#endif
                 // ---- leaf (:517-534)
                 DG_EMU_COUNT(3);
                 const double px = W.px[slot], py = W.py[slot], pz = W.pz[slot], best = W.best[slot];
@@ -872,12 +957,13 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     DG_EMU_COUNT(4);
                     const double nb = sqrt(d2);
                     const float4 q = W.Q[slot];
-                    const float tiny_best = W.B[slot].w, E2 = q.w + q.w;
+                    const float E2 = q.w + q.w;
+                    const float tiny_best = 1.0e-6f * fmaxf(fmaxf(M.half_extent, fabsf(q.x)), fmaxf(fabsf(q.y), fabsf(q.z)));
                     const float best_lo = __double2float_rd(nb), best_hi = __double2float_ru(nb);
                     const float th = __fadd_ru(best_hi, E2);
-                    const float skip_sq = (K1_BOX_SKIP && best_lo >= tiny_best) ? __fmul_ru(th, th) : F_INF;
+                    const bool ok = best_lo >= tiny_best;                   // nothing is skipped for queries practically on the surface
                     W.best[slot] = nb; W.s[slot] = s; W.t[slot] = t;
-                    W.B[slot] = make_float4(best_lo, best_hi, skip_sq, tiny_best);
+                    W.B[slot] = make_float4(best_lo, best_hi, (K1_BOX_SKIP && ok) ? __fmul_ru(th, th) : F_INF, ok ? th : F_INF);
                     W.pos[slot] = b; ent = en;
                 }
                 phase = WP_POP;
@@ -909,12 +995,16 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     }
                     if (visit) {
 #if K1_BOX_SKIP
+#if K1_QBOX
+                        if (qbox_child_gap2(c4, __ldg(f4 + 2), is_left, qx, qy, qz) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
+#else
                         const float4* bq = f4 + (is_left ? 2 : 3);            // the child's box: two of the record's three box quads
                         const float4 u = __ldg(bq), v = __ldg(bq + 1);
                         const float lox = is_left ? u.x : u.z, loy = is_left ? u.y : u.w, loz = is_left ? u.z : v.x;
                         const float hix = is_left ? u.w : v.y, hiy = is_left ? v.x : v.z, hiz = is_left ? v.y : v.w;
                         const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
                         if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
+#endif
 #endif
                         b = rb; depth = rd; e = re;
                         phase = (e - b == 1) ? WP_LEAF : WP_NODE;

@@ -59,8 +59,18 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 #ifndef K1_PREFETCH
 #define K1_PREFETCH 0            // prefetch.global.L1 of both children's records during a node step
 #endif
+// K1_QBOX 1: the child boxes of a node record are stored as 8-bit offsets in their sphere's frame (bvh_build.h: pack_node_records), the
+// record shrinks from 80 to 48 bytes: 3 instead of 5 16-byte loads per node step, 1 instead of 2 per popped sibling -- the kernels are
+// bound by L1 data-pipe wavefronts (profiles/r2a, r2b), not by arithmetic.  Looser boxes only skip slightly less; results are identical.
+#ifndef K1_QBOX
+#define K1_QBOX 0
+#endif
 #ifndef K1_NODEF_STRIDE
+#if K1_QBOX
+#define K1_NODEF_STRIDE 3         // float4s per fp32 node record: sphere pair (2) + quantised boxes and flags (1)
+#else
 #define K1_NODEF_STRIDE 5         // float4s per fp32 node record: 5 = packed 80 B, 6 = padded to 96 B
+#endif
 #endif
 #ifndef K1_EARLY_BOX
 #define K1_EARLY_BOX 1           // issue the box loads together with the sphere loads (latency) instead of after the sphere decision

@@ -165,6 +165,9 @@ inline float dg_emu_round_dn(double v) { float f = (float)v; return ((double)f >
 inline float dg_emu_round_up(double v) { float f = (float)v; return ((double)f < v) ? std::nextafterf(f, INFINITY) : f; }
 inline float __double2float_rd(double v) { return dg_emu_round_dn(v); }
 inline float __double2float_ru(double v) { return dg_emu_round_up(v); }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline float __fmul_rd(float a, float b) { return dg_emu_round_dn((double)a * (double)b); }      // the product of two floats is exact in a double
 inline float __fmul_ru(float a, float b) { return dg_emu_round_up((double)a * (double)b); }
 inline float __fadd_ru(float a, float b) { return dg_emu_round_up((double)a + (double)b); }      // exact unless the exponents differ by > 29

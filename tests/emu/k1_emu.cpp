@@ -39,10 +39,7 @@ void* emu_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t 
     if (!build_host_bvh(V, nV, F, nT, m->host, &err, K1_LEAF_FILTER != 0, K1_FAST_DIV != 0)) { std::fprintf(stderr, "emu_mesh_create: %s\n", err); delete m; return nullptr; }
     // the interleaved fp32 node record, as dg_mesh_create lays it out
     m->nodes_f.assign((size_t)nT * K1_NODEF_STRIDE, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (uint64_t i = 0; i < nT; i++) {
-        std::memcpy(&m->nodes_f[i * K1_NODEF_STRIDE], &m->host.spheres_f[i], sizeof(SpherePairF));
-        std::memcpy(&m->nodes_f[i * K1_NODEF_STRIDE + 2], &m->host.boxes_f[i], sizeof(BoxPairF));
-    }
+    pack_node_records(m->host, K1_NODEF_STRIDE, K1_QBOX != 0, reinterpret_cast<float*>(m->nodes_f.data()));
     DeviceBvh& d = m->dev;
     d.spheres = m->host.spheres.data(); d.leaves = m->host.leaves.data(); d.normals = m->host.normals.data();
     d.leaves_f = m->host.leaves_f.empty() ? nullptr : m->host.leaves_f.data();
