@@ -114,7 +114,10 @@ __device__ __forceinline__ double interp_value(const FieldDev& f, double x, doub
     return missing ? DBL_MAX : phi;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef K3_MIN_BLOCKS
+#define K3_MIN_BLOCKS 1            // blocks of 128 threads per SM the register allocation must allow (1 = compiler's choice, 104 registers)
+#endif
+__global__ void __launch_bounds__(128, K3_MIN_BLOCKS)
 density_map_kernel(FieldDev f, QuadParams qp, const double* __restrict__ Wtab, int no_reduction, unsigned l_begin,
                    unsigned long long count, double* __restrict__ out)
 {
