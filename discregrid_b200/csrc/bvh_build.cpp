@@ -2,7 +2,6 @@
 // reference's x86-64 build (no FMA), because these values feed bit-exact device comparisons.
 #include "bvh_build.h"
 #include "sort_replay.h"
-#include "fast_div.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -106,7 +105,7 @@ struct Builder {
 
 }  // namespace
 
-bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err, bool with_leaf_shadow, bool with_recips)
+bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err, bool with_leaf_shadow)
 {
     if (!Vd || !F || nT == 0 || nV == 0) { *err = "empty triangle list or vertex list"; return false; }
     if (nT >= (1ull << 25) || nV > (uint64_t)0x7fffffff) { *err = "mesh too large (< 2^25 triangles; int32 vertex indices as in the reference)"; return false; }
@@ -226,18 +225,6 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
         }
     });
 
-    if (with_recips) {
-        out.recips.resize(nT);
-        parallel_for(nT, [&](uint64_t p0, uint64_t p1) {
-            for (uint64_t pos = p0; pos < p1; pos++) {
-                const LeafRecord& L = out.leaves[pos];
-                LeafRecip& R = out.recips[pos];
-                R.inv_a00 = 1.0 / L.a00; R.inv_a11 = 1.0 / L.a11; R.inv_denom = 1.0 / L.denom;
-                R.regular = (in_fast_div_range(L.a00) && in_fast_div_range(L.a11) && in_fast_div_range(L.denom)) ? 1u : 0u;   // false for NaN / 0 / inf
-            }
-        });
-    }
-
     // ---- fp32 shadow of the sphere pairs (filter only), relative to the bounding-box centre
     {
         double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
@@ -283,7 +270,7 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
     return true;
 }
 
-void pack_node_records(const HostBvh& h, int stride, bool qbox, float* out)
+void pack_node_records(const HostBvh& h, int stride, float* out)
 {
     const uint64_t nT = h.n_triangles;
     parallel_for(nT, [&](uint64_t m0, uint64_t m1) {
@@ -291,39 +278,7 @@ void pack_node_records(const HostBvh& h, int stride, bool qbox, float* out)
             float* rec = out + m * (uint64_t)stride * 4;
             std::memset(rec, 0, (size_t)stride * 16);
             std::memcpy(rec, &h.spheres_f[m], sizeof(SpherePairF));
-            if (!qbox) { std::memcpy(rec + 8, &h.boxes_f[m], sizeof(BoxPairF)); continue; }
-            const SpherePairF& sp = h.spheres_f[m];
-            const BoxPairF& bx = h.boxes_f[m];
-            uint8_t code[12]; uint32_t flags = 0;
-            for (int child = 0; child < 2; child++) {
-                const float* c = child ? sp.rc : sp.lc;
-                const float r = child ? sp.rr : sp.lr;
-                const float* lo = child ? bx.r_lo : bx.l_lo;
-                const float* hi = child ? bx.r_hi : bx.l_hi;
-                const float step = r * K1_QBOX_STEP;
-                bool ok = (m != 0);
-                for (int d = 0; d < 3 && ok; d++) {
-                    const float t = (c[d] - r) - step;
-                    auto dec = [&](int q) { return std::fmaf((float)q, step, t); };
-                    // lower face: the largest code that does not exceed lo
-                    int q = (step > 0.f) ? (int)std::floor(((double)lo[d] - (double)t) / (double)step) : 0;
-                    q = std::min(255, std::max(0, q));
-                    while (q < 255 && dec(q + 1) <= lo[d]) q++;
-                    while (q >= 0 && !(dec(q) <= lo[d])) q--;
-                    if (q < 0) { ok = false; break; }
-                    code[6 * child + d] = (uint8_t)q;
-                    // upper face: the smallest code that is not below hi
-                    q = (step > 0.f) ? (int)std::ceil(((double)hi[d] - (double)t) / (double)step) : 255;
-                    q = std::min(255, std::max(0, q));
-                    while (q > 0 && dec(q - 1) >= hi[d]) q--;
-                    while (q <= 255 && !(dec(q) >= hi[d])) q++;
-                    if (q > 255) { ok = false; break; }
-                    code[6 * child + 3 + d] = (uint8_t)q;
-                }
-                if (!ok) { flags |= 1u << child; for (int k = 0; k < 6; k++) code[6 * child + k] = (k < 3) ? 0 : 255; }
-            }
-            std::memcpy(rec + 8, code, 12);
-            std::memcpy(rec + 11, &flags, 4);
+            std::memcpy(rec + 8, &h.boxes_f[m], sizeof(BoxPairF));
         }
     });
 }

@@ -102,12 +102,6 @@ struct alignas(64) LeafF {
 };
 static_assert(sizeof(LeafF) == 64, "LeafF must be 64 bytes");
 
-// Correctly rounded reciprocals of the three per-triangle divisors of the leaf test (a00, a11, a00 - 2 a01 + a11), for the
-// K1_FAST_DIV build of the kernel (fast_div.h).  regular = 1 when all three divisors are finite and inside [2^-300, 2^300];
-// otherwise the kernel takes the plain division for this triangle.
-struct alignas(32) LeafRecip { double inv_a00, inv_a11, inv_denom; uint64_t regular; };
-static_assert(sizeof(LeafRecip) == 32, "LeafRecip must be 32 bytes");
-
 struct PseudoNormals { double n[7][3]; };   // V0 V1 V2 E01 E12 E02 F
 static_assert(sizeof(PseudoNormals) == 168, "PseudoNormals must be 168 bytes");
 
@@ -122,7 +116,6 @@ struct HostBvh {
     RawVec<LeafRecord> leaves;              // [T]
     RawVec<LeafF> leaves_f;                 // [T]  fp32 shadow, relative to `center`
     RawVec<PseudoNormals> normals;          // [T]
-    RawVec<LeafRecip> recips;               // [T]  only when asked for (K1_FAST_DIV)
     std::vector<int32_t> order;             // leaf position -> triangle id
     int max_depth = 0;                      // number of levels (root = 1)
     int flags = 0;                          // bit0: edge with a single triangle; bit1: edge with > 2 triangles
@@ -133,19 +126,13 @@ struct HostBvh {
 };
 
 // The fp32 record of every internal node as the traversal kernels read it (index = split position m, `stride` float4s each):
-//   qbox == false: [sphere pair, 32 B][box pair, 48 B] (+ padding)                                    -- 5 x 16-byte loads per node step
-//   qbox == true : [sphere pair, 32 B][both child boxes as 8-bit offsets in their sphere's frame, 12 B][flags, 4 B]   -- 3 loads
-// Quantised boxes (K1_QBOX): value = fmaf(float(q), s, t) with s = r * K1_QBOX_STEP, t = (c - r) - s per child and axis -- the very fp32
-// operations the kernel decodes with -- and q chosen on the host as the largest (lower faces) / smallest (upper faces) code whose
-// DECODED value still encloses the outward-rounded fp32 box; a child whose box cannot be enclosed (degenerate sphere) is flagged and the
-// kernel then never skips it.  Boxes only ever SKIP subtrees that provably cannot change the result, so a looser box changes nothing
-// but the amount of work.
-#define K1_QBOX_STEP 0.007905138f            /* ~ 2 / 253: codes 1 .. 254 span the sphere's diameter, one code of margin either side */
-void pack_node_records(const HostBvh& h, int stride, bool qbox, float* out /* n_triangles * stride * 4 floats */);
+// [sphere pair, 32 B][box pair, 48 B] (+ padding).  (Round 2 measured a 48-byte variant with the boxes as 8-bit offsets in their sphere's
+// frame: 35 % fewer L1 wavefronts, 28 % more instructions to decode them, 90 vs 77 ms -- dropped; profiles/r2f_*.)
+void pack_node_records(const HostBvh& h, int stride, float* out /* n_triangles * stride * 4 floats */);
 
 // Returns false (and leaves *err) on invalid input.
 bool build_host_bvh(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT, HostBvh& out, const char** err,
-                    bool with_leaf_shadow = false, bool with_recips = false);
+                    bool with_leaf_shadow = false);
 
 // Re-expresses the implicit tree in the reference's explicit pre-order numbering (diagnostics only).
 void export_reference_tree(const HostBvh& bvh, double* spheres /*(2T-1) x 8*/, int32_t* kids /*(2T-1) x 2*/);

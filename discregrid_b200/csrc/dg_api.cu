@@ -161,9 +161,6 @@ struct dg_mesh {
     DevBuf<PseudoNormals> d_normals;
     DevBuf<float4> d_nodes_f;
     DevBuf<LeafF> d_leaves_f;
-#if K1_FAST_DIV
-    DevBuf<LeafRecip> d_recips;
-#endif
     DeviceBvh dev;
     int device = 0;
     uint64_t build_us = 0, upload_us = 0;
@@ -318,7 +315,7 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     const auto t0 = std::chrono::steady_clock::now();
     const char* why = "";
     try {
-        if (!build_host_bvh(V, nV, F, nT, m->host, &why, K1_LEAF_FILTER != 0, K1_FAST_DIV != 0)) { delete m; return fail(DG_ERR_INVALID, "dg_mesh_create: %s", why); }
+        if (!build_host_bvh(V, nV, F, nT, m->host, &why, K1_LEAF_FILTER != 0)) { delete m; return fail(DG_ERR_INVALID, "dg_mesh_create: %s", why); }
     } catch (const std::bad_alloc&) { delete m; return fail(DG_ERR_NOMEM, "dg_mesh_create: out of host memory"); }
     const auto t1 = std::chrono::steady_clock::now();
     m->build_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
@@ -335,19 +332,13 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     DG_CUDA_M(cudaMemcpy(m->d_leaves_f.p, m->host.leaves_f.data(), nT * sizeof(LeafF), cudaMemcpyHostToDevice));
     m->dev.leaves_f = m->d_leaves_f.p;
 #endif
-#if K1_FAST_DIV
-    DG_CUDA_M(m->d_recips.alloc(nT));
-    DG_CUDA_M(cudaMemcpy(m->d_recips.p, m->host.recips.data(), nT * sizeof(LeafRecip), cudaMemcpyHostToDevice));
-    m->dev.recips = m->d_recips.p;
-    RawVec<LeafRecip>().swap(m->host.recips);
-#endif
     DG_CUDA_M(cudaMemcpy(m->d_spheres.p, m->host.spheres.data(), nT * sizeof(SpherePair), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_leaves.p, m->host.leaves.data(), nT * sizeof(LeafRecord), cudaMemcpyHostToDevice));
     DG_CUDA_M(cudaMemcpy(m->d_normals.p, m->host.normals.data(), nT * sizeof(PseudoNormals), cudaMemcpyHostToDevice));
-    {   // the fp32 record of every internal node: sphere pair + child boxes (quantised when K1_QBOX), bvh_build.h
-        static_assert(K1_QBOX || K1_NODEF_STRIDE * sizeof(float4) >= sizeof(SpherePairF) + sizeof(BoxPairF), "node record too small");
+    {   // the fp32 record of every internal node: sphere pair + child boxes, bvh_build.h
+        static_assert(K1_NODEF_STRIDE * sizeof(float4) >= sizeof(SpherePairF) + sizeof(BoxPairF), "node record too small");
         RawVec<float4> rec(nT * K1_NODEF_STRIDE);
-        pack_node_records(m->host, K1_NODEF_STRIDE, K1_QBOX != 0, reinterpret_cast<float*>(rec.data()));
+        pack_node_records(m->host, K1_NODEF_STRIDE, reinterpret_cast<float*>(rec.data()));
         DG_CUDA_M(cudaMemcpy(m->d_nodes_f.p, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice));
     }
     m->dev.nodes_f = m->d_nodes_f.p;
@@ -850,11 +841,6 @@ int dg_mesh_group_create(const dg_mesh* mesh, int n_gpus, const int* devices, dg
         DG_CUDA(r->d_leaves_f.alloc(nT));
         DG_CUDA(cudaMemcpyPeer(r->d_leaves_f.p, r->device, mesh->d_leaves_f.p, mesh->device, nT * sizeof(LeafF)));
         r->dev.leaves_f = r->d_leaves_f.p;
-#endif
-#if K1_FAST_DIV
-        DG_CUDA(r->d_recips.alloc(nT));
-        DG_CUDA(cudaMemcpyPeer(r->d_recips.p, r->device, mesh->d_recips.p, mesh->device, nT * sizeof(LeafRecip)));
-        r->dev.recips = r->d_recips.p;
 #endif
         DG_CUDA(k1_configure(r->dev.stack_depth));
         DG_CUDA(cudaDeviceSynchronize());

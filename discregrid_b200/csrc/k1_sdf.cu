@@ -25,7 +25,6 @@
 #include "dg_device.cuh"
 #include "bvh_build.h"
 #include "k1_sdf.h"
-#include "fast_div.h"
 
 #include <cfloat>
 #include <mutex>
@@ -78,9 +77,6 @@ __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterp
 // division (E01: -b0/a00, E02: -b1/a11, E12: numer/denom), one quadratic form (E12 and F), selected per lane.
 // Every value a lane finally uses is produced by exactly the reference's operations in the reference's order.
 __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec,
-#if K1_FAST_DIV
-                                            const LeafRecip* __restrict__ recip,
-#endif
                                             double px, double py, double pz, double& s_out, double& t_out, int& ent_out)
 {
     const double* r = reinterpret_cast<const double*>(rec);
@@ -138,16 +134,7 @@ __device__ __forceinline__ double tri_dist2(const LeafRecord* __restrict__ rec,
     if (ent >= 3 && ent <= 5)
 #endif
     {
-#if K1_FAST_DIV
-        // den is one of three per-triangle constants: same IEEE quotient from its precomputed reciprocal (fast_div.h)
-        const double2 y01 = ldg2(reinterpret_cast<const double*>(recip)), y2r = ldg2(reinterpret_cast<const double*>(recip) + 2);
-        const double y = (ent == 3) ? y01.x : ((ent == 5) ? y01.y : ((ent == 4) ? y2r.x : 1.0));
-        q = div_by_known_reciprocal(num, den, y);
-        const bool needs = (ent >= 3 && ent <= 5);
-        if (needs && !(__double_as_longlong(y2r.y) != 0ll && in_fast_div_range(num))) q = num / den;   // irregular triangle or operand: rare, usually no lane
-#else
         q = num / den;
-#endif
     }
     DG_PIN_D(q);
     // ---- (s, t) of the nearest point
@@ -235,9 +222,6 @@ struct MeshDev {
     const float4* nodes_f;                 // [T][K1_NODEF_STRIDE]: sphere pair (2 float4) + box pair (3 float4)
     const LeafF* leaves_f;                 // [T] fp32 triangle shadows
     const LeafRecord* leaves;
-#if K1_FAST_DIV
-    const LeafRecip* recips;
-#endif
     double cx, cy, cz;
     float half_extent;
     int n_tri;
@@ -262,48 +246,6 @@ __device__ __forceinline__ float sqrt_approx(float x)
 #endif
 }
 
-#if K1_QBOX
-// byte K of w as a float, exactly (0x4b000000 | q is the float 2^23 + q)
-template <int K>
-__device__ __forceinline__ float qbyte(unsigned w)
-{
-#ifdef DG_EMU
-    return (float)((w >> (8 * K)) & 255u);
-#else
-    return __int_as_float((int)__byte_perm(w, 0x4b000000u, 0x7650u + K)) - 8388608.0f;
-#endif
-}
-// squared distance (rounded down) from the query to a child's quantised box: w0 = codes lo.x lo.y lo.z hi.x, w1 = hi.y hi.z (low bytes);
-// decoded with exactly the operations pack_node_records chose the codes with
-__device__ __forceinline__ float qbox_gap2(const float4 sph, unsigned w0, unsigned w1, float qx, float qy, float qz)
-{
-    const float step = __fmul_rn(sph.w, K1_QBOX_STEP);
-    const float tx = __fsub_rn(__fsub_rn(sph.x, sph.w), step), ty = __fsub_rn(__fsub_rn(sph.y, sph.w), step), tz = __fsub_rn(__fsub_rn(sph.z, sph.w), step);
-    const float lox = fmaf(qbyte<0>(w0), step, tx), loy = fmaf(qbyte<1>(w0), step, ty), loz = fmaf(qbyte<2>(w0), step, tz);
-    const float hix = fmaf(qbyte<3>(w0), step, tx), hiy = fmaf(qbyte<0>(w1), step, ty), hiz = fmaf(qbyte<1>(w1), step, tz);
-    const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
-    return __fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx)));
-}
-// the two children's squared box distances from the record's third quad (0 for a flagged child: never skipped)
-__device__ __forceinline__ void qbox_pair_gap2(const float4 l4, const float4 r4, const float4 pk, float qx, float qy, float qz, float& l2, float& r2)
-{
-    const unsigned px = __float_as_uint(pk.x), py = __float_as_uint(pk.y), pz = __float_as_uint(pk.z), fl = __float_as_uint(pk.w);
-#ifdef DG_EMU
-    const unsigned rw0 = (py >> 16) | (pz << 16);
-#else
-    const unsigned rw0 = __byte_perm(py, pz, 0x5432u);
-#endif
-    l2 = (fl & 1u) ? 0.f : qbox_gap2(l4, px, py, qx, qy, qz);
-    r2 = (fl & 2u) ? 0.f : qbox_gap2(r4, rw0, pz >> 16, qx, qy, qz);
-}
-// one child's (popped sibling)
-__device__ __forceinline__ float qbox_child_gap2(const float4 c4, const float4 pk, bool is_left, float qx, float qy, float qz)
-{
-    const unsigned px = __float_as_uint(pk.x), py = __float_as_uint(pk.y), pz = __float_as_uint(pk.z), fl = __float_as_uint(pk.w);
-    const unsigned w0 = is_left ? px : ((py >> 16) | (pz << 16)), w1 = is_left ? py : (pz >> 16);
-    return ((fl >> (is_left ? 0 : 1)) & 1u) ? 0.f : qbox_gap2(c4, w0, w1, qx, qy, qz);
-}
-#endif
 
 // LEAF FILTER (K1_LEAF_FILTER): certified fp32 LOWER bound of the distance from the query to a triangle.
 //   * distance to each of the three closed edges (clamped parameter => an actual point of the edge, so each value is an upper
@@ -445,17 +387,12 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                             // the child's box sits in two of the record's three box quads (l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz): two
                             // 16-byte loads instead of six scalar ones (the six were 29 % of the kernel's L1 tag requests, profiles/r2a)
                             const bool is_left = (r >> 31) != 0u;
-#if K1_QBOX
-                            const float4* rq = M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE;
-                            if (qbox_child_gap2(__ldg(rq + (is_left ? 0 : 1)), __ldg(rq + 2), is_left, qx, qy, qz) > skip_sq) { DG_EMU_COUNT(7); continue; }
-#else
                             const float4* bq = M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE + (is_left ? 2 : 3);
                             const float4 u = __ldg(bq), v = __ldg(bq + 1);
                             const float lox = is_left ? u.x : u.z, loy = is_left ? u.y : u.w, loz = is_left ? u.z : v.x;
                             const float hix = is_left ? u.w : v.y, hiy = is_left ? v.x : v.z, hiz = is_left ? v.y : v.w;
                             const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
                             if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
-#endif
                         }
 #endif
                         b = rb; depth = rd; e = re;
@@ -487,11 +424,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     if (e - m == 1) prefetch_l1(M.leaves + m); else prefetch_l1(M.nodes_f + (size_t)((m + e) >> 1) * K1_NODEF_STRIDE);
 #endif
 #if K1_BOX_SKIP && K1_EARLY_BOX
-#if K1_QBOX
-                    const float4 b0 = __ldg(f4 + 2);                                           // both boxes, quantised (12 bytes) + flags
-#else
                     const float4 b0 = __ldg(f4 + 2), b1 = __ldg(f4 + 3), b2 = __ldg(f4 + 4);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
-#endif
 #endif
                     const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
                     const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
@@ -509,13 +442,6 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                     defer = !(d_second_f - E >= best_hi);
 #if K1_BOX_SKIP
                     if (decided && go_first) {
-#if K1_QBOX
-#if !K1_EARLY_BOX
-                        const float4 b0 = __ldg(f4 + 2);
-#endif
-                        float l2, r2;
-                        qbox_pair_gap2(l4, r4, b0, qx, qy, qz, l2, r2);
-#else
 #if !K1_EARLY_BOX
                         const float4 b0 = __ldg(f4 + 2), b1 = __ldg(f4 + 3), b2 = __ldg(f4 + 4);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
 #endif
@@ -526,7 +452,6 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
                         // squared box distances rounded DOWN (a smaller value only skips less)
                         const float l2 = __fmaf_rd(lgz, lgz, __fmaf_rd(lgy, lgy, __fmul_rd(lgx, lgx)));
                         const float r2 = __fmaf_rd(rgz, rgz, __fmaf_rd(rgy, rgy, __fmul_rd(rgx, rgx)));
-#endif
                         const bool hopeless_first = (left_first ? l2 : r2) > skip_sq;
                         const bool hopeless_second = (left_first ? r2 : l2) > skip_sq;
                         if (hopeless_second) defer = false;
@@ -590,11 +515,7 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
             if (state == (K1_LEAF_FILTER ? LEAFX : LEAF)) {                     // leaf (:517-534)
                 double s, t; int ent;
                 DG_EMU_COUNT(3);
-                #if K1_FAST_DIV
-                const double d2 = tri_dist2(M.leaves + b, M.recips + b, px, py, pz, s, t, ent);
-#else
                 const double d2 = tri_dist2(M.leaves + b, px, py, pz, s, t, ent);
-#endif
                 if (d2 < best_sq) {
                     DG_EMU_COUNT(4);
                     best = sqrt(d2);
@@ -872,11 +793,7 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                 {
                     const float4* f4 = M.nodes_f + (size_t)m * K1_NODEF_STRIDE;
                     const float4 l4 = __ldg(f4), r4 = __ldg(f4 + 1);
-#if K1_QBOX
-                    const float4 b0f = __ldg(f4 + 2);
-#else
                     const float4 b0f = __ldg(f4 + 2), b1f = __ldg(f4 + 3), b2f = __ldg(f4 + 4);
-#endif
                     const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
                     const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
                     const float dl = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) - l4.w;
@@ -889,15 +806,10 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     decided = order_sure && (go_first || skip_first);
                     defer = !(d_second_f - E >= best_hi);
                     if (decided && go_first) {
-#if K1_QBOX
-                        float l2, r2;
-                        qbox_pair_gap2(l4, r4, b0f, qx, qy, qz, l2, r2);
-#else
                         const float lgx = fmaxf(fmaxf(b0f.x - qx, qx - b0f.w), 0.f), lgy = fmaxf(fmaxf(b0f.y - qy, qy - b1f.x), 0.f), lgz = fmaxf(fmaxf(b0f.z - qz, qz - b1f.y), 0.f);
                         const float rgx = fmaxf(fmaxf(b1f.z - qx, qx - b2f.y), 0.f), rgy = fmaxf(fmaxf(b1f.w - qy, qy - b2f.z), 0.f), rgz = fmaxf(fmaxf(b2f.x - qz, qz - b2f.w), 0.f);
                         const float l2 = __fmaf_rd(lgz, lgz, __fmaf_rd(lgy, lgy, __fmul_rd(lgx, lgx)));
                         const float r2 = __fmaf_rd(rgz, rgz, __fmaf_rd(rgy, rgy, __fmul_rd(rgx, rgx)));
-#endif
                         const bool hopeless_first = (left_first ? l2 : r2) > skip_sq, hopeless_second = (left_first ? r2 : l2) > skip_sq;
                         if (hopeless_second) defer = false;
                         if (hopeless_first) {
@@ -948,11 +860,7 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                 const double px = W.px[slot], py = W.py[slot], pz = W.pz[slot], best = W.best[slot];
                 const double best_sq = best * best;                            // result.distance * result.distance (+inf initially), :528
                 double s, t; int en;
-#if K1_FAST_DIV
-                const double d2 = tri_dist2(M.leaves + b, M.recips + b, px, py, pz, s, t, en);
-#else
                 const double d2 = tri_dist2(M.leaves + b, px, py, pz, s, t, en);
-#endif
                 if (d2 < best_sq) {
                     DG_EMU_COUNT(4);
                     const double nb = sqrt(d2);
@@ -995,16 +903,12 @@ sdf_sample_nodes_wave_kernel(MeshDev M, const PseudoNormals* __restrict__ normal
                     }
                     if (visit) {
 #if K1_BOX_SKIP
-#if K1_QBOX
-                        if (qbox_child_gap2(c4, __ldg(f4 + 2), is_left, qx, qy, qz) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
-#else
                         const float4* bq = f4 + (is_left ? 2 : 3);            // the child's box: two of the record's three box quads
                         const float4 u = __ldg(bq), v = __ldg(bq + 1);
                         const float lox = is_left ? u.x : u.z, loy = is_left ? u.y : u.w, loz = is_left ? u.z : v.x;
                         const float hix = is_left ? u.w : v.y, hiy = is_left ? v.x : v.z, hiz = is_left ? v.y : v.w;
                         const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
                         if (__fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx))) > skip_sq) { DG_EMU_COUNT(7); continue; }   // visiting it could not change anything
-#endif
 #endif
                         b = rb; depth = rd; e = re;
                         phase = (e - b == 1) ? WP_LEAF : WP_NODE;
@@ -1096,11 +1000,7 @@ __global__ void __launch_bounds__(256) fp64_rate_probe_kernel(double a, double b
 static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)); }
 static inline MeshDev mesh_dev(const DeviceBvh& m)
 {
-#if K1_FAST_DIV
-    return MeshDev{m.spheres, m.nodes_f, m.leaves_f, m.leaves, m.recips, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri};
-#else
     return MeshDev{m.spheres, m.nodes_f, m.leaves_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri};
-#endif
 }
 
 // The opt-in limit for dynamic shared memory is a per-function attribute: keep it at the maximum any live mesh has needed

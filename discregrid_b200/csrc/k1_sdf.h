@@ -59,18 +59,8 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 #ifndef K1_PREFETCH
 #define K1_PREFETCH 0            // prefetch.global.L1 of both children's records during a node step
 #endif
-// K1_QBOX 1: the child boxes of a node record are stored as 8-bit offsets in their sphere's frame (bvh_build.h: pack_node_records), the
-// record shrinks from 80 to 48 bytes: 3 instead of 5 16-byte loads per node step, 1 instead of 2 per popped sibling -- the kernels are
-// bound by L1 data-pipe wavefronts (profiles/r2a, r2b), not by arithmetic.  Looser boxes only skip slightly less; results are identical.
-#ifndef K1_QBOX
-#define K1_QBOX 0
-#endif
 #ifndef K1_NODEF_STRIDE
-#if K1_QBOX
-#define K1_NODEF_STRIDE 3         // float4s per fp32 node record: sphere pair (2) + quantised boxes and flags (1)
-#else
 #define K1_NODEF_STRIDE 5         // float4s per fp32 node record: 5 = packed 80 B, 6 = padded to 96 B
-#endif
 #endif
 #ifndef K1_EARLY_BOX
 #define K1_EARLY_BOX 1           // issue the box loads together with the sphere loads (latency) instead of after the sphere decision
@@ -130,13 +120,6 @@ struct K1Work {
     int compact;                   // 0: out[l - l_begin]; 1: interleaved exchange slot (see k1_launch_sample_interleaved)
 };
 
-// K1_FAST_DIV 1: the one division of the leaf test (by a per-triangle constant) is replaced by a multiplication with the constant's
-// precomputed reciprocal + four FMAs that land on the same IEEE quotient (fast_div.h; ~68 -> ~8 instructions of a 253-instruction
-// leaf test).  Needs 32 more bytes per triangle.  Off until measured on the GPU.
-#ifndef K1_FAST_DIV
-#define K1_FAST_DIV 0
-#endif
-
 // K1_VOTE_REDUX 1: the phase vote reads the three lane counts from ONE warp-wide integer sum (redux.sync) instead of two ballots +
 // three popcounts (the loop head is ~19 % of the issued instructions).  Off until measured on the GPU.
 #ifndef K1_VOTE_REDUX
@@ -148,9 +131,6 @@ struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once b
     const LeafRecord* leaves = nullptr;
     const PseudoNormals* normals = nullptr;
     const LeafF* leaves_f = nullptr;            // fp32 triangle shadows (leaf filter)
-#if K1_FAST_DIV
-    const LeafRecip* recips = nullptr;          // reciprocals of the leaf test's divisors
-#endif
     const float4* nodes_f = nullptr;          // fp32 record per internal node, K1_NODEF_STRIDE float4s: SpherePairF (2) + BoxPairF (3) [+ pad]
     double ctr[3] = {0, 0, 0};
     float half_extent = 0.f;

@@ -126,7 +126,7 @@ def test_reference_meshes(dg, orc, name, tmp_path):
 
 
 def test_division_by_known_reciprocal_is_the_ieee_quotient():
-    """tests/cpp/fast_div_check.cpp: discregrid_b200/csrc/fast_div.h (the K1_FAST_DIV build's replacement of the leaf test's division)
+    """tests/cpp/fast_div_check.cpp: discregrid_b200/csrc/fast_div.h (K3's division by the smoothing length through its reciprocal; round 2 measured the same trick in K1's leaf test slower and removed it there)
     gives num / den bit for bit on 3e7 operand pairs, including significands next to 1 and 2 and exactly divisible ones"""
     exe = os.path.join(ROOT, "build", "bin", "fast_div_check")
     if not os.path.exists(exe):

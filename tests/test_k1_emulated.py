@@ -11,7 +11,7 @@ import pytest
 from conftest import GOLDEN, ROOT, bits_equal, grid_for
 from test_oracle_golden import read_cdf, read_obj
 
-# default knobs, and the prepared-but-off knob variants (K1_FAST_DIV + K1_VOTE_REDUX); DG_K1_EMU_LIB adds any other build of tests/emu/k1_emu.cpp
+# default knobs, the knob variants (K1_VOTE_REDUX + K1_BRICK_AUTO), the wavefront kernel and the per-lane kernel; DG_K1_EMU_LIB adds any other build of tests/emu/k1_emu.cpp
 LIBS = [os.path.join(ROOT, "build", "bin", n) for n in ("libk1emu.so", "libk1emu_knobs.so", "libk1emu_wave.so", "libk1emu_perlane.so")] + \
        ([os.environ["DG_K1_EMU_LIB"]] if os.environ.get("DG_K1_EMU_LIB") else [])
 _dp, _u32p, _i32p, _u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
