@@ -424,6 +424,9 @@ def main():
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # a host-side group: ranks that must stay OFF their GPU (while rank 0 drives all GPUs from one process) wait in a gloo barrier -- an NCCL
+    # barrier is a spinning kernel, and two processes on one GPU are time-sliced, which halves the throughput of the GPU being measured
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
     dev = torch.device("cuda", local_rank)
 
     def barrier():
@@ -558,6 +561,7 @@ def main():
                    "api": "one process per GPU: dg_sample_sdf(mesh, grid, sign, l_begin, l_end, out_host) per rank over its node-id chunks (kernel + D2H into pageable host buffers)"}
             # ... and the single-process form a C++ caller uses: rank 0 drives ALL N GPUs through dg_add_function_sdf_multi while the other ranks idle
             barrier()
+            dist.barrier(group=cpu_group)
             if rank == 0:
                 try:
                     grp = C.c_void_p()
@@ -576,6 +580,7 @@ def main():
                     capi.lib.dg_mesh_group_destroy(grp)
                 except Exception as ex:                          # an auxiliary leg must not take the bench line down
                     e2e["single_process_c_abi"] = {"error": repr(ex)}
+            dist.barrier(group=cpu_group)                        # the idle ranks wait here, on the host
             barrier()
 
     # ---------------------------------------------------------------- interpolate half of the metric (config 4)

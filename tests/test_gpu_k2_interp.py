@@ -109,3 +109,36 @@ def test_sdf_field_round_trip(dg, orc, torus_small):
     # the interpolant approximates the true distance (sanity of the whole pipeline, loose)
     true = dg.TriangleMeshDistance(torus_small).signed_distance(x).distance
     assert np.median(np.abs(phi - true)) < 5e-3
+
+
+def test_host_pipeline_chunks_pinned_and_pageable(dg, orc):
+    """dg_interpolate_batch's three-slot pipeline: 2.3 M queries = five 512k-query chunks, so every slot is reused; pageable caller buffers
+    (staged through the pinned pool), page-locked ones (direct DMA), value-only and ragged sizes all equal the single-launch device result"""
+    import ctypes as C
+    from discregrid_b200 import _capi as capi
+    torch = pytest.importorskip("torch")
+    g = dg.CubicLagrangeDiscreteGrid(os.path.join(GOLDEN, "box.cdf"))
+    n = 2_300_017
+    x = _queries(g, n, 77)
+    fh = g._device_field(0)
+    xd = torch.from_numpy(x).cuda(); pd = torch.empty(n, dtype=torch.float64, device="cuda"); gd_ = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    capi.check(capi.lib.dg_interpolate_batch_device(fh, C.c_void_p(xd.data_ptr()), n, C.c_void_p(pd.data_ptr()), C.c_void_p(gd_.data_ptr()), None))
+    torch.cuda.synchronize()
+    want_p, want_g = pd.cpu().numpy(), gd_.cpu().numpy()
+    # pageable
+    p1 = np.full(n, np.nan); g1 = np.full((n, 3), np.nan)
+    capi.check(capi.lib.dg_interpolate_batch(fh, capi.ptr(x, capi.F64P), n, capi.ptr(p1, capi.F64P), capi.ptr(g1, capi.F64P)))
+    assert bits_equal(p1, want_p) and bits_equal(g1, want_g)
+    # page-locked
+    xp = torch.from_numpy(x).pin_memory(); pp = torch.empty(n, dtype=torch.float64).pin_memory(); gp = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    capi.check(capi.lib.dg_interpolate_batch(fh, C.cast(xp.data_ptr(), capi.F64P), n, C.cast(pp.data_ptr(), capi.F64P), C.cast(gp.data_ptr(), capi.F64P)))
+    assert bits_equal(pp.numpy(), want_p) and bits_equal(gp.numpy(), want_g)
+    # value only, a size that is not a multiple of anything, mixed: pinned in, pageable out
+    m = 1_048_577
+    p2 = np.full(m, np.nan)
+    capi.check(capi.lib.dg_interpolate_batch(fh, C.cast(xp.data_ptr(), capi.F64P), m, capi.ptr(p2, capi.F64P), None))
+    assert bits_equal(p2, want_p[:m])
+    # a single query still works after the pool has grown
+    p3 = np.empty(1); g3 = np.empty((1, 3))
+    capi.check(capi.lib.dg_interpolate_batch(fh, capi.ptr(x[5:6].copy(), capi.F64P), 1, capi.ptr(p3, capi.F64P), capi.ptr(g3, capi.F64P)))
+    assert bits_equal(p3, want_p[5:6]) and bits_equal(g3, want_g[5:6])
