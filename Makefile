@@ -32,7 +32,7 @@ $(CPPBIN)/bvh_host_check: tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SR
 	@mkdir -p $(CPPBIN)
 	$(HOSTCXX) $(CXXFLAGS) -fvisibility=default tests/cpp/bvh_host_check.cpp $(SRC)/bvh_build.cpp $(SRC)/host_threads.cpp $(SRC)/sort_replay.cpp -o $@ -lpthread
 # test libraries: the K1 translation unit (kernels + launchers) compiled for the CPU by tests/emu -- default knobs, and the prepared
-# knob variants (redux vote, per-array brick shape) so that their logic stays checked while off
+# the knobs that are ON by default (redux vote, per-array brick shape) switched off, so that both settings stay checked
 K1EMU_SRC := tests/emu/k1_emu.cpp $(SRC)/bvh_build.cpp $(SRC)/host_threads.cpp $(SRC)/sort_replay.cpp
 K1EMU_DEP := $(K1EMU_SRC) tests/emu/cuda_emu.h $(SRC)/k1_sdf.cu $(HDRS)
 CUDA_INC  ?= /usr/local/cuda/include
@@ -41,7 +41,7 @@ $(CPPBIN)/libk1emu.so: $(K1EMU_DEP)
 	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
 $(CPPBIN)/libk1emu_knobs.so: $(K1EMU_DEP)
 	@mkdir -p $(CPPBIN)
-	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DK1_VOTE_REDUX=1 -DK1_BRICK_AUTO=1 -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
+	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DK1_VOTE_REDUX=0 -DK1_BRICK_AUTO=0 -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
 # the wavefront node-loop kernel (K1_WAVE=1) and the per-lane one (K1_WAVE=0), whichever is not the default build, stay checked
 $(CPPBIN)/libk1emu_wave.so: $(K1EMU_DEP)
 	@mkdir -p $(CPPBIN)

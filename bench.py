@@ -817,6 +817,28 @@ def main():
             capi.lib.dg_field_destroy(fh)
         del dens
 
+    # ---------------------------------------------------------------- the rebuilt C++ tools as a user runs them (facade over the C-ABI), N = 1 only
+    tools = None
+    gen_sdf, gen_dm = os.path.join(ROOT, "build", "bin", "GenerateSDF"), os.path.join(ROOT, "build", "bin", "GenerateDensityMap")
+    mesh_path = os.path.join(RES_DIR, "bunny.obj")
+    if rank == 0 and world == 1 and not args.no_density and not args.no_e2e and os.path.exists(gen_sdf) and os.path.exists(gen_dm) and os.path.exists(mesh_path) and source == "bunny":
+        try:
+            tdir = scratch_dir()
+            cdf, cdm = os.path.join(tdir, f"_dg_tools_{os.getpid()}.cdf"), os.path.join(tdir, f"_dg_tools_{os.getpid()}.cdm")
+            rstr = f"{res[0]} {res[1]} {res[2]}"
+            t0 = time.perf_counter(); r1 = subprocess.run([gen_sdf, "-r", rstr, "-o", cdf, mesh_path], capture_output=True, text=True, timeout=900); t_sdf = time.perf_counter() - t0
+            h_tool = 0.1 * float(np.max(mx - mn)) / 2.5
+            t0 = time.perf_counter(); r2 = subprocess.run([gen_dm, "-s", repr(h_tool), "-o", cdm, cdf], capture_output=True, text=True, timeout=1800); t_dm = time.perf_counter() - t0
+            tools = {"what": "wall clock of the rebuilt reference tools, process start to exit (OBJ parse, BVH build + upload, CUDA context, addFunction, "
+                             "K3 + both reduceField passes, file I/O): GenerateSDF -r 128^3 bunny.obj; GenerateDensityMap (with reduction) on its output",
+                     "generate_sdf_s": t_sdf, "generate_sdf_rc": r1.returncode, "generate_density_map_s": t_dm, "generate_density_map_rc": r2.returncode,
+                     "cdf_bytes": os.path.getsize(cdf) if os.path.exists(cdf) else None, "cdm_bytes": os.path.getsize(cdm) if os.path.exists(cdm) else None}
+            for f_ in (cdf, cdm):
+                if os.path.exists(f_):
+                    os.remove(f_)
+        except Exception as ex:
+            tools = {"error": repr(ex)}
+
     # ---------------------------------------------------------------- CPU baseline (the reference's real addFunction), rank 0, N = 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -854,7 +876,7 @@ def main():
         line = {"metric": "SDF grid nodes/sec (addFunction)", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": data, "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "target_config": target, "reference_meshes": real, "density_map": density,
+                "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "target_config": target, "reference_meshes": real, "density_map": density, "tools_e2e": tools,
                 "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms,
                            "ideal_ms_per_step_from_n1": None, "collective_and_unpack_ms": ms_step - k1_ms},
                 "parity_full": None if cpu is None else {"nodes_bit_exact": cpu.get("parity_nodes_bit_exact"), "nodes_compared": cpu.get("parity_nodes_compared"),

@@ -99,9 +99,9 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 // diagonal is shortest -- instead of the fixed K1_BRICK_F x K1_BRICK_M x K1_BRICK_S.  On cubic cells that is the default 4 x 4 x 2
 // (x-edge arrays: their node spacing along f is half a cell); on strongly anisotropic cells (a flat bounding box sampled with a cubic
 // resolution) a flatter brick keeps the 32 queries closer together (CPU schedule model: -6 % issued instructions on the bench torus).
-// Off until measured on the GPU; checked against the oracle by the emulated test build.
+// Checked against the oracle by the emulated test builds (on and off).
 #ifndef K1_BRICK_AUTO
-#define K1_BRICK_AUTO 0
+#define K1_BRICK_AUTO 1          // measured with K1_VOTE_REDUX (profiles/r2g_sweep.txt): bunny.obj 128^3 77.0 -> 75.0 ms, anisotropic torus grid 54.9 -> 51.9 ms
 #endif
 
 struct K1Segment {
@@ -121,9 +121,9 @@ struct K1Work {
 };
 
 // K1_VOTE_REDUX 1: the phase vote reads the three lane counts from ONE warp-wide integer sum (redux.sync) instead of two ballots +
-// three popcounts (the loop head is ~19 % of the issued instructions).  Off until measured on the GPU.
+// three popcounts (the loop head is ~19 % of the issued instructions).
 #ifndef K1_VOTE_REDUX
-#define K1_VOTE_REDUX 0
+#define K1_VOTE_REDUX 1          // measured (profiles/r2a_sweep.txt, r2g_sweep.txt): -1.5 %
 #endif
 
 struct DeviceBvh {                 // device mirrors of HostBvh, uploaded once by dg_mesh_create

@@ -115,7 +115,8 @@ __device__ __forceinline__ double interp_value(const FieldDev& f, double x, doub
 }
 
 #ifndef K3_MIN_BLOCKS
-#define K3_MIN_BLOCKS 1            // blocks of 128 threads per SM the register allocation must allow (1 = compiler's choice, 104 registers)
+#define K3_MIN_BLOCKS 5            // blocks of 128 threads per SM the register allocation must allow: 96 registers, no spills; measured 288 vs 324 ms
+                                   // (profiles/r2g_sweep.txt; 6 -> 80 registers with spills 288 ms, 8 -> 64 registers 425 ms)
 #endif
 __global__ void __launch_bounds__(128, K3_MIN_BLOCKS)
 density_map_kernel(FieldDev f, QuadParams qp, const double* __restrict__ Wtab, int no_reduction, unsigned l_begin,
