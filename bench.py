@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--sharding", default="auto", choices=["auto", "slab", "chunks", "interleaved"],
                     help="N>1: round-robin node-id chunks, whole-plane slabs, or plane pairs dealt round-robin (one launch + one all-gather + unpack); "
                          "auto = interleaved from 4 ranks up, chunks below")
+    ap.add_argument("--splits", type=int, default=1, help="interleaved sharding: launches per rank (each on its own stream; world * splits <= 16)")
     ap.add_argument("--no-real", action="store_true", help="skip the leg on the other reference meshes (dragon / happy_buddha)")
     ap.add_argument("--no-density", action="store_true", help="skip the density-map (K3) legs (diagnostics / profiling)")
     ap.add_argument("--cpu-seconds", type=float, default=40.0, help="a CPU leg whose full-size run is estimated to take longer than this falls back to a strided sample")
@@ -451,7 +452,7 @@ def main():
         if args.sharding == "slab":
             return SlabSdfSampler(md_, desc_, rank, world)
         if args.sharding == "interleaved":
-            return InterleavedSdfSampler(md_, desc_, rank, world)
+            return InterleavedSdfSampler(md_, desc_, rank, world, splits=args.splits if world * args.splits <= 16 else 1)
         return ShardedSdfSampler(md_, desc_, make_sharding(n_, world), rank)
 
     sdf_sampler = make_sampler(md, desc, n_nodes)
@@ -500,7 +501,7 @@ def main():
     if args.sharding == "slab" and world > 1:
         my_nodes = sum(e - b for (b, e) in sdf_sampler.sh.ranges[rank]); n_launch = 1
     elif args.sharding == "interleaved" and world > 1:
-        my_nodes = n_nodes // world; n_launch = 1
+        my_nodes = n_nodes // world; n_launch = max(1, args.splits)
     else:
         my_nodes = sum(e - b for (_j, b, e) in my_chunks); n_launch = sum(1 for (_j, b, e) in my_chunks if e > b)
     peaks, peak_src = measured_peaks()

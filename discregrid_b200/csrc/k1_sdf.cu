@@ -1186,18 +1186,19 @@ bool k1_interleaved_layout(const GridDev& g, unsigned n_parts, InterleavedLayout
 #if K1_BRICK_AUTO
     for (int a = 0; a < 4; a++) choose_brick(g, a, L.lf[a], L.lm[a]);
 #endif
-    for (int a = 0; a < 4; a++) { L.pairs[a] = (dims[a][0] + LAY_BS(L, a) - 1) / LAY_BS(L, a); L.plane[a] = dims[a][1] * dims[a][2]; }
-    for (unsigned r = 0; r < n_parts; r++) {
+    for (int a = 0; a < 4; a++) { L.pairs[a] = (dims[a][0] + LAY_BS(L, a) - 1) / LAY_BS(L, a); L.plane[a] = dims[a][1] * dims[a][2]; L.rot[a] = ((unsigned)a * (n_parts >= 4 ? n_parts / 4 : 1u)) % n_parts; }
+    for (unsigned part = 0; part < n_parts; part++) {
         uint64_t off = 0;
         for (int a = 0; a < 4; a++) {
-            L.off[a][r] = (unsigned)off;
-            const uint64_t mine = (L.pairs[a] > r) ? (L.pairs[a] - r + n_parts - 1) / n_parts : 0;      // pairs r, r + n_parts, ...
+            L.off[a][part] = (unsigned)off;
+            const unsigned r = (part + n_parts - L.rot[a]) % n_parts;                                    // first plane group of this part in array a
+            const uint64_t mine = (L.pairs[a] > r) ? (L.pairs[a] - r + n_parts - 1) / n_parts : 0;      // groups r, r + n_parts, ...
             off += mine * LAY_BS(L, a) * (uint64_t)L.plane[a];
         }
         if (off > 0xffffffffull) return false;
         if (off > L.slot_elems) L.slot_elems = off;
     }
-    for (unsigned r = n_parts; r < 16; r++) for (int a = 0; a < 4; a++) L.off[a][r] = 0;
+    for (unsigned part = n_parts; part < 16; part++) for (int a = 0; a < 4; a++) L.off[a][part] = 0;
     return true;
 }
 
@@ -1210,7 +1211,8 @@ cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, d
     w.nseg = 0; w.l_begin = 0u; w.l_end = 0xffffffffu; w.compact = 1;
     unsigned blocks = 0;
     for (int k = 0; k < 4; k++) {
-        const unsigned mine = (L.pairs[k] > part) ? (L.pairs[k] - part + L.n_parts - 1) / L.n_parts : 0;
+        const unsigned first = (part + L.n_parts - L.rot[k]) % L.n_parts;                               // this part's first plane group of array k
+        const unsigned mine = (L.pairs[k] > first) ? (L.pairs[k] - first + L.n_parts - 1) / L.n_parts : 0;
         if (mine == 0) continue;
         K1Segment& S = w.seg[w.nseg++];
         S.kind = k; S.l_base = (unsigned)base[k];
@@ -1218,7 +1220,7 @@ cudaError_t k1_launch_sample_interleaved(const DeviceBvh& m, const GridDev& g, d
 #if K1_BRICK_AUTO
         S.lf = L.lf[k]; S.lm = L.lm[k];
 #endif
-        S.s0 = part * SEG_BS(S); S.s1 = S.Ds; S.pl_stride = L.n_parts; S.out_base = L.off[k][part];
+        S.s0 = first * SEG_BS(S); S.s1 = S.Ds; S.pl_stride = L.n_parts; S.out_base = L.off[k][part];
         const unsigned bf = SEG_BF(S) * (K1_THREADS / 32);
         S.tiles_f = (S.Df + bf - 1) / bf; S.tiles_m = (S.Dm + SEG_BM(S) - 1) / SEG_BM(S);
         S.block_begin = blocks;
@@ -1239,7 +1241,7 @@ __host__ __device__ inline unsigned long long interleaved_slot_of(const GridDev&
     const unsigned s = (unsigned)(rel / plane), inplane = (unsigned)(rel - (unsigned long long)s * plane);
     const unsigned bs = LAY_BS(L, a);
     const unsigned pair = s / bs, j = pair / L.n_parts;
-    part = pair % L.n_parts;
+    part = (pair + L.rot[a]) % L.n_parts;
     return (unsigned long long)L.off[a][part] + (unsigned long long)(j * bs + (s % bs)) * plane + inplane;
 }
 
@@ -1274,7 +1276,7 @@ void k1_interleaved_runs(const GridDev& g, const InterleavedLayout& L, unsigned 
     runs.clear();
     for (int a = 0; a < 4; a++) {
         const unsigned bs = LAY_BS(L, a);
-        for (unsigned pair = part; pair < L.pairs[a]; pair += L.n_parts) {
+        for (unsigned pair = (part + L.n_parts - L.rot[a]) % L.n_parts; pair < L.pairs[a]; pair += L.n_parts) {
             const unsigned s0 = pair * bs, s1 = std::min(dims[a][0], s0 + bs);
             K1Run r;
             r.node_begin = base[a] + (uint64_t)s0 * L.plane[a];

@@ -148,6 +148,9 @@ cudaError_t k1_launch_sample_slab(const DeviceBvh& m, const GridDev& g, double s
 // them compactly into its exchange slot; k1_launch_unpack_interleaved scatters the gathered slots into node order.
 struct InterleavedLayout {
     unsigned n_parts = 1;
+    unsigned rot[4];               // plane group p of array a belongs to part (p + rot[a]) % n_parts: the deal is rotated per array so that the
+                                   // parts that get one plane group more differ from array to array (129 planes = 65 pairs over 8 parts: 9:8 in
+                                   // every array without the rotation, 33:32 over the four arrays with it)
     unsigned off[4][16];           // off[a][part]: element offset of array a in part's slot
     unsigned pairs[4];             // plane pairs of array a
     unsigned plane[4];             // elements per plane of array a
