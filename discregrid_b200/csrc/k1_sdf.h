@@ -105,7 +105,7 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 #endif
 
 struct K1Segment {
-    unsigned l_base, Ds, Dm, Df, s0, s1, tiles_f, tiles_m, block_begin;
+    unsigned l_base, Ds, Dm, Df, s0, s1, tiles_f, tiles_m, tiles_s, block_begin;
 #if K1_BRICK_AUTO
     unsigned lf, lm;               // log2 of the brick's extents along f and m (s extent = 32 >> (lf + lm))
 #endif
