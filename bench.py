@@ -423,7 +423,7 @@ def main():
     torch.cuda.set_device(local_rank)
     capi.check(capi.lib.dg_set_device(local_rank))
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
+        # NCCL_DEBUG stays unset: WARN would make NCCL print its version banner on stdout, next to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # a host-side group: ranks that must stay OFF their GPU (while rank 0 drives all GPUs from one process) wait in a gloo barrier -- an NCCL
     # barrier is a spinning kernel, and two processes on one GPU are time-sliced, which halves the throughput of the GPU being measured
