@@ -3,6 +3,7 @@
 #include "../../include/discregrid_b200.h"
 
 #include <atomic>
+#include <condition_variable>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
@@ -517,7 +518,10 @@ HostPathPool g_pool;
 
 // the pipeline of the host-buffer path; the caller holds g_pool.mu.  copy_threads > 1: the copy from the pinned piece into the
 // caller's memory is split over that many threads (fresh pageable memory: the page faults, not the bytes, are the cost)
-static int sample_sdf_host_locked(const dg_mesh* m, const GridDev& g, double sign, uint64_t l_begin, uint64_t n, double* out_host, unsigned copy_threads)
+namespace { struct HostTablesJob; }
+static void tables_job_copy(HostTablesJob* job, void* dst, const void* src, size_t bytes);
+static int sample_sdf_host_locked(const dg_mesh* m, const GridDev& g, double sign, uint64_t l_begin, uint64_t n, double* out_host, unsigned copy_threads,
+                                  HostTablesJob* copier = nullptr)
 {
     // kernel chunks: a handful, each a multiple of the staging piece so that pieces never straddle chunks
     const uint64_t piece = HostPathPool::kPiece;
@@ -542,7 +546,9 @@ static int sample_sdf_host_locked(const dg_mesh* m, const GridDev& g, double sig
             const uint64_t off = (i - 1) * piece, cnt = (off + piece <= n) ? piece : n - off;
             DG_CUDA(cudaEventSynchronize(g_pool.dma_ev[(i - 1) & 1]));
             const double* src = g_pool.stage[(i - 1) & 1];
-            if (copy_threads > 1 && cnt >= (1u << 16)) {
+            if (copier) {
+                tables_job_copy(copier, out_host + off, src, cnt * sizeof(double));
+            } else if (copy_threads > 1 && cnt >= (1u << 16)) {
                 std::vector<std::thread> th;
                 const uint64_t per = (cnt + copy_threads - 1) / copy_threads;
                 for (unsigned k = 1; k < copy_threads; k++) {
@@ -625,6 +631,48 @@ struct HostTablesJob {
     double ms_prefault = 0.0;
     unsigned n_workers = 0;
     std::vector<std::thread> th;
+    // copy service: once the tables are written the workers wait here and share the copies staging buffer -> caller memory with the
+    // thread that drives the pipeline (one thread copies ~2-4 GB/s into pages another thread faulted in; the pipeline needs a 32 MiB
+    // piece every ~14 ms, which a loaded host does not sustain single-threaded: profiles/r2l_multi_probe.txt)
+    struct CopyJob { char* dst; const char* src; size_t bytes; std::atomic<size_t> next{0}, done{0}; };
+    std::mutex c_mu; std::condition_variable c_cv;
+    std::shared_ptr<CopyJob> c_job;                              // guarded by c_mu; a late worker only ever touches the job it picked up
+    uint64_t c_gen = 0; bool c_quit = false;
+    static constexpr size_t c_blk = 1u << 20;
+    static void copy_blocks(CopyJob& j)
+    {
+        for (;;) {
+            const size_t b = j.next.fetch_add(c_blk);
+            if (b >= j.bytes) break;
+            const size_t n = std::min(c_blk, j.bytes - b);
+            std::memcpy(j.dst + b, j.src + b, n);
+            j.done.fetch_add(n);
+        }
+    }
+    void copy(void* dst, const void* src, size_t bytes)          // called by the pipeline's thread
+    {
+        if (bytes < 4 * c_blk || th.empty()) { std::memcpy(dst, src, bytes); return; }
+        auto job = std::make_shared<CopyJob>();
+        job->dst = static_cast<char*>(dst); job->src = static_cast<const char*>(src); job->bytes = bytes;
+        { std::lock_guard<std::mutex> lk(c_mu); c_job = job; c_gen++; }
+        c_cv.notify_all();
+        copy_blocks(*job);
+        while (job->done.load() < bytes) std::this_thread::yield();
+    }
+    void serve_copies()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            std::shared_ptr<CopyJob> job;
+            {
+                std::unique_lock<std::mutex> lk(c_mu);
+                c_cv.wait(lk, [&] { return c_quit || c_gen != seen; });
+                if (c_quit) return;
+                seen = c_gen; job = c_job;
+            }
+            if (job) copy_blocks(*job);
+        }
+    }
     void work()
     {
         for (;;) {
@@ -660,16 +708,20 @@ struct HostTablesJob {
         const unsigned hw = host_threads();
         (void)reserve_threads;
         n_workers = std::max(1u, std::min(hw / 4u, 24u));
-        try { for (unsigned k = 0; k < n_workers; k++) th.emplace_back([this]() { work(); }); } catch (...) { /* fewer workers: finish() does the rest */ }
+        try { for (unsigned k = 0; k < n_workers; k++) th.emplace_back([this]() { work(); serve_copies(); }); } catch (...) { /* fewer workers: finish() does the rest */ }
     }
     void finish()
     {
         work();                                         // whatever is left
+        { std::lock_guard<std::mutex> lk(c_mu); c_quit = true; }
+        c_cv.notify_all();
         for (auto& t : th) t.join();
         th.clear();
     }
 };
 }  // namespace
+
+static void tables_job_copy(HostTablesJob* job, void* dst, const void* src, size_t bytes) { job->copy(dst, src, bytes); }
 
 // The whole of CubicLagrangeDiscreteGrid::addFunction(GenerateSDF functor) into the caller's three arrays
 // (cubic_lagrange_discrete_grid.cpp:780-899): node loop on the GPU (K1 chunks on two streams, D2H through the pinned double
@@ -694,7 +746,7 @@ int dg_add_function_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign,
     int rc;
     {
         std::lock_guard<std::mutex> lock(g_pool.mu);
-        rc = sample_sdf_host_locked(m, g, sign, 0, n_nodes, nodes_host, copy_threads);
+        rc = sample_sdf_host_locked(m, g, sign, 0, n_nodes, nodes_host, copy_threads, &job);
     }
     const double ms_nodes = ms_since(t0);
     job.finish();
