@@ -763,7 +763,7 @@ int dg_add_function_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign,
 struct dg_mesh_group {
     struct PerDev {
         cudaStream_t st[2] = {nullptr, nullptr};
-        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaEvent_t ev[16] = {};                            // one per part of this device (at most 16 parts in all)
         double* d_buf = nullptr; size_t d_cap = 0;          // host form: 2 slots; device form: n exchange slots
         double* h_stage = nullptr; size_t h_cap = 0;        // pinned staging (pageable destinations only)
         void* comm = nullptr;                               // ncclComm_t
@@ -837,7 +837,8 @@ int dg_mesh_group_destroy(dg_mesh_group* grp)
 #if DG_HAVE_NCCL
         if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(d.comm));
 #endif
-        for (int k = 0; k < 2; k++) { if (d.st[k]) cudaStreamDestroy(d.st[k]); if (d.ev[k]) cudaEventDestroy(d.ev[k]); }
+        for (int k = 0; k < 2; k++) if (d.st[k]) cudaStreamDestroy(d.st[k]);
+        for (int k = 0; k < 16; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
         if (d.d_buf) cudaFree(d.d_buf);
         if (d.h_stage) cudaFreeHost(d.h_stage);
         if (i > 0) delete grp->parts[i];
@@ -873,7 +874,8 @@ int dg_mesh_group_create(const dg_mesh* mesh, int n_gpus, const int* devices, dg
         DG_CUDA(cudaSetDevice(grp->devices[i]));
         grp->n = i + 1;                                             // destroy() only visits initialised entries
         auto& d = grp->dev[i];
-        for (int k = 0; k < 2; k++) { DG_CUDA(cudaStreamCreateWithFlags(&d.st[k], cudaStreamNonBlocking)); DG_CUDA(cudaEventCreateWithFlags(&d.ev[k], cudaEventDisableTiming)); }
+        for (int k = 0; k < 2; k++) DG_CUDA(cudaStreamCreateWithFlags(&d.st[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 16; k++) DG_CUDA(cudaEventCreateWithFlags(&d.ev[k], cudaEventDisableTiming));
         if (i == 0) continue;
         int can = 0;
         if (cudaDeviceCanAccessPeer(&can, grp->devices[i], mesh->device) == cudaSuccess && can) { if (cudaDeviceEnablePeerAccess(mesh->device, 0) != cudaSuccess) cudaGetLastError(); }
@@ -918,7 +920,15 @@ int dg_add_function_sdf_multi(dg_mesh_group* grp, const dg_grid_desc* grid, doub
     if (!nodes_host) return fail(DG_ERR_INVALID, "dg_add_function_sdf_multi: nodes output is NULL");
     std::lock_guard<std::mutex> lock(grp->mu);
     const int n = grp->n;
-    const unsigned splits = (2 * n <= 16) ? 2u : 1u;
+    // parts per GPU: at least two (the D2H and the host copy of one part run under the next launch), more when the grid is large -- what
+    // stays exposed at the end is the copy of ONE part into the caller's memory (profiles/r2l_multi_probe.txt) -- but never below ~4 M
+    // nodes per launch (a launch ends with a ~2 ms tail) and never more than 16 parts in all
+    unsigned splits = (2 * n <= 16) ? 2u : 1u;
+    {
+        const uint64_t by_size = n_nodes / (4000000ull * (uint64_t)n);
+        const unsigned cap = 16u / (unsigned)n;
+        if (by_size > splits) splits = (unsigned)std::min<uint64_t>(by_size, cap);
+    }
     InterleavedLayout L;
     if (!k1_interleaved_layout(g, (unsigned)n * splits, L)) return fail(DG_ERR_INVALID, "dg_add_function_sdf_multi: grid too large for the exchange layout");
     const auto t0 = std::chrono::steady_clock::now();
@@ -933,18 +943,19 @@ int dg_add_function_sdf_multi(dg_mesh_group* grp, const dg_grid_desc* grid, doub
         DG_CUDA(cudaSetDevice(grp->devices[i]));
         auto& d = grp->dev[i];
         if (int rc = group_grow(d, (size_t)splits * L.slot_elems, direct ? 0 : (size_t)splits * L.slot_elems)) return rc;
-        std::vector<K1Run> runs[2];
+        std::vector<K1Run> runs[16];
         for (unsigned sp = 0; sp < splits; sp++) {
             const unsigned part = (unsigned)i + sp * (unsigned)n;
             double* d_slot = d.d_buf + (size_t)sp * L.slot_elems;
-            DG_CUDA(k1_launch_sample_interleaved(grp->parts[i]->dev, g, sign, L, part, d_slot, d.st[sp]));
+            cudaStream_t stream = d.st[sp & 1u];
+            DG_CUDA(k1_launch_sample_interleaved(grp->parts[i]->dev, g, sign, L, part, d_slot, stream));
             launches[i]++;
             k1_interleaved_runs(g, L, part, runs[sp]);
             uint64_t used = 0;
             for (const auto& r : runs[sp]) used = std::max<uint64_t>(used, r.slot_pos + r.count);
-            if (direct) { for (const auto& r : runs[sp]) DG_CUDA(cudaMemcpyAsync(nodes_host + r.node_begin, d_slot + r.slot_pos, r.count * sizeof(double), cudaMemcpyDeviceToHost, d.st[sp])); }
-            else if (used) DG_CUDA(cudaMemcpyAsync(d.h_stage + (size_t)sp * L.slot_elems, d_slot, used * sizeof(double), cudaMemcpyDeviceToHost, d.st[sp]));
-            DG_CUDA(cudaEventRecord(d.ev[sp], d.st[sp]));
+            if (direct) { for (const auto& r : runs[sp]) DG_CUDA(cudaMemcpyAsync(nodes_host + r.node_begin, d_slot + r.slot_pos, r.count * sizeof(double), cudaMemcpyDeviceToHost, stream)); }
+            else if (used) DG_CUDA(cudaMemcpyAsync(d.h_stage + (size_t)sp * L.slot_elems, d_slot, used * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            DG_CUDA(cudaEventRecord(d.ev[sp], stream));
         }
         for (unsigned sp = 0; sp < splits; sp++) {
             DG_CUDA(cudaEventSynchronize(d.ev[sp]));

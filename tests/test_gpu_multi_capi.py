@@ -83,3 +83,24 @@ def test_group_argument_errors(dg, torus_small):
     assert capi.lib.dg_mesh_group_create(None, 1, None, C.byref(h)) == capi.DG_ERR_INVALID
     assert capi.lib.dg_mesh_group_create(md.handle, dg.device_count() + 1, None, C.byref(h)) == capi.DG_ERR_INVALID
     assert capi.lib.dg_mesh_group_destroy(None) == capi.DG_OK
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2])
+def test_large_grid_uses_more_parts_per_gpu(dg, torus_small, n_gpus):
+    """12.4 M nodes: dg_add_function_sdf_multi deals more than two parts to a GPU (three with one GPU) -- same coefficients as the single-GPU call"""
+    from discregrid_b200 import _capi as capi
+    if dg.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    md = dg.TriangleMeshDistance(torus_small)
+    mn, mx = dg.generate_sdf_domain(torus_small.vertices)
+    desc = dg.grid_desc(mn, mx, (120, 120, 120))
+    n = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(n))); n = n.value
+    single = np.empty(n)
+    capi.check(capi.lib.dg_sample_sdf(md.handle, C.byref(desc), 1.0, 0, n, capi.ptr(single, capi.F64P)))
+    grp = _group(dg, capi, md, n_gpus)
+    try:
+        multi = np.full(n, np.nan)
+        capi.check(capi.lib.dg_add_function_sdf_multi(grp, C.byref(desc), 1.0, capi.ptr(multi, capi.F64P), None, None, None))
+        assert np.array_equal(multi.view(np.uint64), single.view(np.uint64))
+    finally:
+        capi.lib.dg_mesh_group_destroy(grp)
