@@ -559,11 +559,9 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
     const K1Segment& S = w.seg[sg];
     unsigned t = this_block - S.block_begin;
     const unsigned tf = t % S.tiles_f; t /= S.tiles_f;
-    const unsigned tm = t % S.tiles_m; const unsigned ts_launch = t / S.tiles_m;
-    // plane groups are taken from the outside in (first, last, second, second to last, ...): the groups at the faces of the domain hold the
-    // queries farthest from the mesh -- the longest walks -- and the launch should END with the short ones (a ~2 ms tail of long-lived warps
-    // otherwise: irrelevant for one big launch, 20 % of a rank's step on 8 GPUs)
-    const unsigned ts = (ts_launch & 1u) ? S.tiles_s - 1u - (ts_launch >> 1) : (ts_launch >> 1);
+    const unsigned tm = t % S.tiles_m; const unsigned ts = t / S.tiles_m;
+    // (round 2 measured taking the plane groups from the outside in, to end a launch with the short walks near the mesh: 3 % slower at
+    // N = 1 -- L1 hit rate 74 -> 67 % -- and no gain on 8 GPUs; profiles/r2m_outside_in.txt)
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #if K1_BRICK_AUTO
     const unsigned f = tf * (SEG_BF(S) * (unsigned)(K1_THREADS / 32)) + warp * SEG_BF(S) + (lane & (SEG_BF(S) - 1u));
