@@ -1,5 +1,5 @@
 """diagnostic (1 GPU): per-part K1 kernel time of the three multi-GPU shardings for a simulated world size -- max over parts is what a
-real N-GPU step would wait for (collective excluded).  usage: part_times.py [world] [resolution] [n_tris-ish: torus|target]"""
+real N-GPU step would wait for (collective excluded).  usage: part_times.py [world] [resolution] [mesh: torus|target|bunny]"""
 import ctypes as C, sys, os
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,17 +10,20 @@ import bench
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 res = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 which = sys.argv[3] if len(sys.argv) > 3 else "torus"
-mesh = dg.bumpy_torus(*bench.WORKLOAD["torus"]) if which == "torus" else dg.bumpy_torus()
+mesh = bench.workload_mesh(dg, "bunny")[0] if which == "bunny" else (dg.bumpy_torus(*bench.WORKLOAD["torus"]) if which == "torus" else dg.bumpy_torus())
 md = dg.TriangleMeshDistance(mesh)
 mn, mx = dg.generate_sdf_domain(mesh.vertices); desc = dg.grid_desc(mn, mx, [res] * 3)
 n = C.c_uint64(); capi.check(capi.lib.dg_grid_num_nodes(desc.resolution, C.byref(n))); n = n.value
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 full = torch.empty(n + 4096, dtype=torch.float64, device="cuda")
 
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if os.environ.get("DG_FLUSH_L2") == "1" else None
+
 def timed(fn, reps=3):
     fn(); torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
+        if flush is not None: flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
     return min(ts)
