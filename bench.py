@@ -879,7 +879,7 @@ def main():
                 "dtype": "f64", "data": data, "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "interpolate": interp, "target_config": target, "reference_meshes": real, "density_map": density, "tools_e2e": tools,
                 "timing": {"per_step_ms": sdf_ms, "wall_s_timed_region": sdf_wall, "k1_only_ms_per_step": k1_ms,
-                           "ideal_ms_per_step_from_n1": None, "collective_and_unpack_ms": ms_step - k1_ms},
+                           "collective_and_unpack_ms": ms_step - k1_ms},
                 "parity_full": None if cpu is None else {"nodes_bit_exact": cpu.get("parity_nodes_bit_exact"), "nodes_compared": cpu.get("parity_nodes_compared"),
                                                          "cells_equal": cpu.get("parity_cells_equal"),
                                                          "interpolate_bit_exact": ((interp or {}).get("cpu_baseline") or {}).get("bit_exact_vs_gpu"),
