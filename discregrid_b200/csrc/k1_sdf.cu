@@ -546,17 +546,13 @@ extern __shared__ __align__(16) unsigned char k1_smem[];
 // take similar numbers of steps.  Whole slow-planes are covered; nodes outside [l_begin, l_end) are masked.
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals, int stack_depth, GridDev g, K1Work w, double sign,
-                        double* __restrict__ out
-#if K1_TAIL_CLASSES
-                        , const unsigned* __restrict__ block_order      // launch position -> block id (heaviest class first), or nullptr
-#endif
-                        )
+                        double* __restrict__ out)
 {
-#if K1_TAIL_CLASSES
-    const unsigned this_block = block_order ? __ldg(block_order + blockIdx.x) : blockIdx.x;
-#else
+    // blocks run in launch order.  Round 2 measured three ways of ending a launch with short walks instead (a launch of an eighth of the 128^3
+    // grid takes 12 - 14 ms instead of 9.3: profiles/r2o): plane groups from the outside in, and a stable heaviest-class-first order from a
+    // coarse distance lattice with 2 / 4 / 8 classes -- all slower (N = 1: 77.5 / 80.9 / 79.3 / 93.1 vs 74.9 ms; parts no better; r2m, r2p):
+    // neighbouring bricks running at the same time share tree nodes in L1, and that is worth more than a short drain.
     const unsigned this_block = blockIdx.x;
-#endif
     DG_EMU_TRACE_BLOCK(this_block);
     float* stack_d = reinterpret_cast<float*>(k1_smem);
     unsigned* stack_rng = reinterpret_cast<unsigned*>(k1_smem + (size_t)stack_depth * K1_THREADS * sizeof(float));
@@ -967,109 +963,6 @@ mesh_distance_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals, in
 }
 
 
-#if K1_TAIL_CLASSES
-// ---- heaviest-class-first launch order (K1_TAIL_CLASSES): see k1_sdf.h ---------------------------------------------------------------
-constexpr unsigned TAIL_TILE = 1024;               // blocks per warp in the counting / scatter passes
-__global__ void tail_lattice_points_kernel(GridDev g, double* __restrict__ pts)
-{
-    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned L = K1_TAIL_LATTICE;
-    if (idx >= L * L * L) return;
-    const unsigned ix = idx % L, iy = (idx / L) % L, iz = idx / (L * L);
-    pts[3 * idx + 0] = g.mn[0] + (g.mx[0] - g.mn[0]) * (((double)ix + 0.5) / (double)L);
-    pts[3 * idx + 1] = g.mn[1] + (g.mx[1] - g.mn[1]) * (((double)iy + 0.5) / (double)L);
-    pts[3 * idx + 2] = g.mn[2] + (g.mx[2] - g.mn[2]) * (((double)iz + 0.5) / (double)L);
-}
-// max of the (non-negative) lattice distances: the bit pattern of a non-negative double orders like the value
-__global__ void tail_lattice_max_kernel(const double* __restrict__ dist, unsigned long long* __restrict__ max_bits)
-{
-    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned L = K1_TAIL_LATTICE;
-    if (idx >= L * L * L) return;
-    const double d = dist[idx];
-    if (d >= 0.0 && d < 1.0e300) atomicMax(max_bits, (unsigned long long)__double_as_longlong(d));
-}
-// class of every block (0 = farthest from the surface = heaviest): lattice distance at the block's central node
-__global__ void tail_classify_kernel(GridDev g, K1Work w, unsigned n_blocks, const double* __restrict__ dist, const unsigned long long* __restrict__ max_bits,
-                                     unsigned char* __restrict__ cls)
-{
-    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_blocks) return;
-    int sg = 0;
-    for (int k = 1; k < 4; k++) if (k < w.nseg && b >= w.seg[k].block_begin) sg = k;
-    const K1Segment& S = w.seg[sg];
-    unsigned t = b - S.block_begin;
-    const unsigned tf = t % S.tiles_f; t /= S.tiles_f;
-    const unsigned tm = t % S.tiles_m; const unsigned ts = t / S.tiles_m;
-    unsigned f = tf * (SEG_BF(S) * (unsigned)(K1_THREADS / 32)) + (SEG_BF(S) * (unsigned)(K1_THREADS / 32)) / 2u;
-    unsigned m = tm * SEG_BM(S) + SEG_BM(S) / 2u;
-    unsigned sl = S.s0 + ts * S.pl_stride * SEG_BS(S) + SEG_BS(S) / 2u;
-    if (f >= S.Df) f = S.Df - 1; if (m >= S.Dm) m = S.Dm - 1; if (sl >= S.Ds) sl = S.Ds - 1;
-    unsigned i, j, k;
-    const unsigned fh = f >> 1;
-    if (S.kind == 0) { i = f; j = m; k = sl; }
-    else if (S.kind == 1) { i = fh; j = m; k = sl; }
-    else if (S.kind == 2) { i = sl; k = m; j = fh; }
-    else { j = sl; i = m; k = fh; }
-    const double p[3] = {g.mn[0] + g.cell[0] * (double)i, g.mn[1] + g.cell[1] * (double)j, g.mn[2] + g.cell[2] * (double)k};
-    const unsigned L = K1_TAIL_LATTICE;
-    unsigned li[3];
-    for (int d = 0; d < 3; d++) {
-        const double u = (p[d] - g.mn[d]) / (g.mx[d] - g.mn[d]) * (double)L;
-        li[d] = (u > 0.0) ? (unsigned)u : 0u;                       // NaN / negative -> 0
-        if (li[d] >= L) li[d] = L - 1;
-    }
-    const double dd = dist[(li[2] * L + li[1]) * L + li[0]];
-    const double dmax = __longlong_as_double((long long)*max_bits);
-    unsigned c = 0;                                                 // by distance: 0 = nearest
-    if (dmax > 0.0 && dd >= 0.0) { const double r = dd / dmax * (double)K1_TAIL_CLASSES; c = (r >= (double)K1_TAIL_CLASSES) ? (unsigned)K1_TAIL_CLASSES - 1u : (unsigned)r; }
-    cls[b] = (unsigned char)((unsigned)K1_TAIL_CLASSES - 1u - c);   // 0 = farthest
-}
-// blocks per class in every tile of TAIL_TILE blocks (one warp per tile): cnt[c * n_tiles + tile]
-__global__ void tail_tile_count_kernel(const unsigned char* __restrict__ cls, unsigned n_blocks, unsigned n_tiles, unsigned* __restrict__ cnt)
-{
-    const unsigned tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (tile >= n_tiles) return;
-    unsigned c_run[K1_TAIL_CLASSES];
-#pragma unroll
-    for (int c = 0; c < K1_TAIL_CLASSES; c++) c_run[c] = 0;
-    for (unsigned k = 0; k < TAIL_TILE; k += 32) {
-        const unsigned b = tile * TAIL_TILE + k + lane;
-        const int mine = (b < n_blocks) ? (int)cls[b] : -1;
-#pragma unroll
-        for (int c = 0; c < K1_TAIL_CLASSES; c++) c_run[c] += (unsigned)__popc(__ballot_sync(0xffffffffu, mine == c));
-    }
-    if (lane == 0) for (int c = 0; c < K1_TAIL_CLASSES; c++) cnt[(unsigned)c * n_tiles + tile] = c_run[c];
-}
-// exclusive scan of the (class-major) tile counts, in place: a few hundred entries, one thread
-__global__ void tail_scan_kernel(unsigned* __restrict__ cnt, unsigned n)
-{
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    unsigned run = 0;
-    for (unsigned i = 0; i < n; i++) { const unsigned c = cnt[i]; cnt[i] = run; run += c; }
-}
-// stable scatter: order[position] = block id, class by class, launch order kept inside a class
-__global__ void tail_scatter_kernel(const unsigned char* __restrict__ cls, unsigned n_blocks, unsigned n_tiles, const unsigned* __restrict__ off, unsigned* __restrict__ order)
-{
-    const unsigned tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (tile >= n_tiles) return;
-    unsigned run[K1_TAIL_CLASSES];
-#pragma unroll
-    for (int c = 0; c < K1_TAIL_CLASSES; c++) run[c] = off[(unsigned)c * n_tiles + tile];
-    const unsigned lt = (1u << lane) - 1u;
-    for (unsigned k = 0; k < TAIL_TILE; k += 32) {
-        const unsigned b = tile * TAIL_TILE + k + lane;
-        const int mine = (b < n_blocks) ? (int)cls[b] : -1;
-#pragma unroll
-        for (int c = 0; c < K1_TAIL_CLASSES; c++) {
-            const unsigned m = __ballot_sync(0xffffffffu, mine == c);
-            if (mine == c) order[run[c] + (unsigned)__popc(m & lt)] = b;
-            run[c] += (unsigned)__popc(m);
-        }
-    }
-}
-#endif
-
 __global__ void node_positions_kernel(GridDev g, unsigned l_begin, unsigned long long count, double* __restrict__ x)
 {
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1191,50 +1084,6 @@ static cudaError_t launch_sampling_wave(const DeviceBvh& m, const GridDev& g, co
 #endif
 }
 #define DG_LAUNCH_SAMPLING(m, g, w, blocks, sign, out, stream) return launch_sampling_wave((m), (g), (w), (blocks), (sign), (out), (stream))
-#elif K1_TAIL_CLASSES
-#ifdef DG_EMU
-#define DG_SCRATCH_ALLOC(ptr, bytes, stream) ((*(void**)(ptr) = std::malloc(bytes)) ? cudaSuccess : cudaErrorMemoryAllocation)
-#define DG_SCRATCH_FREE(p, stream) std::free(p)
-#define DG_SCRATCH_ZERO(p, bytes, stream) (std::memset((p), 0, (bytes)), cudaSuccess)
-#else
-#define DG_SCRATCH_ALLOC(ptr, bytes, stream) cudaMallocAsync((void**)(ptr), (bytes), (stream))
-#define DG_SCRATCH_FREE(p, stream) cudaFreeAsync((p), (stream))
-#define DG_SCRATCH_ZERO(p, bytes, stream) cudaMemsetAsync((p), 0, (bytes), (stream))
-#endif
-// the sampling launch with its blocks ordered heaviest class first (k1_sdf.h); small launches are not worth the six extra kernels
-static cudaError_t launch_sampling_tail_ordered(const DeviceBvh& m, const GridDev& g, const K1Work& w, unsigned blocks, double sign, double* d_out, cudaStream_t stream)
-{
-    const unsigned L3 = K1_TAIL_LATTICE * K1_TAIL_LATTICE * K1_TAIL_LATTICE;
-    unsigned* order = nullptr;
-    unsigned char* scratch = nullptr;
-    if (blocks >= (unsigned)K1_TAIL_MIN_BLOCKS) {
-        const unsigned n_tiles = (blocks + TAIL_TILE - 1) / TAIL_TILE;
-        // one stream-ordered allocation: points | distances | max | tile counts / offsets | order | classes
-        const size_t o_pts = 0, o_dist = o_pts + 3ull * L3 * 8, o_max = o_dist + (size_t)L3 * 8, o_cnt = o_max + 8, o_ord = o_cnt + 4ull * K1_TAIL_CLASSES * n_tiles,
-                     o_cls = o_ord + 4ull * blocks, total = o_cls + blocks;
-        cudaError_t e = DG_SCRATCH_ALLOC(&scratch, total, stream);
-        if (e != cudaSuccess) return e;
-        double* pts = reinterpret_cast<double*>(scratch + o_pts); double* dist = reinterpret_cast<double*>(scratch + o_dist);
-        unsigned long long* mx = reinterpret_cast<unsigned long long*>(scratch + o_max);
-        unsigned* cnt = reinterpret_cast<unsigned*>(scratch + o_cnt);
-        order = reinterpret_cast<unsigned*>(scratch + o_ord); unsigned char* cls = scratch + o_cls;
-        e = DG_SCRATCH_ZERO(scratch + o_max, 8, stream);
-        if (e != cudaSuccess) { DG_SCRATCH_FREE(scratch, stream); return e; }
-        DG_KERNEL_LAUNCH(tail_lattice_points_kernel, (L3 + 127) / 128, 128, 0, stream, g, pts);
-        DG_KERNEL_LAUNCH(mesh_distance_kernel, (L3 + K1_THREADS - 1) / K1_THREADS, K1_THREADS, k1_smem_bytes(m.stack_depth), stream, mesh_dev(m), m.normals, m.stack_depth,
-                         pts, (unsigned long long)L3, 0, dist, (double*)nullptr, (int*)nullptr, (int*)nullptr);
-        DG_KERNEL_LAUNCH(tail_lattice_max_kernel, (L3 + 127) / 128, 128, 0, stream, dist, mx);
-        DG_KERNEL_LAUNCH(tail_classify_kernel, (blocks + 127) / 128, 128, 0, stream, g, w, blocks, dist, mx, cls);
-        DG_KERNEL_LAUNCH(tail_tile_count_kernel, (n_tiles * 32 + 127) / 128, 128, 0, stream, cls, blocks, n_tiles, cnt);
-        DG_KERNEL_LAUNCH(tail_scan_kernel, 1, 32, 0, stream, cnt, (unsigned)K1_TAIL_CLASSES * n_tiles);
-        DG_KERNEL_LAUNCH(tail_scatter_kernel, (n_tiles * 32 + 127) / 128, 128, 0, stream, cls, blocks, n_tiles, cnt, order);
-    }
-    DG_KERNEL_LAUNCH(sdf_sample_nodes_kernel, blocks, K1_THREADS, k1_smem_bytes(m.stack_depth), stream, mesh_dev(m), m.normals, m.stack_depth, g, w, sign, d_out, order);
-    const cudaError_t e = DG_AFTER_LAUNCH();
-    if (scratch) DG_SCRATCH_FREE(scratch, stream);
-    return e;
-}
-#define DG_LAUNCH_SAMPLING(m, g, w, blocks, sign, out, stream) return launch_sampling_tail_ordered((m), (g), (w), (blocks), (sign), (out), (stream))
 #else
 #define DG_LAUNCH_SAMPLING(m, g, w, blocks, sign, out, stream) \
     DG_KERNEL_LAUNCH(sdf_sample_nodes_kernel, (blocks), K1_THREADS, k1_smem_bytes((m).stack_depth), (stream), mesh_dev(m), (m).normals, (m).stack_depth, (g), (w), (sign), (out)); \

@@ -75,21 +75,6 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 #define K1_MIN_BLOCKS (1024 / K1_THREADS_PER_BLOCK)   // blocks per SM the register allocation must allow (32 warps)
 #endif
 
-// K1_TAIL_CLASSES n > 0: a launch of the per-lane kernel takes its blocks heaviest class first.  A block lives 0.2 - 4 ms depending on how far
-// its queries are from the surface; in launch order the last-started blocks include long ones and the launch drains for ~3 ms with most SMs idle
-// (profiles/r2o_part_times.txt: an eighth of the 128^3 grid takes 12 - 14 ms instead of 9.3).  Before the sampling kernel, on the same stream:
-// unsigned distances on a 16^3 lattice (the query kernel itself), their maximum, a class per block from the lattice value at the block's
-// centre, and a STABLE counting sort by class (ballot scans per 1024-block tile, one small scan over the tile counts) -- within a class the
-// blocks keep their launch order, so neighbouring bricks still run together (round 1's unstable 32-class version lost that and 45 %).
-#ifndef K1_TAIL_CLASSES
-#define K1_TAIL_CLASSES 0
-#endif
-#ifndef K1_TAIL_LATTICE
-#define K1_TAIL_LATTICE 16         // lattice points per axis
-#endif
-#ifndef K1_TAIL_MIN_BLOCKS
-#define K1_TAIL_MIN_BLOCKS 4096    // smaller launches keep the plain order
-#endif
 // K1_WAVE 1: the node-loop kernel is the WAVEFRONT variant (k1_sdf.cu): persistent warps, a pool of K1_WAVE_SLOTS query slots per warp in
 // shared memory, per iteration the fullest phase is compacted onto the lanes by ballot.  0: the per-lane kernel (one query per lane).
 #ifndef K1_WAVE
