@@ -516,12 +516,12 @@ struct HostPathPool {
 HostPathPool g_pool;
 }  // namespace
 
-// the pipeline of the host-buffer path; the caller holds g_pool.mu.  copy_threads > 1: the copy from the pinned piece into the
-// caller's memory is split over that many threads (fresh pageable memory: the page faults, not the bytes, are the cost)
+// the pipeline of the host-buffer path; the caller holds g_pool.mu.  copier: the table workers of dg_add_function_sdf, which share the copies
+// from the pinned piece into the caller's memory with this thread (fresh pageable memory: page faults and remote NUMA nodes make a single
+// thread's copy the bottleneck on a loaded host); NULL: this thread copies alone
 namespace { struct HostTablesJob; }
 static void tables_job_copy(HostTablesJob* job, void* dst, const void* src, size_t bytes);
-static int sample_sdf_host_locked(const dg_mesh* m, const GridDev& g, double sign, uint64_t l_begin, uint64_t n, double* out_host, unsigned copy_threads,
-                                  HostTablesJob* copier = nullptr)
+static int sample_sdf_host_locked(const dg_mesh* m, const GridDev& g, double sign, uint64_t l_begin, uint64_t n, double* out_host, HostTablesJob* copier = nullptr)
 {
     // kernel chunks: a handful, each a multiple of the staging piece so that pieces never straddle chunks
     const uint64_t piece = HostPathPool::kPiece;
@@ -546,20 +546,8 @@ static int sample_sdf_host_locked(const dg_mesh* m, const GridDev& g, double sig
             const uint64_t off = (i - 1) * piece, cnt = (off + piece <= n) ? piece : n - off;
             DG_CUDA(cudaEventSynchronize(g_pool.dma_ev[(i - 1) & 1]));
             const double* src = g_pool.stage[(i - 1) & 1];
-            if (copier) {
-                tables_job_copy(copier, out_host + off, src, cnt * sizeof(double));
-            } else if (copy_threads > 1 && cnt >= (1u << 16)) {
-                std::vector<std::thread> th;
-                const uint64_t per = (cnt + copy_threads - 1) / copy_threads;
-                for (unsigned k = 1; k < copy_threads; k++) {
-                    const uint64_t b = k * per, e = std::min<uint64_t>(cnt, b + per);
-                    if (b < e) th.emplace_back([=]() { std::memcpy(out_host + off + b, src + b, (e - b) * sizeof(double)); });
-                }
-                std::memcpy(out_host + off, src, std::min<uint64_t>(cnt, per) * sizeof(double));
-                for (auto& t : th) t.join();
-            } else {
-                std::memcpy(out_host + off, src, cnt * sizeof(double));
-            }
+            if (copier) tables_job_copy(copier, out_host + off, src, cnt * sizeof(double));
+            else std::memcpy(out_host + off, src, cnt * sizeof(double));
         }
     }
     return DG_OK;
@@ -575,7 +563,7 @@ int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint6
     if (!out_host) return fail(DG_ERR_INVALID, "dg_sample_sdf: output is NULL");
     if (int rc = check_handle_device(m->device, "dg_sample_sdf")) return rc;
     std::lock_guard<std::mutex> lock(g_pool.mu);
-    return sample_sdf_host_locked(m, g, sign, l_begin, n, out_host, 1);
+    return sample_sdf_host_locked(m, g, sign, l_begin, n, out_host);
 }
 
 // Makes the pages of [p, p + bytes) present and writable WITHOUT changing their content (safe against a concurrent writer).
@@ -692,7 +680,7 @@ struct HostTablesJob {
             }
         }
     }
-    void start(const GridDev& g_, uint64_t n_nodes_, double* nodes_, uint32_t* cells_, uint32_t* cell_map_, unsigned reserve_threads)
+    void start(const GridDev& g_, uint64_t n_nodes_, double* nodes_, uint32_t* cells_, uint32_t* cell_map_)
     {
         g = g_; n_nodes = n_nodes_; n_cells = (uint64_t)g.n[0] * g.n[1] * g.n[2];
         nodes = nodes_; cells = cells_; cell_map = cell_map_;
@@ -706,7 +694,6 @@ struct HostTablesJob {
         // 2 workers -> the call ends 8 ms after the last kernel; 11 workers + 4 copy threads (= every CPU of the quota busy) -> 95 ms
         // later, because the bandwidth controller then throttles the thread that drives the GPU pipeline along with the rest.
         const unsigned hw = host_threads();
-        (void)reserve_threads;
         n_workers = std::max(1u, std::min(hw / 4u, 24u));
         try { for (unsigned k = 0; k < n_workers; k++) th.emplace_back([this]() { work(); serve_copies(); }); } catch (...) { /* fewer workers: finish() does the rest */ }
     }
@@ -740,13 +727,12 @@ int dg_add_function_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign,
     if (int rc = check_handle_device(m->device, "dg_add_function_sdf")) return rc;
     const auto t0 = std::chrono::steady_clock::now();
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
-    const unsigned copy_threads = 1;                   // the pages are pre-faulted by the workers: one thread copies a 32 MiB piece in ~3 ms
     HostTablesJob job;
-    job.start(g, n_nodes, nodes_host, cells_host, cell_map_host, copy_threads);
+    job.start(g, n_nodes, nodes_host, cells_host, cell_map_host);
     int rc;
     {
         std::lock_guard<std::mutex> lock(g_pool.mu);
-        rc = sample_sdf_host_locked(m, g, sign, 0, n_nodes, nodes_host, copy_threads, &job);
+        rc = sample_sdf_host_locked(m, g, sign, 0, n_nodes, nodes_host, &job);
     }
     const double ms_nodes = ms_since(t0);
     job.finish();
@@ -935,7 +921,7 @@ int dg_add_function_sdf_multi(dg_mesh_group* grp, const dg_grid_desc* grid, doub
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     const bool direct = is_pinned_host(nodes_host);
     HostTablesJob job;
-    job.start(g, n_nodes, nodes_host, cells_host, cell_map_host, (unsigned)n);
+    job.start(g, n_nodes, nodes_host, cells_host, cell_map_host);
     std::vector<int> rcs(n, DG_OK);
     std::vector<std::string> errs(n);
     std::vector<uint64_t> launches(n, 0);

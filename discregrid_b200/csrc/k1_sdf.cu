@@ -551,7 +551,9 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
     // blocks run in launch order.  Round 2 measured three ways of ending a launch with short walks instead (a launch of an eighth of the 128^3
     // grid takes 12 - 14 ms instead of 9.3: profiles/r2o): plane groups from the outside in, and a stable heaviest-class-first order from a
     // coarse distance lattice with 2 / 4 / 8 classes -- all slower (N = 1: 77.5 / 80.9 / 79.3 / 93.1 vs 74.9 ms; parts no better; r2m, r2p):
-    // neighbouring bricks running at the same time share tree nodes in L1, and that is worth more than a short drain.
+    // neighbouring bricks running at the same time share tree nodes in L1, and that is worth more than a short drain.  Enumerating the blocks
+    // super-tile by super-tile (4^3 / 8^3 / 16^3 blocks, a compact box of resident queries instead of four whole planes) changed nothing
+    // (74.4 - 74.9 ms; r2q): plane-by-plane order already shares what there is to share.
     const unsigned this_block = blockIdx.x;
     DG_EMU_TRACE_BLOCK(this_block);
     float* stack_d = reinterpret_cast<float*>(k1_smem);
