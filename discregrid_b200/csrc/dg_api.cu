@@ -61,6 +61,15 @@ int fail(int code, const char* fmt, ...)
     return code;
 }
 
+// C++ exceptions (allocation failures in the host-side containers and threads) must not cross the C boundary
+template <class F>
+int guarded(const char* who, F&& body)
+{
+    try { return body(); }
+    catch (const std::bad_alloc&) { return fail(DG_ERR_NOMEM, "%s: out of host memory", who); }
+    catch (const std::exception& ex) { return fail(DG_ERR_INVALID, "%s: %s", who, ex.what()); }
+}
+
 #define DG_CUDA(call)                                                                                    \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -705,6 +714,7 @@ struct HostTablesJob {
         for (auto& t : th) t.join();
         th.clear();
     }
+    ~HostTablesJob() { if (!th.empty()) finish(); }      // an early return of the caller must not leave joinable threads behind
 };
 }  // namespace
 
@@ -715,7 +725,7 @@ static void tables_job_copy(HostTablesJob* job, void* dst, const void* src, size
 // buffer), and -- while the GPU works -- the host threads write the 32-index connectivity table (:833-886) and the identity cell
 // map (:888-891) straight into the caller's memory and pre-fault the coefficient array, so that the call ends one D2H piece after
 // the last kernel chunk.
-int dg_add_function_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host, uint32_t* cell_map_host,
+static int dg_add_function_sdf_impl(const dg_mesh* m, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host, uint32_t* cell_map_host,
                         double* timings_ms)
 {
     if (!m) return fail(DG_ERR_INVALID, "dg_add_function_sdf: mesh is NULL (not constructed)");
@@ -827,7 +837,7 @@ int dg_mesh_group_destroy(dg_mesh_group* grp)
         for (int k = 0; k < 16; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
         if (d.d_buf) cudaFree(d.d_buf);
         if (d.h_stage) cudaFreeHost(d.h_stage);
-        if (i > 0) delete grp->parts[i];
+        if (i > 0 && (size_t)i < grp->parts.size()) delete grp->parts[i];
     }
     delete grp;
     return DG_OK;
@@ -895,7 +905,7 @@ int dg_mesh_group_size(const dg_mesh_group* grp) { return grp ? grp->n : 0; }
 // GPU's first part runs under its second launch); each GPU is driven by its own host thread and DMAs the contiguous plane-pair runs
 // of its parts to their final positions (directly when nodes_host is page-locked, else through pinned staging).  No collective is
 // needed: the exchange target is host memory.  cells_host / cell_map_host as in dg_add_function_sdf (nullable).
-int dg_add_function_sdf_multi(dg_mesh_group* grp, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host,
+static int dg_add_function_sdf_multi_impl(dg_mesh_group* grp, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host,
                               uint32_t* cell_map_host, double* timings_ms)
 {
     if (!grp) return fail(DG_ERR_INVALID, "dg_add_function_sdf_multi: group is NULL");
@@ -952,9 +962,12 @@ int dg_add_function_sdf_multi(dg_mesh_group* grp, const dg_grid_desc* grid, doub
     {
         DeviceGuard guard;
         std::vector<std::thread> th;
-        for (int i = 1; i < n; i++) th.emplace_back([&, i]() { DeviceGuard tg; rcs[i] = drive(i); if (rcs[i] != DG_OK) errs[i] = g_err; });
-        rcs[0] = drive(0);
-        if (rcs[0] != DG_OK) errs[0] = g_err;
+        auto guarded = [&](int i) {
+            try { rcs[i] = drive(i); if (rcs[i] != DG_OK) errs[i] = g_err; }
+            catch (const std::exception& ex) { rcs[i] = DG_ERR_NOMEM; errs[i] = ex.what(); }
+        };
+        for (int i = 1; i < n; i++) th.emplace_back([&, i]() { DeviceGuard tg; guarded(i); });
+        guarded(0);
         for (auto& t : th) t.join();
     }
     const double ms_nodes = ms_since(t0);
@@ -1337,7 +1350,7 @@ void threaded_copy(void* dst, const void* src, size_t bytes, unsigned nt)
 }
 }  // namespace
 
-int dg_interpolate_batch(const dg_field* f, const double* x, uint64_t n, double* phi, double* grad)
+static int dg_interpolate_batch_impl(const dg_field* f, const double* x, uint64_t n, double* phi, double* grad)
 {
     if (!f) return fail(DG_ERR_INVALID, "dg_interpolate_batch: field is NULL");
     if (n == 0) return DG_OK;
@@ -1487,7 +1500,7 @@ static int reduce_field_gpu(const GridDev& g, double* nodes, uint64_t n_nodes, c
     return DG_OK;
 }
 
-int dg_reduce_field(const dg_grid_desc* grid, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
+static int dg_reduce_field_impl(const dg_grid_desc* grid, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
                     uint32_t* cell_map, uint32_t flags, uint64_t* n_nodes_out, uint64_t* n_cells_out, double* timings_ms)
 {
     GridDev g; const char* why = "";
@@ -1533,6 +1546,31 @@ int dg_obj_read(const char* path, double** vertices, uint64_t* n_vertices, uint3
 void dg_obj_free(double* vertices, uint32_t* triangles)
 {
     std::free(vertices); std::free(triangles);
+}
+
+
+// ---- entry points whose bodies use host containers / threads: exceptions are turned into status codes
+int dg_add_function_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host, uint32_t* cell_map_host,
+                        double* timings_ms)
+{
+    return guarded("dg_add_function_sdf", [&]() { return dg_add_function_sdf_impl(m, grid, sign, nodes_host, cells_host, cell_map_host, timings_ms); });
+}
+
+int dg_add_function_sdf_multi(dg_mesh_group* grp, const dg_grid_desc* grid, double sign, double* nodes_host, uint32_t* cells_host,
+                              uint32_t* cell_map_host, double* timings_ms)
+{
+    return guarded("dg_add_function_sdf_multi", [&]() { return dg_add_function_sdf_multi_impl(grp, grid, sign, nodes_host, cells_host, cell_map_host, timings_ms); });
+}
+
+int dg_interpolate_batch(const dg_field* f, const double* x, uint64_t n, double* phi, double* grad)
+{
+    return guarded("dg_interpolate_batch", [&]() { return dg_interpolate_batch_impl(f, x, n, phi, grad); });
+}
+
+int dg_reduce_field(const dg_grid_desc* grid, double* nodes, uint64_t n_nodes, const uint8_t* keep_node, uint32_t* cells, uint64_t n_cells_in,
+                    uint32_t* cell_map, uint32_t flags, uint64_t* n_nodes_out, uint64_t* n_cells_out, double* timings_ms)
+{
+    return guarded("dg_reduce_field", [&]() { return dg_reduce_field_impl(grid, nodes, n_nodes, keep_node, cells, n_cells_in, cell_map, flags, n_nodes_out, n_cells_out, timings_ms); });
 }
 
 }  // extern "C"
