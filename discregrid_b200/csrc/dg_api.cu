@@ -1361,7 +1361,7 @@ static int dg_interpolate_batch_impl(const dg_field* f, const double* x, uint64_
     const uint64_t chunk = std::min<uint64_t>(InterpPool::kChunk, n);
     const bool x_direct = is_pinned_host(x), out_direct = is_pinned_host(phi) && is_pinned_host(grad);
     DG_CUDA(g_ipool.prepare(std::max<uint64_t>(chunk, g_ipool.cap), !x_direct, !out_direct));
-    const unsigned nt = std::max(1u, std::min(8u, host_threads() / 2));
+    const unsigned nt = std::max(1u, std::min(4u, host_threads() / 4));      // copy threads of the staged (pageable) path, started per chunk
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     auto unstage = [&](uint64_t c) {                      // results of chunk c: pinned staging -> caller memory
         const uint64_t off = c * chunk, cnt = std::min(chunk, n - off);
