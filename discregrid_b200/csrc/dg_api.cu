@@ -325,7 +325,7 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     const auto t0 = std::chrono::steady_clock::now();
     const char* why = "";
     try {
-        if (!build_host_bvh(V, nV, F, nT, m->host, &why, K1_LEAF_FILTER != 0)) { delete m; return fail(DG_ERR_INVALID, "dg_mesh_create: %s", why); }
+        if (!build_host_bvh(V, nV, F, nT, m->host, &why, K1_NEEDS_LEAF_SHADOW != 0)) { delete m; return fail(DG_ERR_INVALID, "dg_mesh_create: %s", why); }
     } catch (const std::bad_alloc&) { delete m; return fail(DG_ERR_NOMEM, "dg_mesh_create: out of host memory"); }
     const auto t1 = std::chrono::steady_clock::now();
     m->build_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
@@ -337,7 +337,7 @@ int dg_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t nT,
     DG_CUDA_M(m->d_leaves.alloc(nT));
     DG_CUDA_M(m->d_normals.alloc(nT));
     DG_CUDA_M(m->d_nodes_f.alloc(nT * K1_NODEF_STRIDE));
-#if K1_LEAF_FILTER
+#if K1_NEEDS_LEAF_SHADOW
     DG_CUDA_M(m->d_leaves_f.alloc(nT));
     DG_CUDA_M(cudaMemcpy(m->d_leaves_f.p, m->host.leaves_f.data(), nT * sizeof(LeafF), cudaMemcpyHostToDevice));
     m->dev.leaves_f = m->d_leaves_f.p;
@@ -887,7 +887,7 @@ int dg_mesh_group_create(const dg_mesh* mesh, int n_gpus, const int* devices, dg
         DG_CUDA(cudaMemcpyPeer(r->d_nodes_f.p, r->device, mesh->d_nodes_f.p, mesh->device, nT * K1_NODEF_STRIDE * sizeof(float4)));
         r->dev = mesh->dev;
         r->dev.spheres = r->d_spheres.p; r->dev.leaves = r->d_leaves.p; r->dev.normals = r->d_normals.p; r->dev.nodes_f = r->d_nodes_f.p;
-#if K1_LEAF_FILTER
+#if K1_NEEDS_LEAF_SHADOW
         DG_CUDA(r->d_leaves_f.alloc(nT));
         DG_CUDA(cudaMemcpyPeer(r->d_leaves_f.p, r->device, mesh->d_leaves_f.p, mesh->device, nT * sizeof(LeafF)));
         r->dev.leaves_f = r->d_leaves_f.p;

@@ -533,6 +533,267 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
     return res;
 }
 
+#if K1_PACKET
+// =====================================================================================================================================
+// PACKET TRAVERSAL (K1_PACKET): the 32 queries of a brick walk the tree TOGETHER -- one node per step for all lanes, one shared order
+// (majority of the lanes that still want the node), one stack -- and the reference's ORDER-DEPENDENT result is reconstructed afterwards.
+//
+// Why this is admissible although _query's result depends on each query's own visit order (file header): the order only matters among the
+// handful of triangles whose d2 lies within a few ulps of the minimum.  Write v_T for the d2 the reference computes for triangle T (a pure
+// function of T and the query: tri_dist2), D(v) = fl(sqrt(v)), g(v) = fl(D(v) * D(v)).  The reference accepts T in state v' iff v_T < g(v')
+// (:528) and g(v') lies in [v'(1 - 3 eps), v'(1 + 3 eps)].  Let m be the smallest v_T over ALL triangles and C the closure of {m} under
+// "x <= c (1 + 2^-49) for some c in C" (a chain of values a few ulps apart).  If every other triangle has v > cmax (1 + 2^-49), then
+//   (i)  a state outside C accepts every member of C (g(v') > cmax), a state inside C never accepts anything outside C, so the reference's
+//        final state is the fold of C's members alone, in the reference's order, the first of them accepted unconditionally;
+//   (ii) the reference does visit every member T of C provided none of T's ancestors n fails `d_n < result.distance` (:545-557) for the
+//        smallest state that can ever occur, D(m): certified here by  max over ancestors (fp32 sphere distance + E)  <  best_lo;
+//   (iii) the reference's order of two visited leaves is decided at their lowest common ancestor by `d_left < d_right` (:542), evaluated
+//        here in fp64 exactly as the reference does (ref_visits_first).
+// So the packet walk only has to (a) evaluate, with the reference's own fp64 leaf test, every triangle whose v could be <= m (1 + 1e-6)
+// -- subtrees and leaves are dropped only by the CERTIFIED fp32 bounds of the box skip (true distance > best_hi + 2E  =>  v > m (1 + 2e-6),
+// error budget at K1_BOX_SKIP above) -- (b) keep the K1_PKT_K smallest values near the minimum with their leaf position and ancestor
+// certificate, plus the smallest value it did not keep, (c) form C, check (i) and (ii), order C by (iii) and replay the reference's
+// accept rule.  A lane for which any check fails (on-surface queries below tiny_best, more than K1_PKT_K near-ties, a sphere that is tight
+// to within E, non-finite input) is walked again by nearest_triangle() -- the per-lane reference-order traversal above -- so the result is
+// the reference's in every case; the checks decide only how fast it is obtained.
+// =====================================================================================================================================
+#ifndef K1_PKT_K
+#define K1_PKT_K 8
+#endif
+
+// does the reference reach leaf position pa before leaf position pb (pa != pb, both visited)?
+#ifdef DG_EMU
+#define DG_NOINLINE
+#else
+#define DG_NOINLINE __noinline__
+#endif
+__device__ DG_NOINLINE bool ref_visits_first(const SpherePair* __restrict__ spheres, int n_tri, int pa, int pb, double px, double py, double pz)
+{
+    int b = 0, e = n_tri;
+    for (;;) {
+        const int m = (b + e) >> 1;
+        const bool al = pa < m, bl = pb < m;
+        if (al != bl) {
+            const double* sp8 = reinterpret_cast<const double*>(spheres + m);
+            const double2 a0 = ldg2(sp8), a1 = ldg2(sp8 + 2), a2 = ldg2(sp8 + 4), a3 = ldg2(sp8 + 6);
+            const double d_left = sphere_dist(px, py, pz, a0.x, a0.y, a1.x, a1.y);      // :539
+            const double d_right = sphere_dist(px, py, pz, a2.x, a2.y, a3.x, a3.y);     // :540
+            return al == (d_left < d_right);                                            // :542
+        }
+        if (al) e = m; else b = m;
+    }
+}
+
+__device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M, bool alive, double px, double py, double pz,
+                                                               unsigned* stack_rng, float* stack_pm, double* cv, int* cpos, float* cpm, int stride)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int n_tri = M.n_tri;
+    const float INF = __int_as_float(0x7f800000);
+    const double DINF = (double)INF;
+    QueryResult res;
+    res.dist = DBL_MAX; res.s = 0; res.t = 0; res.pos = -1; res.entity = 0;
+    const float qx = (float)(px - M.cx), qy = (float)(py - M.cy), qz = (float)(pz - M.cz);
+    const float Mq = fmaxf(fmaxf(M.half_extent, fabsf(qx)), fmaxf(fabsf(qy), fabsf(qz)));
+    const float E = __fmul_ru(Mq, 3.814697265625e-06f), E2 = E + E;        // as in nearest_triangle
+    const float tiny_best = 1.0e-6f * Mq;
+    bool need_fb = false;
+    bool act = alive;                                   // lane still takes part in the shared walk
+    if (alive && (!(Mq < 1.0e18f) || !(qx == qx) || !(qy == qy) || !(qz == qz) || n_tri < 2)) { need_fb = true; act = false; }
+    float skip_lin = INF, skip_sq = INF, best_lo = INF;
+    double dropped = DINF;                              // smallest evaluated value that is NOT in the list
+    int cnt = 0;                                        // list: cv[0] <= cv[1] <= ... (stride apart), all within 1e-6 of the minimum when inserted
+    float pm = -INF;                                    // max over the ancestors on the current path of (fp32 sphere distance + E)
+    int b = 0, e = n_tri, depth = 0, sp = 0;            // warp-uniform
+    bool have = true;
+    for (;;) {
+        if (!have) {
+            if (sp == 0) break;
+            sp--;
+            DG_EMU_COUNT(16);
+            const unsigned r = stack_rng[sp * stride];
+            const int rb = (int)(r & 0x01ffffffu), rd = (int)((r >> 25) & 31u);
+            const int re = rb + (n_tri >> rd) + (int)((r >> 30) & 1u);
+            const bool is_left = (r >> 31) != 0u;
+            const float4* f4 = M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE;
+            const float4 s4 = __ldg(f4 + (is_left ? 0 : 1));
+            const float4 u = __ldg(f4 + (is_left ? 2 : 3)), v = __ldg(f4 + (is_left ? 3 : 4));
+            const float lox = is_left ? u.x : u.z, loy = is_left ? u.y : u.w, loz = is_left ? u.z : v.x;
+            const float hix = is_left ? u.w : v.y, hiy = is_left ? v.x : v.z, hiz = is_left ? v.y : v.w;
+            const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
+            const float box2 = __fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx)));
+            const float sx = qx - s4.x, sy = qy - s4.y, sz = qz - s4.z;
+            const float df = sqrt_approx(fmaf(sz, sz, fmaf(sy, sy, sx * sx))) - s4.w;
+            const bool want = act && !(df - E > skip_lin) && !(box2 > skip_sq);
+            if (!__any_sync(FULL, want)) continue;
+            DG_EMU_COUNT(17);
+            b = rb; e = re; depth = rd; pm = stack_pm[sp * stride];
+            have = true;
+        }
+        if (e - b == 1) {
+            // ---- leaf: certified fp32 lower bound for all lanes, the reference's fp64 test for the lanes it cannot rule out
+            DG_EMU_COUNT(18);
+            const float lb = leaf_lower_bound(M.leaves_f + b, qx, qy, qz, E);
+            const bool pass = act && !(lb > skip_lin);
+            if (__any_sync(FULL, pass)) {
+                DG_EMU_COUNT(19);
+                if (pass) {
+                    DG_EMU_COUNT(20);
+                    double s, t; int ent;
+                    const double x = tri_dist2(M.leaves + b, px, py, pz, s, t, ent);
+                    const double v0 = cnt ? cv[0] : DINF;
+                    bool insert = false;
+                    if (x < v0) {
+                        if (!(v0 <= x + x * 1e-6)) {                    // clear improvement (or empty list): the list restarts
+                            dropped = fmin(dropped, v0);
+                            cnt = 1; cv[0] = x; cpos[0] = b; cpm[0] = pm;
+                        } else insert = true;
+                        const double best = sqrt(x);
+                        best_lo = __double2float_rd(best);
+                        const float th = __fadd_ru(__double2float_ru(best), E2);
+                        if (best_lo >= tiny_best) { skip_lin = th; skip_sq = __fmul_ru(th, th); }
+                        else { need_fb = true; act = false; }           // practically on the surface: no certified pruning possible
+                    } else if (x <= v0 + v0 * 1e-6) insert = true;
+                    else dropped = fmin(dropped, x);                    // NaN falls through: never accepted by the reference either
+                    if (insert) {
+                        int i = cnt;
+                        bool room = true;
+                        if (cnt == K1_PKT_K) {
+                            const double last = cv[(K1_PKT_K - 1) * stride];
+                            if (x < last) { dropped = fmin(dropped, last); i = K1_PKT_K - 1; }
+                            else { dropped = fmin(dropped, x); room = false; }
+                        } else cnt++;
+                        if (room) {
+                            while (i > 0 && x < cv[(i - 1) * stride]) {
+                                cv[i * stride] = cv[(i - 1) * stride]; cpos[i * stride] = cpos[(i - 1) * stride]; cpm[i * stride] = cpm[(i - 1) * stride];
+                                i--;
+                            }
+                            cv[i * stride] = x; cpos[i * stride] = b; cpm[i * stride] = pm;
+                        }
+                    }
+                }
+            }
+            have = false;
+            continue;
+        }
+        // ---- internal node: both children's certified bounds for all lanes
+        DG_EMU_COUNT(21);
+        const int m = (b + e) >> 1;
+        const float4* f4 = M.nodes_f + (size_t)m * K1_NODEF_STRIDE;
+        const float4 l4 = __ldg(f4), r4 = __ldg(f4 + 1);
+        const float4 b0 = __ldg(f4 + 2), b1 = __ldg(f4 + 3), b2 = __ldg(f4 + 4);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
+        const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
+        const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
+        const float dl = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) - l4.w;
+        const float dr = sqrt_approx(fmaf(rz, rz, fmaf(ry, ry, rx * rx))) - r4.w;
+        const float lgx = fmaxf(fmaxf(b0.x - qx, qx - b0.w), 0.f), lgy = fmaxf(fmaxf(b0.y - qy, qy - b1.x), 0.f), lgz = fmaxf(fmaxf(b0.z - qz, qz - b1.y), 0.f);
+        const float rgx = fmaxf(fmaxf(b1.z - qx, qx - b2.y), 0.f), rgy = fmaxf(fmaxf(b1.w - qy, qy - b2.z), 0.f), rgz = fmaxf(fmaxf(b2.x - qz, qz - b2.w), 0.f);
+        const float l2 = __fmaf_rd(lgz, lgz, __fmaf_rd(lgy, lgy, __fmul_rd(lgx, lgx)));
+        const float r2 = __fmaf_rd(rgz, rgz, __fmaf_rd(rgy, rgy, __fmul_rd(rgx, rgx)));
+        const bool wl = act && !(dl - E > skip_lin) && !(l2 > skip_sq);
+        const bool wr = act && !(dr - E > skip_lin) && !(r2 > skip_sq);
+        const unsigned ml = __ballot_sync(FULL, wl), mr = __ballot_sync(FULL, wr);
+        if ((ml | mr) == 0u) { have = false; continue; }
+        const unsigned pl = __ballot_sync(FULL, (wl || wr) && (dl < dr));
+        const bool left_first = 2 * __popc(pl) >= __popc(ml | mr);
+        depth++;
+        const unsigned m1 = left_first ? ml : mr, m2 = left_first ? mr : ml;
+        const float d1u = __fadd_ru(left_first ? dl : dr, E), d2u = __fadd_ru(left_first ? dr : dl, E);
+        if (m1) {
+            if (m2) {
+                stack_rng[sp * stride] = left_first ? pack_range(m, e, depth, n_tri, false) : pack_range(b, m, depth, n_tri, true);
+                stack_pm[sp * stride] = fmaxf(pm, d2u);
+                sp++;
+            }
+            pm = fmaxf(pm, d1u);
+            if (left_first) e = m; else b = m;
+        } else {
+            pm = fmaxf(pm, d2u);
+            if (left_first) b = m; else e = m;
+        }
+    }
+    // ---- the closure C of the minimum, the checks (i) (ii), the reference's order (iii) and its accept rule
+    bool ok = alive && !need_fb;
+    if (ok && cnt == 0) { need_fb = true; ok = false; }
+    int win = -1; double D = DBL_MAX;
+    int ncmp = 0; (void)ncmp;
+    if (ok) {
+        const double EPSC = 1.7763568394002505e-15;     // 2^-49
+        const double v0 = cv[0];
+        double cmax = v0; int nC = 1;
+        while (nC < cnt) { const double nx = cv[nC * stride]; if (nx <= cmax + cmax * EPSC) { cmax = nx; nC++; } else break; }
+        bool good = (dropped > cmax + cmax * EPSC) && (cmax <= v0 + v0 * 1e-7);
+        for (int i = 0; i < nC; i++) good = good && (cpm[i * stride] < best_lo);
+        if (!good) { need_fb = true; ok = false; }
+        else if (nC == 1) { win = cpos[0]; D = sqrt(v0); }
+        else {
+            // order-free shortcut: with g monotone, "v1 >= g(v0)" means no member can displace the minimum once it is the state, and
+            // "v0 < g(v1)" means the minimum is accepted from every other member's state: the fold ends at cv[0] whatever the order
+            const double D0 = sqrt(v0), v1 = cv[stride], D1 = sqrt(v1);
+            if (v1 >= D0 * D0 && v0 < D1 * D1) { win = cpos[0]; D = D0; }
+            else {
+            // tie shortcut: the k members equal to the minimum, every other member neither able to displace that state (v >= g(v0)) nor
+            // to refuse it (v0 < g(v), monotone: checked on the smallest of them).  The state enters the tie group at its first member in
+            // the reference's order and then moves on at every further member iff v0 < g(v0): winner = first or last of the group.
+            int k = 1;
+            while (k < nC && cv[k * stride] == v0) k++;
+            bool tie_case = true;
+            if (k < nC) { const double vk = cv[k * stride], Dk = sqrt(vk); tie_case = (vk >= D0 * D0) && (v0 < Dk * Dk); }
+            if (tie_case) {
+                DG_EMU_COUNT(26); DG_EMU_ADD(27, k - 1);
+                const bool want_last = v0 < D0 * D0;
+                int w = cpos[0];
+                for (int i = 1; i < k; i++) {
+                    const int p = cpos[i * stride];
+                    ncmp++;
+                    if (ref_visits_first(M.spheres, n_tri, p, w, px, py, pz) != want_last) w = p;
+                }
+                win = w; D = D0;
+            } else {
+            DG_EMU_COUNT(22);
+            for (int i = 1; i < nC; i++) {              // insertion sort of C by the reference's visit order
+                const double x = cv[i * stride]; const int p = cpos[i * stride];
+                int j = i;
+                while (j > 0 && (ncmp++, ref_visits_first(M.spheres, n_tri, p, cpos[(j - 1) * stride], px, py, pz))) {
+                    DG_EMU_COUNT(23);
+                    cv[j * stride] = cv[(j - 1) * stride]; cpos[j * stride] = cpos[(j - 1) * stride];
+                    j--;
+                }
+                cv[j * stride] = x; cpos[j * stride] = p;
+            }
+            double thr = DINF;                          // result.distance = max(): max() * max() = +inf (:528)
+            for (int i = 0; i < nC; i++) {
+                const double x = cv[i * stride];
+                if (x < thr) { win = cpos[i * stride]; D = sqrt(x); thr = D * D; }
+            }
+            }
+            }
+        }
+    }
+#ifdef DG_EMU
+    {   // emulation only: the warp pays for its slowest lane -- max over lanes of the comparator calls
+        int mx = 0;
+        for (int bit = 5; bit >= 0; bit--) { const unsigned msk = __ballot_sync(FULL, ncmp >= (mx | (1 << bit))); if (msk) mx |= 1 << bit; }
+        if ((threadIdx.x & 31u) == 0u) DG_EMU_ADD(28, mx);
+    }
+#endif
+    if (__any_sync(FULL, ok)) {
+        if (ok) {                                       // (s, t, entity) of the winner: the same function of (T, query) the reference stored at :529-530
+            double s, t; int ent;
+            (void)tri_dist2(M.leaves + win, px, py, pz, s, t, ent);
+            res.dist = D; res.s = s; res.t = t; res.pos = win; res.entity = ent;
+        }
+    }
+    if (__any_sync(FULL, need_fb)) {                    // the lanes the checks could not clear: the per-lane reference-order walk
+        DG_EMU_COUNT(24);
+        DG_EMU_ADD(25, need_fb ? 1 : 0);
+        const QueryResult r2 = nearest_triangle(M, need_fb, px, py, pz, stack_rng, stack_pm, stride);
+        if (need_fb) res = r2;
+    }
+    return res;
+}
+#endif  // K1_PACKET
+
 #ifdef DG_EMU
 extern unsigned char k1_smem[];                    // defined by the emulation TU (one block runs at a time)
 #else
@@ -598,7 +859,15 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
     else if (S.kind == 2) py = py + fr * g.cell[1];
     else if (S.kind == 3) pz = pz + fr * g.cell[2];
 
+#if K1_PACKET
+    double* cand_v = reinterpret_cast<double*>(k1_smem + (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)));
+    int* cand_pos = reinterpret_cast<int*>(cand_v + (size_t)K1_PKT_K * K1_THREADS);
+    float* cand_pm = reinterpret_cast<float*>(cand_pos + (size_t)K1_PKT_K * K1_THREADS);
+    const QueryResult r = nearest_triangle_packet(mesh, alive, px, py, pz, stack_rng + threadIdx.x, stack_d + threadIdx.x,
+                                                  cand_v + threadIdx.x, cand_pos + threadIdx.x, cand_pm + threadIdx.x, K1_THREADS);
+#else
     const QueryResult r = nearest_triangle(mesh, alive, px, py, pz, stack_rng + threadIdx.x, stack_d + threadIdx.x, K1_THREADS);
+#endif
     if (!alive) return;
     double dist, qx, qy, qz; int tri;
     finish_query(mesh.leaves, normals, r, px, py, pz, true, dist, qx, qy, qz, tri);
@@ -1005,7 +1274,14 @@ __global__ void __launch_bounds__(256) fp64_rate_probe_kernel(double a, double b
 
 }  // namespace
 
-static inline size_t k1_smem_bytes(int stack_depth) { return (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)); }
+static inline size_t k1_smem_bytes(int stack_depth)
+{
+    size_t n = (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned));
+#if K1_PACKET
+    n += (size_t)K1_PKT_K * K1_THREADS * (sizeof(double) + sizeof(int) + sizeof(float));       // candidate lists of the packet walk
+#endif
+    return n;
+}
 static inline MeshDev mesh_dev(const DeviceBvh& m)
 {
     return MeshDev{m.spheres, m.nodes_f, m.leaves_f, m.leaves, m.ctr[0], m.ctr[1], m.ctr[2], m.half_extent, m.n_tri};

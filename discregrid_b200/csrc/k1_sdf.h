@@ -75,6 +75,13 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 #define K1_MIN_BLOCKS (1024 / K1_THREADS_PER_BLOCK)   // blocks per SM the register allocation must allow (32 warps)
 #endif
 
+// K1_PACKET 1: the 32 queries of a brick walk the tree together (one shared order, certified fp32 pruning) and the reference's
+// order-dependent accept rule is replayed on the few near-minimum triangles afterwards; lanes whose checks fail are walked again per lane
+// (k1_sdf.cu, nearest_triangle_packet).  K1_PKT_K = near-minimum candidates kept per query.
+#ifndef K1_PACKET
+#define K1_PACKET 0
+#endif
+#define K1_NEEDS_LEAF_SHADOW (K1_LEAF_FILTER || K1_PACKET)     // the fp32 triangle shadows (LeafF) are built and uploaded
 // K1_WAVE 1: the node-loop kernel is the WAVEFRONT variant (k1_sdf.cu): persistent warps, a pool of K1_WAVE_SLOTS query slots per warp in
 // shared memory, per iteration the fullest phase is compacted onto the lanes by ballot.  0: the per-lane kernel (one query per lane).
 #ifndef K1_WAVE

@@ -149,6 +149,7 @@ inline void launch(unsigned grid, unsigned block, size_t /*smem*/, const std::fu
 #define gridDim dg_emu::g_gridDim
 
 inline unsigned __ballot_sync(unsigned, int pred) { dg_emu::collective_wait(pred ? 1u : 0u); return dg_emu::g_warp->result_ballot; }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 inline unsigned __reduce_add_sync(unsigned, unsigned v) { dg_emu::collective_wait(v); return dg_emu::g_warp->result_sum; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

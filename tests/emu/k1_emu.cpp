@@ -36,7 +36,7 @@ void* emu_mesh_create(const double* V, uint64_t nV, const uint32_t* F, uint64_t 
 {
     auto* m = new EmuMesh();
     const char* err = "";
-    if (!build_host_bvh(V, nV, F, nT, m->host, &err, K1_LEAF_FILTER != 0)) { std::fprintf(stderr, "emu_mesh_create: %s\n", err); delete m; return nullptr; }
+    if (!build_host_bvh(V, nV, F, nT, m->host, &err, K1_NEEDS_LEAF_SHADOW != 0)) { std::fprintf(stderr, "emu_mesh_create: %s\n", err); delete m; return nullptr; }
     // the interleaved fp32 node record, as dg_mesh_create lays it out
     m->nodes_f.assign((size_t)nT * K1_NODEF_STRIDE, make_float4(0.f, 0.f, 0.f, 0.f));
     pack_node_records(m->host, K1_NODEF_STRIDE, reinterpret_cast<float*>(m->nodes_f.data()));

@@ -11,8 +11,8 @@ import pytest
 from conftest import GOLDEN, ROOT, bits_equal, grid_for
 from test_oracle_golden import read_cdf, read_obj
 
-# default knobs, the knob variants (K1_VOTE_REDUX + K1_BRICK_AUTO), the wavefront kernel and the per-lane kernel; DG_K1_EMU_LIB adds any other build of tests/emu/k1_emu.cpp
-LIBS = [os.path.join(ROOT, "build", "bin", n) for n in ("libk1emu.so", "libk1emu_knobs.so", "libk1emu_wave.so", "libk1emu_perlane.so")] + \
+# default knobs, the knob variants (K1_VOTE_REDUX + K1_BRICK_AUTO), the wavefront kernel, the per-lane kernel and the packet walk (K1_PACKET); DG_K1_EMU_LIB adds any other build of tests/emu/k1_emu.cpp
+LIBS = [os.path.join(ROOT, "build", "bin", n) for n in ("libk1emu.so", "libk1emu_knobs.so", "libk1emu_wave.so", "libk1emu_perlane.so", "libk1emu_packet.so")] + \
        ([os.environ["DG_K1_EMU_LIB"]] if os.environ.get("DG_K1_EMU_LIB") else [])
 _dp, _u32p, _i32p, _u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
 
@@ -191,6 +191,21 @@ def test_tie_rich_fuzz_against_reference_header():
     if not os.path.exists(REF_SO) or not os.path.exists(so):
         pytest.skip("needs oracle/_ref/libdgref.so and build/bin/libk1emu.so")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k1_fuzz.py"), "42", "7", so], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["libk1emu.so", "libk1emu_packet.so"])
+def test_tie_rich_grid_fuzz_node_loop_against_reference_header(name):
+    """tools/k1_fuzz.py in grid mode: the addFunction node loop (bricks of lattice nodes; for libk1emu_packet.so the packet walk with its
+    tie replay, certificates and per-lane fallback) on half-integer lattices through coplanar grids, cubes, octahedra, duplicated triangles,
+    slivers and random soups == sign * the reference header's signed distance at the node positions, bit for bit"""
+    import subprocess
+    import sys
+    from oracle_api import REF_SO
+    so = os.path.join(ROOT, "build", "bin", name)
+    if not os.path.exists(REF_SO) or not os.path.exists(so):
+        pytest.skip("needs oracle/_ref/libdgref.so and build/bin/" + name)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k1_fuzz.py"), "21", "11", so, "grid"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 

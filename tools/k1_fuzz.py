@@ -2,7 +2,10 @@
 """Parity fuzzer (CPU): the product's K1 kernel code run by tests/emu (build/bin/libk1emu*.so) against the reference's own
 TriangleMeshDistance.h (oracle/_ref/libdgref.so) on meshes built to provoke exact ties and awkward arithmetic -- regular grids of coplanar
 triangles, cubes / octahedra with queries on symmetry planes, duplicated triangles, slivers, lattice-aligned queries -- signed and unsigned,
-distance bits, nearest point, entity and triangle id.  usage: tools/k1_fuzz.py [rounds=200] [seed=0] [lib=libk1emu.so]"""
+distance bits, nearest point, entity and triangle id.  usage: tools/k1_fuzz.py [rounds=200] [seed=0] [lib=libk1emu.so] [points|grid]
+mode `grid` runs the addFunction NODE LOOP (sdf_sample_nodes_kernel: bricks of lattice nodes, the packet walk when built with K1_PACKET) on
+lattices laid over the same meshes -- half-integer lattices through the symmetric ones -- and compares sign * distance bit for bit with the
+reference header evaluated at the node positions."""
 import ctypes as C, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,12 +14,15 @@ from oracle_api import RefMesh
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 so = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "build", "bin", "libk1emu.so")
+mode = sys.argv[4] if len(sys.argv) > 4 else "points"
 lib = C.CDLL(so)
 dp, u32p, i32p = C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
 lib.emu_mesh_create.restype = C.c_void_p
 lib.emu_mesh_create.argtypes = [dp, C.c_uint64, u32p, C.c_uint64]
 lib.emu_mesh_destroy.argtypes = [C.c_void_p]
 lib.emu_mesh_distance.argtypes = [C.c_void_p, dp, C.c_uint64, C.c_int, dp, dp, i32p, i32p]
+lib.emu_sample_sdf.argtypes = [C.c_void_p, dp, u32p, C.c_double, C.c_uint64, C.c_uint64, dp]
+lib.emu_node_positions.argtypes = [dp, u32p, C.c_uint64, C.c_uint64, dp]
 rng = np.random.default_rng(seed)
 
 
@@ -78,6 +84,28 @@ for k in range(rounds):
     except Exception as ex:
         print("reference refused the mesh", ex); continue
     h = lib.emu_mesh_create(V.ctypes.data_as(dp), len(V), F.ctypes.data_as(u32p), len(F))
+    if mode == "grid":
+        from oracle_api import Oracle
+        lo, hi = V.min(0), V.max(0); ext = np.maximum(hi - lo, 1e-9)
+        if k % 7 in (0, 2, 3, 4):                                 # nodes on the half-integer lattice: ties by symmetry
+            mn = np.floor(lo) - 1.0; mx = mn + 4.0 * np.ceil((hi - mn + 1.0) / 4.0); res = tuple(int(r) for r in ((mx - mn) * 2))
+        else:
+            mn = lo - 0.3 * ext; mx = hi + 0.3 * ext; res = (9, 7, 6)
+        gd, r = Oracle().grid_desc(mn, mx, res)
+        nn = (res[0] + 1) * (res[1] + 1) * (res[2] + 1) + 2 * (res[0] * (res[1] + 1) * (res[2] + 1) + (res[0] + 1) * res[1] * (res[2] + 1) + (res[0] + 1) * (res[1] + 1) * res[2])
+        xs = np.empty((nn, 3)); lib.emu_node_positions(gd.ctypes.data_as(dp), r.ctypes.data_as(u32p), 0, nn, xs.ctypes.data_as(dp))
+        sign = 1.0 if k % 2 else -1.0
+        wd = ref.distance(xs, signed=True)[0]
+        want = wd if sign == 1.0 else sign * wd
+        got = np.full(nn, np.nan)
+        assert lib.emu_sample_sdf(h, gd.ctypes.data_as(dp), r.ctypes.data_as(u32p), sign, 0, nn, got.ctypes.data_as(dp)) == 0
+        ok = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+        total += nn
+        if not ok.all():
+            i = int(np.nonzero(~ok)[0][0]); bad += int((~ok).sum())
+            print(f"MISMATCH case {k} (kind {k % 7}, {len(F)} tris) grid {res} node {i} x={xs[i]!r}: {got[i]!r} vs {want[i]!r}")
+        lib.emu_mesh_destroy(h)
+        continue
     n = len(x)
     for signed in (1, 0):
         wd, wn, we, wt = ref.distance(x, signed=bool(signed))
