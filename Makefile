@@ -41,7 +41,7 @@ $(CPPBIN)/libk1emu.so: $(K1EMU_DEP)
 	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
 $(CPPBIN)/libk1emu_knobs.so: $(K1EMU_DEP)
 	@mkdir -p $(CPPBIN)
-	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DK1_VOTE_REDUX=0 -DK1_BRICK_AUTO=0 -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
+	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DK1_PACKET=0 -DK1_VOTE_REDUX=0 -DK1_BRICK_AUTO=0 -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
 # the wavefront node-loop kernel (K1_WAVE=1) and the per-lane one (K1_WAVE=0), whichever is not the default build, stay checked
 $(CPPBIN)/libk1emu_wave.so: $(K1EMU_DEP)
 	@mkdir -p $(CPPBIN)
@@ -51,7 +51,7 @@ $(CPPBIN)/libk1emu_packet.so: $(K1EMU_DEP)
 	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DK1_PACKET=1 -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
 $(CPPBIN)/libk1emu_perlane.so: $(K1EMU_DEP)
 	@mkdir -p $(CPPBIN)
-	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DK1_WAVE=0 -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
+	$(HOSTCXX) -std=c++17 -O2 -ffp-contract=off -fPIC -shared -DK1_WAVE=0 -DK1_PACKET=0 -I$(CUDA_INC) -Itests/emu -I$(SRC) $(K1EMU_SRC) -o $@ -lpthread
 K23EMU_SRC := tests/emu/k2_emu.cpp tests/emu/k3_emu.cpp
 K23EMU_DEP := $(K23EMU_SRC) tests/emu/cuda_emu.h $(SRC)/k2_interp.cu $(SRC)/k3_density.cu $(HDRS)
 $(CPPBIN)/libk23emu.so: $(K23EMU_DEP)

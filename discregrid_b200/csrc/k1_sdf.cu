@@ -27,6 +27,7 @@
 #include "k1_sdf.h"
 
 #include <cfloat>
+#include <cstdio>
 #include <mutex>
 #include <vector>
 #include <algorithm>
@@ -585,7 +586,7 @@ __device__ DG_NOINLINE bool ref_visits_first(const SpherePair* __restrict__ sphe
 }
 
 __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M, bool alive, double px, double py, double pz,
-                                                               unsigned* stack_rng, float* stack_pm, double* cv, int* cpos, float* cpm, int stride)
+                                                               unsigned* wstack, unsigned* stack_rng, float* stack_pm, float* stack_key, double* cv, int* cpos, int stride)
 {
     const unsigned FULL = 0xffffffffu;
     const int n_tri = M.n_tri;
@@ -603,6 +604,7 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
     float skip_lin = INF, skip_sq = INF, best_lo = INF;
     double dropped = DINF;                              // smallest evaluated value that is NOT in the list
     int cnt = 0;                                        // list: cv[0] <= cv[1] <= ... (stride apart), all within 1e-6 of the minimum when inserted
+    float pm_list = -INF;                               // max of the ancestor certificates (pm) of the entries inserted since the list last restarted
     float pm = -INF;                                    // max over the ancestors on the current path of (fp32 sphere distance + E)
     int b = 0, e = n_tri, depth = 0, sp = 0;            // warp-uniform
     bool have = true;
@@ -611,23 +613,13 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
             if (sp == 0) break;
             sp--;
             DG_EMU_COUNT(16);
-            const unsigned r = stack_rng[sp * stride];
-            const int rb = (int)(r & 0x01ffffffu), rd = (int)((r >> 25) & 31u);
-            const int re = rb + (n_tri >> rd) + (int)((r >> 30) & 1u);
-            const bool is_left = (r >> 31) != 0u;
-            const float4* f4 = M.nodes_f + (size_t)(is_left ? re : rb) * K1_NODEF_STRIDE;
-            const float4 s4 = __ldg(f4 + (is_left ? 0 : 1));
-            const float4 u = __ldg(f4 + (is_left ? 2 : 3)), v = __ldg(f4 + (is_left ? 3 : 4));
-            const float lox = is_left ? u.x : u.z, loy = is_left ? u.y : u.w, loz = is_left ? u.z : v.x;
-            const float hix = is_left ? u.w : v.y, hiy = is_left ? v.x : v.z, hiz = is_left ? v.y : v.w;
-            const float gx = fmaxf(fmaxf(lox - qx, qx - hix), 0.f), gy = fmaxf(fmaxf(loy - qy, qy - hiy), 0.f), gz = fmaxf(fmaxf(loz - qz, qz - hiz), 0.f);
-            const float box2 = __fmaf_rd(gz, gz, __fmaf_rd(gy, gy, __fmul_rd(gx, gx)));
-            const float sx = qx - s4.x, sy = qy - s4.y, sz = qz - s4.z;
-            const float df = sqrt_approx(fmaf(sz, sz, fmaf(sy, sy, sx * sx))) - s4.w;
-            const bool want = act && !(df - E > skip_lin) && !(box2 > skip_sq);
+            // the deferred child's certified lower bound was stored per lane when it was pushed; only the running best has moved since
+            const bool want = act && !(stack_key[sp * stride] > skip_lin);
             if (!__any_sync(FULL, want)) continue;
             DG_EMU_COUNT(17);
-            b = rb; e = re; depth = rd; pm = stack_pm[sp * stride];
+            const unsigned r = wstack[sp];                   // one copy per warp: every lane stored the same word
+            const int rb = (int)(r & 0x01ffffffu), rd = (int)((r >> 25) & 31u);
+            b = rb; e = rb + (n_tri >> rd) + (int)((r >> 30) & 1u); depth = rd; pm = stack_pm[sp * stride];
             have = true;
         }
         if (e - b == 1) {
@@ -646,13 +638,13 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
                     if (x < v0) {
                         if (!(v0 <= x + x * 1e-6)) {                    // clear improvement (or empty list): the list restarts
                             dropped = fmin(dropped, v0);
-                            cnt = 1; cv[0] = x; cpos[0] = b; cpm[0] = pm;
+                            cnt = 1; cv[0] = x; cpos[0] = b; pm_list = pm;
                         } else insert = true;
                         const double best = sqrt(x);
                         best_lo = __double2float_rd(best);
                         const float th = __fadd_ru(__double2float_ru(best), E2);
                         if (best_lo >= tiny_best) { skip_lin = th; skip_sq = __fmul_ru(th, th); }
-                        else { need_fb = true; act = false; }           // practically on the surface: no certified pruning possible
+                        else { need_fb = true; act = false; DG_EMU_COUNT(15); }           // practically on the surface: no certified pruning possible
                     } else if (x <= v0 + v0 * 1e-6) insert = true;
                     else dropped = fmin(dropped, x);                    // NaN falls through: never accepted by the reference either
                     if (insert) {
@@ -665,10 +657,10 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
                         } else cnt++;
                         if (room) {
                             while (i > 0 && x < cv[(i - 1) * stride]) {
-                                cv[i * stride] = cv[(i - 1) * stride]; cpos[i * stride] = cpos[(i - 1) * stride]; cpm[i * stride] = cpm[(i - 1) * stride];
+                                cv[i * stride] = cv[(i - 1) * stride]; cpos[i * stride] = cpos[(i - 1) * stride];
                                 i--;
                             }
-                            cv[i * stride] = x; cpos[i * stride] = b; cpm[i * stride] = pm;
+                            cv[i * stride] = x; cpos[i * stride] = b; pm_list = fmaxf(pm_list, pm);
                         }
                     }
                 }
@@ -682,6 +674,15 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
         const float4* f4 = M.nodes_f + (size_t)m * K1_NODEF_STRIDE;
         const float4 l4 = __ldg(f4), r4 = __ldg(f4 + 1);
         const float4 b0 = __ldg(f4 + 2), b1 = __ldg(f4 + 3), b2 = __ldg(f4 + 4);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
+#if K1_PKT_PREFETCH && !defined(DG_EMU)
+        // one of the two children is the next step of the whole warp: pull both records towards L1 while this node is being evaluated
+        {
+            const void* pl_ = (m - b == 1) ? (const void*)(M.leaves_f + b) : (const void*)(M.nodes_f + (size_t)((b + m) >> 1) * K1_NODEF_STRIDE);
+            const void* pr_ = (e - m == 1) ? (const void*)(M.leaves_f + m) : (const void*)(M.nodes_f + (size_t)((m + e) >> 1) * K1_NODEF_STRIDE);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pl_));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pr_));
+        }
+#endif
         const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
         const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
         const float dl = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) - l4.w;
@@ -701,8 +702,11 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
         const float d1u = __fadd_ru(left_first ? dl : dr, E), d2u = __fadd_ru(left_first ? dr : dl, E);
         if (m1) {
             if (m2) {
-                stack_rng[sp * stride] = left_first ? pack_range(m, e, depth, n_tri, false) : pack_range(b, m, depth, n_tri, true);
+                wstack[sp] = left_first ? pack_range(m, e, depth, n_tri, false) : pack_range(b, m, depth, n_tri, true);
                 stack_pm[sp * stride] = fmaxf(pm, d2u);
+                // lower bound of the true distance to anything in the deferred child: sphere (fp32 value - E) or box (sqrt.approx is within
+                // 2 ulp: scaled down by 1 - 2^-21 it is a lower bound of the root of the squared box distance, itself rounded down)
+                stack_key[sp * stride] = fmaxf((left_first ? dr : dl) - E, __fmul_rd(sqrt_approx(left_first ? r2 : l2), 0.99999952f));
                 sp++;
             }
             pm = fmaxf(pm, d1u);
@@ -723,7 +727,10 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
         double cmax = v0; int nC = 1;
         while (nC < cnt) { const double nx = cv[nC * stride]; if (nx <= cmax + cmax * EPSC) { cmax = nx; nC++; } else break; }
         bool good = (dropped > cmax + cmax * EPSC) && (cmax <= v0 + v0 * 1e-7);
-        for (int i = 0; i < nC; i++) good = good && (cpm[i * stride] < best_lo);
+        if (!(dropped > cmax + cmax * EPSC)) DG_EMU_COUNT(29);
+        if (!(cmax <= v0 + v0 * 1e-7)) DG_EMU_COUNT(30);
+        if (!(pm_list < best_lo)) DG_EMU_COUNT(31);
+        good = good && (pm_list < best_lo);             // (ii) for every entry of the list, hence for every member of C
         if (!good) { need_fb = true; ok = false; }
         else if (nC == 1) { win = cpos[0]; D = sqrt(v0); }
         else {
@@ -784,6 +791,11 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
             res.dist = D; res.s = s; res.t = t; res.pos = win; res.entity = ent;
         }
     }
+#if K1_PKT_DEBUG && !defined(DG_EMU)
+    if (need_fb && (blockIdx.x % 1499u) == 0u)
+        printf("PKTFB blk %u lane %u cnt %d v0 %.17g dropped %.17g best_lo %.9g pm0 %.9g tiny %.9g Mq %.9g act %d\n", blockIdx.x, threadIdx.x & 31u, cnt,
+               cnt ? cv[0] : -1.0, dropped, (double)best_lo, (double)pm_list, (double)tiny_best, (double)Mq, (int)act);
+#endif
     if (__any_sync(FULL, need_fb)) {                    // the lanes the checks could not clear: the per-lane reference-order walk
         DG_EMU_COUNT(24);
         DG_EMU_ADD(25, need_fb ? 1 : 0);
@@ -805,7 +817,7 @@ extern __shared__ __align__(16) unsigned char k1_smem[];
 // owns a 4 x 4 x 2 brick (fast x mid x slow) of one of them and a 128-thread block four bricks side by side along the
 // fast axis, so the 32 queries of a warp are spatial neighbours: they visit nearly the same tree nodes (L1 hits) and
 // take similar numbers of steps.  Whole slow-planes are covered; nodes outside [l_begin, l_end) are masked.
-__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
+__global__ void __launch_bounds__(K1_THREADS, K1_PACKET ? K1_PKT_MIN_BLOCKS : K1_MIN_BLOCKS)
 sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals, int stack_depth, GridDev g, K1Work w, double sign,
                         double* __restrict__ out)
 {
@@ -862,9 +874,12 @@ sdf_sample_nodes_kernel(MeshDev mesh, const PseudoNormals* __restrict__ normals,
 #if K1_PACKET
     double* cand_v = reinterpret_cast<double*>(k1_smem + (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned)));
     int* cand_pos = reinterpret_cast<int*>(cand_v + (size_t)K1_PKT_K * K1_THREADS);
-    float* cand_pm = reinterpret_cast<float*>(cand_pos + (size_t)K1_PKT_K * K1_THREADS);
-    const QueryResult r = nearest_triangle_packet(mesh, alive, px, py, pz, stack_rng + threadIdx.x, stack_d + threadIdx.x,
-                                                  cand_v + threadIdx.x, cand_pos + threadIdx.x, cand_pm + threadIdx.x, K1_THREADS);
+    // shared memory: [stack_d | stack_rng] as the per-lane walk (the fallback) needs them; the packet walk keeps its per-lane certificate in the
+    // first and the deferred children's lower bounds in the second, its own (warp-uniform) range stack once per warp behind the candidates
+    unsigned* wstack = reinterpret_cast<unsigned*>(cand_pos + (size_t)K1_PKT_K * K1_THREADS) + (size_t)(threadIdx.x >> 5) * stack_depth;
+    const QueryResult r = nearest_triangle_packet(mesh, alive, px, py, pz, wstack, stack_rng + threadIdx.x, stack_d + threadIdx.x,
+                                                  reinterpret_cast<float*>(stack_rng) + threadIdx.x,
+                                                  cand_v + threadIdx.x, cand_pos + threadIdx.x, K1_THREADS);
 #else
     const QueryResult r = nearest_triangle(mesh, alive, px, py, pz, stack_rng + threadIdx.x, stack_d + threadIdx.x, K1_THREADS);
 #endif
@@ -1278,7 +1293,8 @@ static inline size_t k1_smem_bytes(int stack_depth)
 {
     size_t n = (size_t)stack_depth * K1_THREADS * (sizeof(float) + sizeof(unsigned));
 #if K1_PACKET
-    n += (size_t)K1_PKT_K * K1_THREADS * (sizeof(double) + sizeof(int) + sizeof(float));       // candidate lists of the packet walk
+    n += (size_t)K1_PKT_K * K1_THREADS * (sizeof(double) + sizeof(int));                        // candidate lists of the packet walk
+    n += (size_t)(K1_THREADS / 32) * stack_depth * sizeof(unsigned);                            // the warp-uniform range stack
 #endif
     return n;
 }

@@ -75,11 +75,23 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 #define K1_MIN_BLOCKS (1024 / K1_THREADS_PER_BLOCK)   // blocks per SM the register allocation must allow (32 warps)
 #endif
 
-// K1_PACKET 1: the 32 queries of a brick walk the tree together (one shared order, certified fp32 pruning) and the reference's
-// order-dependent accept rule is replayed on the few near-minimum triangles afterwards; lanes whose checks fail are walked again per lane
-// (k1_sdf.cu, nearest_triangle_packet).  K1_PKT_K = near-minimum candidates kept per query.
+// K1_PACKET 1 (default since round 2, profiles/r2s - r2v): the 32 queries of a brick walk the tree TOGETHER (one shared order, certified fp32
+// pruning) and the reference's order-dependent accept rule is replayed afterwards on the few near-minimum triangles; lanes whose checks fail
+// are walked again per lane (k1_sdf.cu, nearest_triangle_packet).  0: one query per lane in the reference's own order for the whole walk
+// (the round-1 kernel; still what mesh_distance_kernel -- arbitrary points, no bricks -- and the fallback run).
+//   K1_PKT_K          near-minimum candidates kept per query (8: K = 6 falls back on bunny.obj's valence-7/8 vertices, 50.3 vs 37.3 ms)
+//   K1_PKT_MIN_BLOCKS blocks per SM the register allocation of the node-loop kernel must allow
 #ifndef K1_PACKET
-#define K1_PACKET 0
+#define K1_PACKET 1
+#endif
+#ifndef K1_PKT_MIN_BLOCKS
+#define K1_PKT_MIN_BLOCKS 14
+#endif
+#ifndef K1_PKT_PREFETCH
+#define K1_PKT_PREFETCH 0
+#endif
+#ifndef K1_PKT_DEBUG
+#define K1_PKT_DEBUG 0
 #endif
 #define K1_NEEDS_LEAF_SHADOW (K1_LEAF_FILTER || K1_PACKET)     // the fp32 triangle shadows (LeafF) are built and uploaded
 // K1_WAVE 1: the node-loop kernel is the WAVEFRONT variant (k1_sdf.cu): persistent warps, a pool of K1_WAVE_SLOTS query slots per warp in
