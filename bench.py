@@ -894,13 +894,16 @@ def main():
 # ncu-derived constants of the shipped kernels AT THE BENCH CONFIGURATIONS (profiles/: `ncu --set full --clock-control none`; numbers taken
 # under ncu are never bench values -- these are per-launch DRAM bytes and pipe statistics only)
 NCU = {
-    "k1_mesh": "bunny", "k1_dram_bytes_per_launch": 39.58e6 + 79.56e6,
-    "k1_source": "profiles/r2a_ncu_summary.csv: ncu --set full of sdf_sample_nodes_kernel at this configuration (bunny.obj, 128^3): dram read 39.6 MB (mesh records once) "
-                 "+ write 79.6 MB (8 B/node; the rest of the 119 MB drains after the launch)",
-    "k1_summary": {"capture": "profiles/r2a_ncu_summary.csv (bunny.obj 128^3, 76.9 ms under ncu)", "lanes_active_per_instruction": 15.44, "issue_active_pct": 67.5,
-                   "fp64_pipe_pct": 15.7, "alu_pipe_pct": 45.7, "l1_lsu_wavefronts_pct_of_peak": 67.2, "warps_active_pct": 43.6, "l1_hit_pct": 74.3, "l2_hit_pct": 98.1,
-                   "top_stalls": "long scoreboard 31 %, fixed-latency wait 25 %, branch resolving 10 %",
-                   "reading": "bound jointly by instruction issue (67 %) and L1 data-pipe wavefronts (67 %) at 15.4 of 32 lanes; neither HBM (0.02 %) nor the fp64 pipe (16 %)"},
+    "k1_mesh": "bunny", "k1_dram_bytes_per_launch": 48.75e6 + 83.26e6,
+    "k1_source": "profiles/r2w_ncu_summary.csv: ncu --set full of the shipped sdf_sample_nodes_kernel (packet walk) at this configuration (bunny.obj, 128^3): dram read 48.8 MB "
+                 "(mesh records) + write 83.3 MB (8 B/node; the rest of the 119 MB drains after the launch)",
+    "k1_summary": {"capture": "profiles/r2w_ncu_summary.csv (bunny.obj 128^3, 34.1 ms under ncu; the per-lane kernel of round 1: r2a, 76.9 ms)",
+                   "warp_instructions": 29.5e9, "warp_instructions_per_lane_kernel": 60.4e9, "lanes_active_per_instruction": 28.6, "issue_active_pct": 74.9,
+                   "fp64_pipe_pct": 7.2, "alu_pipe_pct": 44.1, "warps_active_pct": 37.6, "registers": 72, "shared_kb_per_block": 15.0, "l1_hit_pct": 56.2, "l2_hit_pct": 94.4,
+                   "instruction_shares": "(r2v capture, same walk) node step 43 %, certified fp32 triangle bound 23 %, exact fp64 triangle test 7.5 %, deferred-child re-test 7 %, "
+                                         "candidate list 6 %, index arithmetic + sign 8 %, reference-order replay 3 %, per-lane fallback 0.1 %",
+                   "reading": "instruction-issue bound (75 % of the issue slots busy, 28.6 of 32 lanes) with half the instructions of the per-lane kernel; neither HBM (0.03 %), "
+                              "the fp64 pipe (7 %) nor the L1 data pipe (41 %)"},
     "k1_flops_per_node_fallback": 15800.0,
     "k2_dram_bytes_per_launch": 2757.4e6 + 312.9e6,
     "k2_source": "profiles/r2a_ncu_summary.csv: ncu --set full of interpolate_kernel<true>, 10 M queries on the 256^3 field: dram read 2.757 GB + write 0.313 GB = 3.07 GB "

@@ -231,6 +231,12 @@ bool build_host_bvh(const double* Vd, uint64_t nV, const uint32_t* F, uint64_t n
         for (uint64_t i = 0; i < nV; i++) for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], Vd[3 * i + d]); hi[d] = std::max(hi[d], Vd[3 * i + d]); }
         out.half_extent = 0;
         for (int d = 0; d < 3; d++) { out.center[d] = 0.5 * (lo[d] + hi[d]); out.half_extent = std::max(out.half_extent, std::max(hi[d] - out.center[d], out.center[d] - lo[d])); }
+        // a NaN coordinate slips through min / max: with any non-finite vertex the fp32 shadows mean nothing.  half_extent = +inf switches every
+        // fp32 filter of K1 off (E = inf: all decisions in fp64, exactly the reference's, NaN comparisons included) and sends the packet walk's
+        // lanes to the per-lane walk.
+        bool finite = true;
+        for (uint64_t i = 0; i < 3 * nV && finite; i++) finite = std::isfinite(Vd[i]);
+        if (!finite || !std::isfinite(out.half_extent)) { out.half_extent = INFINITY; for (int d = 0; d < 3; d++) if (!std::isfinite(out.center[d])) out.center[d] = 0.0; }
         out.spheres_f.resize(nT);
         out.boxes_f.resize(nT);
         // child boxes are rounded outward so that the fp32 box contains the fp64 one

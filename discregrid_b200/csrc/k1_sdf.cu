@@ -1,16 +1,19 @@
-// K1: nearest-triangle query + pseudonormal sign, one query per lane, exact reference traversal order.
+// K1: nearest-triangle query + pseudonormal sign on the reference's own tree, bit-identical to the reference.
 //
 // Replaces TriangleMeshDistance::signed_distance / unsigned_distance / _query / point_triangle_sq_unsigned
 // (TriangleMeshDistance.h:269-328, 514-562, 564-820) and, fused in front of it, indexToNodePosition
 // (cubic_lagrange_discrete_grid.cpp:604-665) for the addFunction node loop (:806-817).
 //
-// Why per-lane depth-first order and not a warp-shared traversal: _query keeps the FIRST strictly smaller
-// triangle in nearer-child-first order and prunes with the running best (TriangleMeshDistance.h:528, 542-560),
-// so both the winner among equidistant triangles (hence the sign) and, through floating-point cancellation in
-// d2, the last bits of the distance depend on each query's own visit order.  Bit-exact parity therefore needs
-// each lane to walk its own order.  What the warp shares instead is the code path (one loop, leaf tests
-// batched behind a ballot) and the caches: the 32 lanes of a warp are 32 adjacent grid nodes, so they fetch
-// mostly the same 64-byte sphere pairs and 128-byte triangle records.
+// What makes this more than a nearest-neighbour search: _query keeps the FIRST strictly smaller triangle in nearer-child-first
+// order, compares d2 against fl(sqrt(best))^2 (:528) and prunes with the running best (:542-560), so the winner among triangles
+// whose d2 differ by a few ulps (hence the nearest point, the entity, the sign and occasionally the last bit of the distance)
+// depends on each query's own visit order.  Two walks live here:
+//   * nearest_triangle        -- one query per lane, every lane in the reference's own order with its own stack; the warp shares the
+//                                code path (one loop, phases chosen by vote) and the caches.  Round 1's node loop; now the kernel for
+//                                arbitrary points, the fallback of the packet walk and the -DK1_PACKET=0 build.
+//   * nearest_triangle_packet -- the 32 queries of a brick walk the tree together (certified fp32 pruning only), keep the few
+//                                near-minimum triangles, and the reference's choice among them is replayed exactly afterwards; a lane
+//                                whose checks fail is handed to nearest_triangle.  The node loop since round 2 (2x fewer instructions).
 //
 // Data (see bvh_build.h): implicit tree over leaf ranges [b,e); per internal node one 80-byte fp32 record (child spheres +
 // child boxes, relative to the mesh centre) that DECIDES, the 64-byte fp64 sphere pair at spheres[(b+e)>>1] for the rare
@@ -18,9 +21,9 @@
 // per-lane stack of deferred siblings (packed range + fp32 sphere distance, 8 bytes) lives in shared memory, laid out
 // [depth][lane] so it is bank-conflict-free whatever depth each lane is at.
 //
-// Structure of this file: tri_dist2 (leaf test) -> finish_query (nearest point + sign) -> [leaf_lower_bound: optional fp32
-// leaf filter, compiled out] -> nearest_triangle (the warp-synchronous traversal: NODE / LEAF / POP phases, fp32 interval
-// filter, exact-preserving shortcuts) -> the two kernels (grid nodes in 4x4x2 bricks; arbitrary points) -> launchers.
+// Structure of this file: tri_dist2 (leaf test) -> finish_query (nearest point + sign) -> leaf_lower_bound (certified fp32
+// triangle bound) -> nearest_triangle (the warp-synchronous per-lane traversal: NODE / LEAF / POP phases, fp32 interval
+// filter, exact-preserving shortcuts) -> nearest_triangle_packet -> the two kernels (grid nodes in bricks of 32; arbitrary points) -> launchers.
 // Tuning knobs and the measured variants are listed in k1_sdf.h / profiles/README.md.
 #include "dg_device.cuh"
 #include "bvh_build.h"
@@ -552,8 +555,8 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
 //        here in fp64 exactly as the reference does (ref_visits_first).
 // So the packet walk only has to (a) evaluate, with the reference's own fp64 leaf test, every triangle whose v could be <= m (1 + 1e-6)
 // -- subtrees and leaves are dropped only by the CERTIFIED fp32 bounds of the box skip (true distance > best_hi + 2E  =>  v > m (1 + 2e-6),
-// error budget at K1_BOX_SKIP above) -- (b) keep the K1_PKT_K smallest values near the minimum with their leaf position and ancestor
-// certificate, plus the smallest value it did not keep, (c) form C, check (i) and (ii), order C by (iii) and replay the reference's
+// error budget at K1_BOX_SKIP above) -- (b) keep the K1_PKT_K smallest values near the minimum with their leaf position, the largest ancestor
+// certificate of any of them, and the smallest value it did not keep, (c) form C, check (i) and (ii), order C by (iii) and replay the reference's
 // accept rule.  A lane for which any check fails (on-surface queries below tiny_best, more than K1_PKT_K near-ties, a sphere that is tight
 // to within E, non-finite input) is walked again by nearest_triangle() -- the per-lane reference-order traversal above -- so the result is
 // the reference's in every case; the checks decide only how fast it is obtained.

@@ -209,6 +209,27 @@ def test_tie_rich_grid_fuzz_node_loop_against_reference_header(name):
     assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_node_loop_on_a_mesh_with_non_finite_vertices(emu, orc):
+    """NaN / inf vertices: the reference's sphere tests then compare false and whole subtrees go unvisited -- nothing an order-free search may
+    assume.  The host builder marks such a mesh (half_extent = +inf), every fp32 filter switches off and the packet walk hands all its lanes to
+    the per-lane walk: node loop == reference header bit for bit"""
+    from oracle_api import RefMesh, have_ref
+    if not have_ref():
+        pytest.skip("needs oracle/_ref/libdgref.so")
+    V = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [np.nan, 2, 2], [3, 3, np.inf], [2, 2, 2]], float)
+    F = np.array([[0, 2, 4], [2, 1, 4], [1, 3, 4], [3, 0, 4], [2, 0, 5], [1, 2, 5], [3, 1, 5], [0, 3, 5], [6, 0, 2], [7, 8, 4]], np.uint32)
+    ref = RefMesh(V, F)
+    gd, r = orc.grid_desc(np.array([-2.0, -2, -2]), np.array([2.0, 2, 2]), (8, 8, 8))
+    nn = orc.num_nodes(r)
+    xs = np.empty((nn, 3))
+    emu.lib.emu_node_positions(_p(gd, _dp), _p(r, _u32p), 0, nn, _p(xs, _dp))
+    h = emu.mesh(V, F)
+    got = emu.sample(h, gd, r, 0, nn)
+    want = ref.distance(xs, signed=True)[0]
+    assert bits_equal(got, want)
+    emu.lib.emu_mesh_destroy(h)
+
+
 def test_emulated_launch_order(emu, orc):
     """the per-lane sampling kernel takes its blocks in launch order, every block exactly once (the wavefront kernel hands out bricks
     through a counter instead and has no block order)"""
