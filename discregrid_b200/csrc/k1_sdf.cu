@@ -30,7 +30,6 @@
 #include "k1_sdf.h"
 
 #include <cfloat>
-#include <cstdio>
 #include <mutex>
 #include <vector>
 #include <algorithm>
@@ -564,13 +563,13 @@ __device__ __forceinline__ QueryResult nearest_triangle(const MeshDev& M, bool a
 #ifndef K1_PKT_K
 #define K1_PKT_K 8
 #endif
-
-// does the reference reach leaf position pa before leaf position pb (pa != pb, both visited)?
 #ifdef DG_EMU
 #define DG_NOINLINE
 #else
 #define DG_NOINLINE __noinline__
 #endif
+
+// does the reference reach leaf position pa before leaf position pb (pa != pb, both visited)?
 __device__ DG_NOINLINE bool ref_visits_first(const SpherePair* __restrict__ spheres, int n_tri, int pa, int pb, double px, double py, double pz)
 {
     int b = 0, e = n_tri;
@@ -677,15 +676,7 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
         const float4* f4 = M.nodes_f + (size_t)m * K1_NODEF_STRIDE;
         const float4 l4 = __ldg(f4), r4 = __ldg(f4 + 1);
         const float4 b0 = __ldg(f4 + 2), b1 = __ldg(f4 + 3), b2 = __ldg(f4 + 4);   // l_lo.xyz l_hi.x | l_hi.yz r_lo.xy | r_lo.z r_hi.xyz
-#if K1_PKT_PREFETCH && !defined(DG_EMU)
-        // one of the two children is the next step of the whole warp: pull both records towards L1 while this node is being evaluated
-        {
-            const void* pl_ = (m - b == 1) ? (const void*)(M.leaves_f + b) : (const void*)(M.nodes_f + (size_t)((b + m) >> 1) * K1_NODEF_STRIDE);
-            const void* pr_ = (e - m == 1) ? (const void*)(M.leaves_f + m) : (const void*)(M.nodes_f + (size_t)((m + e) >> 1) * K1_NODEF_STRIDE);
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pl_));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pr_));
-        }
-#endif
+        // (prefetching both children's records here -- one of them is the warp's next step -- was measured 4 % slower: profiles/r2v)
         const float lx = qx - l4.x, ly = qy - l4.y, lz = qz - l4.z;
         const float rx = qx - r4.x, ry = qy - r4.y, rz = qz - r4.z;
         const float dl = sqrt_approx(fmaf(lz, lz, fmaf(ly, ly, lx * lx))) - l4.w;
@@ -794,11 +785,6 @@ __device__ __forceinline__ QueryResult nearest_triangle_packet(const MeshDev& M,
             res.dist = D; res.s = s; res.t = t; res.pos = win; res.entity = ent;
         }
     }
-#if K1_PKT_DEBUG && !defined(DG_EMU)
-    if (need_fb && (blockIdx.x % 1499u) == 0u)
-        printf("PKTFB blk %u lane %u cnt %d v0 %.17g dropped %.17g best_lo %.9g pm0 %.9g tiny %.9g Mq %.9g act %d\n", blockIdx.x, threadIdx.x & 31u, cnt,
-               cnt ? cv[0] : -1.0, dropped, (double)best_lo, (double)pm_list, (double)tiny_best, (double)Mq, (int)act);
-#endif
     if (__any_sync(FULL, need_fb)) {                    // the lanes the checks could not clear: the per-lane reference-order walk
         DG_EMU_COUNT(24);
         DG_EMU_ADD(25, need_fb ? 1 : 0);

@@ -87,12 +87,6 @@ static_assert(K1_BRICK_F * K1_BRICK_M * K1_BRICK_S == 32, "a brick is one warp")
 #ifndef K1_PKT_MIN_BLOCKS
 #define K1_PKT_MIN_BLOCKS 14
 #endif
-#ifndef K1_PKT_PREFETCH
-#define K1_PKT_PREFETCH 0
-#endif
-#ifndef K1_PKT_DEBUG
-#define K1_PKT_DEBUG 0
-#endif
 #define K1_NEEDS_LEAF_SHADOW (K1_LEAF_FILTER || K1_PACKET)     // the fp32 triangle shadows (LeafF) are built and uploaded
 // K1_WAVE 1: the node-loop kernel is the WAVEFRONT variant (k1_sdf.cu): persistent warps, a pool of K1_WAVE_SLOTS query slots per warp in
 // shared memory, per iteration the fullest phase is compacted onto the lanes by ballot.  0: the per-lane kernel (one query per lane).
