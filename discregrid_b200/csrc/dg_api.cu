@@ -562,19 +562,6 @@ static int sample_sdf_host_locked(const dg_mesh* m, const GridDev& g, double sig
     return DG_OK;
 }
 
-int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* out_host)
-{
-    if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf: mesh is NULL (not constructed)");
-    GridDev g;
-    if (int rc = check_range(grid, l_begin, l_end, g, "dg_sample_sdf")) return rc;
-    const uint64_t n = l_end - l_begin;
-    if (n == 0) return DG_OK;
-    if (!out_host) return fail(DG_ERR_INVALID, "dg_sample_sdf: output is NULL");
-    if (int rc = check_handle_device(m->device, "dg_sample_sdf")) return rc;
-    std::lock_guard<std::mutex> lock(g_pool.mu);
-    return sample_sdf_host_locked(m, g, sign, l_begin, n, out_host);
-}
-
 // Makes the pages of [p, p + bytes) present and writable WITHOUT changing their content (safe against a concurrent writer).
 static void prefault_preserving(char* p, uint64_t bytes)
 {
@@ -719,6 +706,38 @@ struct HostTablesJob {
 }  // namespace
 
 static void tables_job_copy(HostTablesJob* job, void* dst, const void* src, size_t bytes) { job->copy(dst, src, bytes); }
+
+int dg_sample_sdf(const dg_mesh* m, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* out_host)
+{
+    if (!m) return fail(DG_ERR_INVALID, "dg_sample_sdf: mesh is NULL (not constructed)");
+    GridDev g;
+    if (int rc = check_range(grid, l_begin, l_end, g, "dg_sample_sdf")) return rc;
+    const uint64_t n = l_end - l_begin;
+    if (n == 0) return DG_OK;
+    if (!out_host) return fail(DG_ERR_INVALID, "dg_sample_sdf: output is NULL");
+    if (int rc = check_handle_device(m->device, "dg_sample_sdf")) return rc;
+    // A large range into pageable memory: one thread copying staging buffer -> caller memory (2 - 4 GB/s into pages it has to fault in itself)
+    // is slower than the packet walk produces coefficients (5.5 GB/s at 256^3), so a few workers pre-fault the range and share the copies,
+    // exactly as in dg_add_function_sdf (profiles/r2x: per-rank e2e 26.1 ms for 17.8 ms of kernel before this).
+    static const uint64_t helpers_min_bytes = []() -> uint64_t {
+        const char* e = std::getenv("DG_HOST_HELPERS_MIN_BYTES");
+        return (e && *e) ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(32u << 20);
+    }();
+    if (n * sizeof(double) >= helpers_min_bytes) {
+        HostTablesJob job;
+        job.start(g, n, out_host, nullptr, nullptr);
+        int rc;
+        {
+            std::lock_guard<std::mutex> lock(g_pool.mu);
+            rc = sample_sdf_host_locked(m, g, sign, l_begin, n, out_host, &job);
+        }
+        job.finish();
+        return rc;
+    }
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    return sample_sdf_host_locked(m, g, sign, l_begin, n, out_host);
+}
+
 
 // The whole of CubicLagrangeDiscreteGrid::addFunction(GenerateSDF functor) into the caller's three arrays
 // (cubic_lagrange_discrete_grid.cpp:780-899): node loop on the GPU (K1 chunks on two streams, D2H through the pinned double

@@ -21,7 +21,8 @@ SKIP = "not large_grid and not host_pipeline and not device_form and not full_si
 def test_gpu_suite_passes_on_the_emulated_library():
     if not os.path.exists(EMU):
         pytest.skip("build/bin/libdgemu.so not built (make cpp)")
-    env = dict(os.environ, DISCREGRID_B200_LIB=EMU, LD_PRELOAD=EMU, DG_ALLOW_EMULATED_LIBRARY="1")
+    # DG_HOST_HELPERS_MIN_BYTES: dg_sample_sdf hands ranges of >= 32 MiB to pre-fault / copy workers; lowered so that the toy ranges take that path too
+    env = dict(os.environ, DISCREGRID_B200_LIB=EMU, LD_PRELOAD=EMU, DG_ALLOW_EMULATED_LIBRARY="1", DG_HOST_HELPERS_MIN_BYTES="4096")
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-k", SKIP, "-p", "no:cacheprovider"] + FILES,
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
