@@ -46,7 +46,7 @@ static double tri_d2(const LeafRecord& L, P3 p)
 }
 
 
-struct PCounts { long long nodes = 0, filters = 0, exacts = 0, exact_lanes = 0, pops = 0, pops_hit = 0, bricks = 0, queries = 0, maxstack = 0; };
+struct PCounts { long long nodes_even = 0, nodes_odd = 0, nodes = 0, filters = 0, exacts = 0, exact_lanes = 0, pops = 0, pops_hit = 0, bricks = 0, queries = 0, maxstack = 0; };
 
 struct Packet {
     const HostBvh& H; int T;
@@ -68,12 +68,12 @@ struct Packet {
         const double s = which ? sph(S.rc, S.rr, p) : sph(S.lc, S.lr, p);
         return std::max(s, boxd(m, which, p));
     }
-    struct Item { int b, e, m, which; };
+    struct Item { int b, e, m, which, depth; };
     void brick(const P3* p, int n, double* best, PCounts& c, double slack, int order_mode) const
     {
         for (int i = 0; i < n; i++) best[i] = DBL_MAX;
         std::vector<Item> st; st.reserve(128);
-        int b = 0, e = T; bool have = true;
+        int b = 0, e = T, depth = 0; bool have = true;
         for (;;) {
             if (!have) {
                 bool found = false;
@@ -82,7 +82,7 @@ struct Packet {
                     bool any = false;
                     for (int i = 0; i < n && !any; i++) any = lb(it.m, it.which, p[i]) < best[i] * slack;
                     if (!any) continue;
-                    c.pops_hit++; b = it.b; e = it.e; found = true; break;
+                    c.pops_hit++; b = it.b; e = it.e; depth = it.depth; found = true; break;
                 }
                 if (!found) break;
             }
@@ -95,7 +95,7 @@ struct Packet {
                 if (pass) { c.exacts++; c.exact_lanes += pass; for (int i = 0; i < n; i++) if (d2[i] < best[i] * best[i]) best[i] = std::sqrt(d2[i]); }
                 continue;
             }
-            c.nodes++;
+            c.nodes++; if (depth & 1) c.nodes_odd++; else c.nodes_even++;
             const int m = (b + e) >> 1;
             int wantL = 0, wantR = 0, prefL = 0, prefR = 0; double sumL = 0, sumR = 0;
             for (int i = 0; i < n; i++) {
@@ -109,9 +109,9 @@ struct Packet {
             const int fb = leftFirst ? b : m, fe = leftFirst ? m : e, sb = leftFirst ? m : b, se = leftFirst ? e : m;
             const int w1 = leftFirst ? wantL : wantR, w2 = leftFirst ? wantR : wantL;
             if (w1) {
-                if (w2) { st.push_back({sb, se, m, leftFirst ? 1 : 0}); c.maxstack = std::max<long long>(c.maxstack, (long long)st.size()); }
-                b = fb; e = fe; have = true;
-            } else if (w2) { b = sb; e = se; have = true; }
+                if (w2) { st.push_back({sb, se, m, leftFirst ? 1 : 0, depth + 1}); c.maxstack = std::max<long long>(c.maxstack, (long long)st.size()); }
+                b = fb; e = fe; depth++; have = true;
+            } else if (w2) { b = sb; e = se; depth++; have = true; }
         }
     }
 };
@@ -161,13 +161,14 @@ int main(int argc, char** argv)
                     }
 #pragma omp critical
             {
-                tot.nodes += c.nodes; tot.filters += c.filters; tot.exacts += c.exacts; tot.exact_lanes += c.exact_lanes; tot.pops += c.pops; tot.pops_hit += c.pops_hit;
+                tot.nodes += c.nodes; tot.nodes_even += c.nodes_even; tot.nodes_odd += c.nodes_odd; tot.filters += c.filters; tot.exacts += c.exacts; tot.exact_lanes += c.exact_lanes; tot.pops += c.pops; tot.pops_hit += c.pops_hit;
                 tot.bricks += c.bricks; tot.queries += c.queries; tot.maxstack = std::max(tot.maxstack, c.maxstack);
             }
         }
         const double B = (double)tot.bricks;
         printf("order %s: per brick: node steps %.1f  leaf filter steps %.1f  exact blocks %.1f (%.1f lanes each)  pops %.1f (%.1f hit)  max stack %lld\n",
                mode == 0 ? "majority" : "mean-lb", tot.nodes / B, tot.filters / B, tot.exacts / B, tot.exact_lanes / (double)std::max(1LL, tot.exacts), tot.pops / B, tot.pops_hit / B, tot.maxstack);
+        printf("   node steps at even / odd depth: %.1f / %.1f per brick (a 4-wide node = an even-depth node with its two children inlined: %.1f steps instead of %.1f)\n", tot.nodes_even / B, tot.nodes_odd / B, tot.nodes_even / B, tot.nodes / B);
         const double instr = tot.nodes / B * 60 + tot.filters / B * 90 + tot.exacts / B * 270 + tot.pops / B * 40;
         printf("   modelled warp instructions per brick %.0f = %.0f per query (node 60, filter 90, exact 270, pop 40)\n", instr, instr * B / tot.queries);
     }
