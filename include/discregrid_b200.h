@@ -137,8 +137,10 @@ DG_API int dg_mesh_distance_device(const dg_mesh* mesh, const double* d_points, 
  * indexToNodePosition = cubic_lagrange_discrete_grid.cpp:604-665.  Node ids are the reference's (uint32 in
  * the file format); 64-bit here only so ranges can be expressed without overflow.
  * A sub-range is what a rank computes when the grid is sharded across GPUs.
- * The host form overlaps kernel chunks, D2H DMA (pooled pinned double buffer) and the copy into `out_host`; calls are serialised per
- * process.  The _device form is asynchronous on `stream` and may be issued concurrently on several streams. */
+ * The host form overlaps kernel chunks, D2H DMA (pooled pinned double buffer) and the copy into `out_host`; for ranges of 32 MiB and more
+ * (environment: DG_HOST_HELPERS_MIN_BYTES) a few worker threads (a quarter of the usable CPUs, DG_HOST_THREADS) pre-fault `out_host` and
+ * share that copy, as in dg_add_function_sdf; calls are serialised per process.  The _device form is asynchronous on `stream` and may be
+ * issued concurrently on several streams. */
 DG_API int dg_sample_sdf(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end, double* out_host);
 DG_API int dg_sample_sdf_device(const dg_mesh* mesh, const dg_grid_desc* grid, double sign, uint64_t l_begin, uint64_t l_end,
                          double* d_out, void* stream);
